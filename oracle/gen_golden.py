@@ -1,0 +1,161 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference functions (container only).
+
+    python -m oracle.gen_golden            # rewrites tests/golden/
+
+The reference ships no tests/golden vectors, so these fixtures — inputs and the
+outputs the reference itself produced on CPU (torch 2.11, fp32 unless the reference casts to fp64)
+— are the pin for both the oracle (`oracle/restate.py`) and the CUDA path.  Everything is seeded;
+inputs are stored next to outputs so the fixtures stay valid if a torch release changes `randn`.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle.reference_loader import load_reference  # noqa: E402
+from oracle.restate import synth_features, synth_labels  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (_np(v) if torch.is_tensor(v) else np.asarray(v)) for k, v in arrays.items()})
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def gen_adain(net):
+    base = sys.modules["network.base"]
+    cases = {}
+    for tag, shape, signed in [("odd", (2, 5, 7, 9), False), ("sq", (1, 8, 16, 16), False),
+                               ("signed", (3, 4, 12, 10), True), ("hw2", (2, 3, 1, 2), True)]:
+        c, s = synth_features(shape, cfg=len(cases), signed=signed)
+        g = torch.Generator().manual_seed(77 + len(cases))
+        prev = torch.randn(shape, generator=g)
+        mean, std = base.calc_mean_std(c)
+        out = base.adaptive_instance_normalization(c, s)
+        cases[tag] = True
+        _save(f"adain_{tag}", content=c, style=s, prev=prev, mean=mean, std=std, out=out,
+              blend=prev + out, mvn=sys.modules["network.sanet"].mean_variance_norm(c))
+
+
+def gen_seg(net):
+    base = sys.modules["network.base"]
+    c, s = synth_features((1, 6, 24, 20), cfg=11)
+    s = torch.relu(torch.randn((1, 6, 18, 30), generator=torch.Generator().manual_seed(3011)) * 2 + 1)
+    cl = synth_labels(1, 24, 20, classes=5, block=6, seed=4000)[0]
+    sl = synth_labels(1, 18, 30, classes=5, block=6, seed=5000)[0]
+    # adversarial labels (network/base.py:435): label 7 absent in style, label 8 has <=10 content
+    # pixels, label 9 has a count ratio >= 100 (handled via a tiny style region)
+    cl[0:3, 0:4] = 7
+    cl[10:12, 0:4] = 8           # 8 pixels -> invalid
+    sl[0:2, 0:6] = 8
+    cl[12:24, 10:20] = 9         # 120 px content
+    sl[17, 29] = 9               # 1 px style -> cnt_s<=10 -> invalid
+    saved = base.get_segment_and_info
+    base.get_segment_and_info = lambda cp, sp, csh, ssh: (
+        cl.numpy(), sl.numpy(), *base.compute_label_info(cl.numpy(), sl.numpy()))
+    try:
+        out = base.adaptive_instance_normalization_with_segment(c, s, None, None)
+    finally:
+        base.get_segment_and_info = saved
+    _save("seg_adain", content=c, style=s, c_labels=cl, s_labels=sl, out=out)
+
+
+def gen_wct(net):
+    wct = sys.modules["network.wct_rp"]
+    g = torch.Generator().manual_seed(21)
+    a = torch.randn(16, 40, generator=g, dtype=torch.float64)
+    spd = a @ a.t() / 39
+    _save("wct_matfn", a=spd, sqrt=wct.matrix_sqrt(spd), inv_sqrt=wct.matrix_inv_sqrt(spd))
+    c, s = synth_features((2, 16, 20, 20), cfg=3)
+    dummy = object.__new__(wct.WCTRPNet)  # whiten_and_color / fuse use no module state
+    cf, sf = c[0].reshape(16, -1).double(), s[0].reshape(16, -1).double()
+    _save("wct", content=c, style=s,
+          closed_form=wct.WCTRPNet.whiten_and_color(dummy, cf, sf),
+          original=wct.WCTRPNet.whiten_and_color(dummy, cf, sf, method="original"),
+          fuse=wct.WCTRPNet.fuse(dummy, c, s))
+
+
+def gen_sanet(net):
+    sanet = sys.modules["network.sanet"]
+    torch.manual_seed(0)
+    planes = 16
+    c4, s4 = synth_features((2, planes, 8, 8), cfg=4)
+    c5, s5 = synth_features((2, planes, 4, 4), cfg=5)
+    m = sanet.SANet(planes)
+    arrays = {"c4": c4, "s4": s4, "c5": c5, "s5": s5, "sanet_out": m(c4, s4)}
+    arrays.update({"sanet." + k: v for k, v in m.state_dict().items()})
+    tr = sanet.Transform(planes)
+    arrays["transform_out"] = tr(c4, s4, c5, s5)
+    arrays.update({"transform." + k: v for k, v in tr.state_dict().items()})
+    for mode in ("aea", "relu"):
+        am = sanet.AdaptiveSANet(planes, 64, ada_module=mode)
+        arrays[f"ada_{mode}_out"] = am(c4, s4)
+        arrays[f"ada_{mode}_before"] = am.claim_before
+        arrays[f"ada_{mode}_after"] = am.claim_after
+        arrays[f"ada_{mode}_clamp"] = am.claim_value
+        arrays.update({f"ada_{mode}." + k: v for k, v in am.state_dict().items()})
+        at = sanet.AdaptiveTransform(planes, 64, 16, ada_module=mode)
+        arrays[f"adatr_{mode}_out"] = at(c4, s4, c5, s5)
+        arrays.update({f"adatr_{mode}." + k: v for k, v in at.state_dict().items()})
+    arrays["affinity"] = sanet.cal_affinity_matrix(c4, s4)
+    with torch.no_grad():
+        _save("sanet", **arrays)
+
+
+def gen_mrf(net):
+    base = sys.modules["network.base"]
+    mrf = sys.modules["network.mrf_rp"]
+    c, s = synth_features((1, 16, 8, 8), cfg=6)
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # reference hard-codes .cuda() (base.py:325-343)
+    try:
+        k = 3
+        aff = base.cal_affinity_map(c, s, k)
+        loss = mrf.MRFLoss(k)(c, s)
+        loss_all = mrf.MRFLoss(k, mean="all")(c, s)
+    finally:
+        torch.Tensor.cuda = saved
+    cn = torch.nn.functional.normalize(c.squeeze(), dim=0).view(16, -1)
+    sn = torch.nn.functional.normalize(s.squeeze(), dim=0).view(16, -1)
+    ncc = cn.t() @ sn
+    _save("mrf", content=c, style=s, k=k, affinity=aff, loss=loss, loss_all=loss_all,
+          dist=base.cal_dist(c.view(16, -1), s.view(16, -1)),
+          idx0=torch.topk(ncc, k, 0)[1], idx1=torch.topk(ncc, k, 1)[1])
+
+
+def gen_se(net):
+    att = sys.modules["network.attention"]
+    torch.manual_seed(1)
+    m = att.SELayer(32, reduction=16)
+    x, _ = synth_features((2, 32, 6, 10), cfg=7)
+    with torch.no_grad():
+        _save("se", x=x, out=m(x), gate=m.attention_map,
+              w1=m.fc[0].weight, w2=m.fc[2].weight)
+
+
+def main():
+    net = load_reference()
+    with torch.no_grad():
+        gen_adain(net)
+        gen_seg(net)
+        gen_wct(net)
+        gen_sanet(net)
+        gen_mrf(net)
+        gen_se(net)
+
+
+if __name__ == "__main__":
+    main()
