@@ -1,0 +1,99 @@
+/* librpst — C ABI of the B200-native stylization transform for RP-Style-Transfer.
+ *
+ * The reference (LuletterSoul/RP-Style-Transfer) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md §2b); each entry point below therefore cites the reference *Python* interface it
+ * replaces (file:line relative to the reference root).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; all tensors are contiguous NCHW fp32 device memory
+ *    unless stated; labels are uint8; index outputs are int64.
+ *  - the caller owns every buffer (inputs const, outputs and workspace pre-allocated); the library
+ *    keeps no device allocations between calls.  `*_workspace_bytes` tells how much scratch a call
+ *    needs; workspace contents need not be initialised.
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no host
+ *    synchronisation, re-entrant, safe to drive one stream per device from one thread each.
+ *  - return value: 0 on success, a negative RPST_ERR_* code otherwise; `rpst_last_error()` returns
+ *    a thread-local human-readable message.  Nothing throws or aborts.
+ */
+#ifndef RPST_H_
+#define RPST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPST_VERSION 100 /* major*100 + minor */
+
+#if defined(__GNUC__)
+#define RPST_API __attribute__((visibility("default")))
+#else
+#define RPST_API
+#endif
+
+#define RPST_OK 0
+#define RPST_ERR_INVALID (-1)   /* bad argument / shape mismatch (Python side raises AssertionError) */
+#define RPST_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define RPST_ERR_WORKSPACE (-3) /* workspace too small */
+#define RPST_ERR_UNSUPPORTED (-4)
+
+RPST_API int rpst_version(void);
+RPST_API const char* rpst_last_error(void);
+/* Tuning knobs for experiments (name -> integer value); unknown names return RPST_ERR_INVALID.
+ *   "adain_lag_bytes"  bytes of content kept L2-resident between the statistics and the apply phase
+ *   "adain_hints"      0/1: L2 eviction-priority hints on the streaming loads/stores
+ *   "adain_ctas_per_sm" persistent CTAs per SM for the pipelined kernel */
+RPST_API int rpst_set_tuning(const char* name, int64_t value);
+RPST_API int64_t rpst_get_tuning(const char* name);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  calc_mean_std(feat, eps=1e-5)                                   network/base.py:399-407
+ * Per-(n,c) plane mean and sqrt(unbiased variance + eps) over H*W.
+ *   x      [planes, hw]  (planes = N*C)
+ *   mean, std  [planes]  (either may be NULL)
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_stats_workspace_bytes(int64_t planes, int64_t hw);
+RPST_API int rpst_stats_nchw(const float* x, int64_t planes, int64_t hw, float eps, float* mean, float* std,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2  adaptive_instance_normalization(content_feat, style_feat)       network/base.py:410-418
+ * a3  stylized + AdaIN(c_l, s_l)  (multiscale blend)                  network/adain_rp.py:295-301
+ *     cat([stylized, AdaIN(c_l, s_l)], 1)  (LD4/LD5 concat-write)     network/adain_rp.py:786-798
+ * a8  mean_variance_norm(feat)                                        network/sanet.py:20-24
+ *
+ *   out[n,ch,:] = (content - mu_c)/sd_c * sd_s + mu_s  (+ prev)
+ *   content [n, c, hw]; style [n, c, hw] or NULL (=> sd_s=1, mu_s=0: mean_variance_norm);
+ *   prev    [n, c, hw] or NULL (=> plain AdaIN); prev may alias content (LDMS variants);
+ *   out     plane (i, ch) is written at out + i*out_batch_stride + ch*hw (elements), so the call can
+ *           write into a channel slice of a wider tensor; out_batch_stride = c*hw for a dense result.
+ *   saved_stats [n*c, 4] or NULL: (mu_c, sd_c, mu_s, sd_s) per plane, kept for the backward pass.
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw);
+RPST_API int rpst_adain_fwd(const float* content, const float* style, const float* prev, float* out,
+                   int64_t n, int64_t c, int64_t hw, int64_t out_batch_stride, float eps,
+                   float* saved_stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of rpst_adain_fwd w.r.t. content and style (autograd gives this to the reference for
+ * free; gradients reach the shared RP encoder through both arguments, SURVEY.md §7 hard part 7).
+ *   grad_out [n,c,hw]; saved_stats from the forward; grad_content / grad_style [n,c,hw]
+ *   (grad_style may be NULL; style may then be NULL as well).  d/dprev is grad_out itself. */
+RPST_API size_t rpst_adain_bwd_workspace_bytes(int64_t n, int64_t c, int64_t hw);
+RPST_API int rpst_adain_bwd(const float* grad_out, const float* content, const float* style,
+                   const float* saved_stats, float* grad_content, float* grad_style,
+                   int64_t n, int64_t c, int64_t hw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a15 SELayer.forward: x * gate[n,c]   (the pooling is rpst_stats_nchw)  network/attention.py:17-22
+ *   out[p,:] = x[p,:] * scale[p] + shift[p]   (shift may be NULL)
+ * ------------------------------------------------------------------------------------------ */
+RPST_API int rpst_plane_affine(const float* x, const float* scale, const float* shift, float* out,
+                      int64_t planes, int64_t hw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPST_H_ */

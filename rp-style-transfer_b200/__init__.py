@@ -1,0 +1,14 @@
+"""rpst — B200-native stylization transform for RP-Style-Transfer (hot path only).
+
+`import rpst` works through the alias package at the repo root; this directory is the product.
+Everything here calls hand-written sm_100a kernels through the C ABI in include/rpst.h."""
+from . import _lib
+from ._lib import RpstError, get_tuning, set_tuning
+from .functional import (adain_blend, adain_concat, adaptive_instance_normalization, calc_mean_std,
+                         mean_variance_norm, plane_affine)
+
+AdaIN = adaptive_instance_normalization
+
+
+def version() -> int:
+    return int(_lib.lib().rpst_version())

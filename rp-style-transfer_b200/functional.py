@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference's transform FUNCTIONS (same names, arguments and error
+behaviour), each a thin call into librpst through the C ABI.
+
+Reference interfaces mirrored (paths relative to the reference root):
+  calc_mean_std                        network/base.py:399-407
+  adaptive_instance_normalization      network/base.py:410-418
+  mean_variance_norm                   network/sanet.py:20-24
+plus the fused forms the reference spells as two ops:
+  adain_blend(prev, c, s)              network/adain_rp.py:300-301  (`stylized + AdaIN(c, s)`)
+  adain_concat(prev, c, s)             network/adain_rp.py:793      (`cat([stylized, AdaIN(c, s)], 1)`)
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+EPS = 1e-5
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"rpst: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"rpst: `{name}` must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------ raw calls
+def _stats_raw(feat: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    n, c = feat.shape[:2]
+    hw = feat[0, 0].numel() if feat.numel() else 0
+    mean = torch.empty(n * c, dtype=torch.float32, device=feat.device)
+    std = torch.empty_like(mean)
+    L = _lib.lib()
+    ws = _workspace(L.rpst_stats_workspace_bytes(n * c, hw), feat.device)
+    _lib.check(L.rpst_stats_nchw(feat.data_ptr(), n * c, hw, eps, mean.data_ptr(), std.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream()))
+    return mean, std
+
+
+def _adain_raw(content, style, prev, out, out_batch_stride, eps, want_saved):
+    n, c = content.shape[:2]
+    hw = content[0, 0].numel() if content.numel() else 0
+    saved = torch.empty(n * c, 4, dtype=torch.float32, device=content.device) if want_saved else None
+    L = _lib.lib()
+    ws = _workspace(L.rpst_adain_workspace_bytes(n, c, hw), content.device)
+    _lib.check(L.rpst_adain_fwd(content.data_ptr(), _ptr(style), _ptr(prev), out.data_ptr(), n, c, hw,
+                                out_batch_stride, eps, _ptr(saved), ws.data_ptr(), ws.numel(), _stream()))
+    return saved
+
+
+def _adain_bwd_raw(grad_out, content, style, saved, need_style):
+    n, c = content.shape[:2]
+    hw = content[0, 0].numel() if content.numel() else 0
+    dc = torch.empty_like(content)
+    ds = torch.empty_like(content) if need_style else None
+    L = _lib.lib()
+    ws = _workspace(L.rpst_adain_bwd_workspace_bytes(n, c, hw), content.device)
+    _lib.check(L.rpst_adain_bwd(grad_out.data_ptr(), content.data_ptr(), _ptr(style) if need_style else None,
+                                saved.data_ptr(), dc.data_ptr(), _ptr(ds), n, c, hw,
+                                ws.data_ptr(), ws.numel(), _stream()))
+    return dc, ds
+
+
+class _AdaINFn(torch.autograd.Function):
+    """out = AdaIN(content, style) [+ prev]; style None => mean_variance_norm."""
+
+    @staticmethod
+    def forward(ctx, content, style, prev):
+        out = torch.empty_like(content)
+        n, c = content.shape[:2]
+        hw = content[0, 0].numel() if content.numel() else 0
+        need_grad = content.requires_grad or (style is not None and style.requires_grad)
+        saved = _adain_raw(content, style, prev, out, c * hw, EPS, need_grad)
+        if need_grad:
+            ctx.save_for_backward(content, style if style is not None else content, saved)
+        ctx.has_style = style is not None
+        ctx.has_prev = prev is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        content, style, saved = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        need_style = ctx.has_style and ctx.needs_input_grad[1]
+        dc, ds = _adain_bwd_raw(grad_out, content, style, saved, need_style)
+        return (dc if ctx.needs_input_grad[0] else None, ds,
+                grad_out if (ctx.has_prev and ctx.needs_input_grad[2]) else None)
+
+
+# ------------------------------------------------------------------------------------ public API
+def calc_mean_std(feat: torch.Tensor, eps: float = EPS) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for network/base.py:399 — returns (mean, std), both [N,C,1,1]."""
+    size = feat.size()
+    assert (len(size) == 4)
+    n, c = size[:2]
+    if feat.requires_grad and torch.is_grad_enabled():
+        # style-loss statistics need autograd; keep them differentiable through a tiny torch graph
+        # built on the kernel's numbers: d(mean)/dx and d(std)/dx are cheap closed forms.
+        return _StatsFn.apply(feat, eps)
+    mean, std = _stats_raw(_prep(feat, "feat"), eps)
+    return mean.view(n, c, 1, 1), std.view(n, c, 1, 1)
+
+
+class _StatsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, eps):
+        x = _prep(feat, "feat")
+        n, c = x.shape[:2]
+        mean, std = _stats_raw(x, eps)
+        mean, std = mean.view(n, c, 1, 1), std.view(n, c, 1, 1)
+        ctx.save_for_backward(x, mean, std)
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, g_mean, g_std):
+        x, mean, std = ctx.saved_tensors
+        hw = x[0, 0].numel()
+        # d mean/dx = 1/HW ; d std/dx = (x-mean)/((HW-1) std): one fused plane-affine pass
+        scale = (g_std / ((hw - 1) * std)).reshape(-1).contiguous()
+        shift = (g_mean / hw - scale.view_as(mean) * mean).reshape(-1).contiguous()
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().rpst_plane_affine(x.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
+                                                x.shape[0] * x.shape[1], hw, _stream()))
+        return out, None
+
+
+def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+    """Drop-in for network/base.py:410."""
+    assert (content_feat.size() == style_feat.size())
+    assert content_feat.dim() == 4
+    return _AdaINFn.apply(_prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"), None)
+
+
+def adain_blend(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+    """`prev + AdaIN(content_feat, style_feat)` in one pass (network/adain_rp.py:300-301)."""
+    assert (content_feat.size() == style_feat.size())
+    assert (prev.size() == content_feat.size())
+    return _AdaINFn.apply(_prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"), _prep(prev, "prev"))
+
+
+def adain_concat(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+    """`torch.cat([prev, AdaIN(content_feat, style_feat)], dim=1)` with the AdaIN half written
+    straight into the channel slice of the result (network/adain_rp.py:793).  Inference only."""
+    assert (content_feat.size() == style_feat.size())
+    assert prev.shape[0] == content_feat.shape[0] and prev.shape[2:] == content_feat.shape[2:]
+    if torch.is_grad_enabled() and (prev.requires_grad or content_feat.requires_grad or style_feat.requires_grad):
+        return torch.cat([prev, adaptive_instance_normalization(content_feat, style_feat)], dim=1)
+    c = _prep(content_feat, "content_feat")
+    s = _prep(style_feat, "style_feat")
+    n, cp = prev.shape[:2]
+    cc = c.shape[1]
+    hw = c[0, 0].numel()
+    out = torch.empty((n, cp + cc) + tuple(c.shape[2:]), dtype=c.dtype, device=c.device)
+    out[:, :cp].copy_(prev)
+    _adain_raw(c, s, None, out[:, cp:], (cp + cc) * hw, EPS, False)
+    return out
+
+
+def mean_variance_norm(feat: torch.Tensor) -> torch.Tensor:
+    """Drop-in for network/sanet.py:20."""
+    assert feat.dim() == 4
+    return _AdaINFn.apply(_prep(feat, "feat"), None, None)
+
+
+def plane_affine(x: torch.Tensor, scale: torch.Tensor, shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[n,c,:,:] = x[n,c,:,:] * scale[n,c] (+ shift[n,c])."""
+    x = _prep(x, "x")
+    n, c = x.shape[:2]
+    scale = _prep(scale.reshape(-1), "scale")
+    assert scale.numel() == n * c
+    if shift is not None:
+        shift = _prep(shift.reshape(-1), "shift")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().rpst_plane_affine(x.data_ptr(), scale.data_ptr(), _ptr(shift), out.data_ptr(),
+                                            n * c, x[0, 0].numel() if x.numel() else 0, _stream()))
+    return out

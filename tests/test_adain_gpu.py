@@ -1,0 +1,170 @@
+"""GPU parity tests for the AdaIN family through the C ABI (rpst -> librpst.so) against the oracle
+and the reference-generated golden vectors.  Tolerance: rel-L2 <= 1e-3 is the contract
+(BASELINE.json north_star, fp32); these kernels are expected to sit at ~1e-6."""
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3      # contract
+TIGHT = 2e-6    # what an fp32 kernel with pairwise moments should reach
+
+
+@pytest.fixture(scope="module")
+def rpst():
+    import rpst as m
+    return m
+
+
+def dev(t):
+    return t.cuda()
+
+
+@pytest.mark.parametrize("tag", ["odd", "sq", "signed"])
+def test_golden(rpst, golden, tag):
+    g = golden(f"adain_{tag}")
+    c, s, p = dev(g["content"]), dev(g["style"]), dev(g["prev"])
+    mean, std = rpst.calc_mean_std(c)
+    assert mean.shape == g["mean"].shape and std.shape == g["std"].shape
+    assert R.rel_l2(mean, g["mean"]) < TIGHT and R.rel_l2(std, g["std"]) < TIGHT
+    assert R.rel_l2(rpst.adaptive_instance_normalization(c, s), g["out"]) < TIGHT
+    assert R.rel_l2(rpst.adain_blend(p, c, s), g["blend"]) < TIGHT
+    assert R.rel_l2(rpst.mean_variance_norm(c), g["mvn"]) < TIGHT
+
+
+def test_golden_hw2(rpst, golden):
+    g = golden("adain_hw2")
+    out = rpst.adaptive_instance_normalization(dev(g["content"]), dev(g["style"]))
+    assert R.rel_l2(out, g["out"]) < 1e-5
+
+
+def test_hw1_is_nan_like_torch(rpst):
+    c = torch.randn(1, 2, 1, 1).cuda()
+    mean, std = rpst.calc_mean_std(c)
+    assert torch.isnan(std).all() and torch.equal(mean.cpu(), c.cpu())
+
+
+# direct kernel (register resident), pipelined kernel (vector + tail chunk), scalar paths, big plane
+SHAPES = [(2, 3, 8, 8), (1, 512, 64, 64), (2, 5, 128, 128), (1, 3, 300, 300), (2, 4, 512, 512),
+          (1, 2, 301, 301), (1, 3, 33, 31), (1, 2, 1024, 2048), (3, 2, 130, 130)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_vs_oracle(rpst, shape):
+    c, s = R.synth_features(shape, cfg=sum(shape) % 7)
+    prev = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    cd, sd, pd = dev(c), dev(s), dev(prev)
+    want = R.adain(c, s, dtype=torch.float64)
+    assert R.rel_l2(rpst.adaptive_instance_normalization(cd, sd), want) < TIGHT
+    assert R.rel_l2(rpst.adain_blend(pd, cd, sd), want + prev.double()) < TIGHT
+    mu, sd_ = R.plane_stats(c, dtype=torch.float64)
+    gm, gs = rpst.calc_mean_std(cd)
+    assert R.rel_l2(gm, mu) < TIGHT and R.rel_l2(gs, sd_) < TIGHT
+    assert R.rel_l2(rpst.mean_variance_norm(cd), R.mean_variance_norm(c, dtype=torch.float64)) < TIGHT
+
+
+def test_large_mean_small_std_is_stable(rpst):
+    # sum/sum-of-squares would lose everything here; (count, mean, M2) merging must not
+    g = torch.Generator().manual_seed(3)
+    c = 1000.0 + 0.01 * torch.randn(1, 2, 512, 512, generator=g)
+    s = torch.randn(1, 2, 512, 512, generator=g)
+    want = R.adain(c, s, dtype=torch.float64)
+    got = rpst.adaptive_instance_normalization(dev(c), dev(s))
+    assert R.rel_l2(got, want) < 1e-3
+
+
+def test_concat_write_and_alias(rpst):
+    c, s = R.synth_features((2, 6, 96, 96), cfg=2)
+    prev = torch.randn(2, 10, 96, 96)
+    got = rpst.adain_concat(dev(prev), dev(c), dev(s))
+    want = torch.cat([prev.double(), R.adain(c, s, dtype=torch.float64)], dim=1)
+    assert got.shape == want.shape and R.rel_l2(got, want) < TIGHT
+    # LDMS variant: prev aliases content (network/adain_rp.py:543-552)
+    cd, sdv = dev(c), dev(s)
+    got = rpst.adain_blend(cd, cd, sdv)
+    assert R.rel_l2(got, c.double() + R.adain(c, s, dtype=torch.float64)) < TIGHT
+
+
+def test_shape_mismatch_asserts_like_reference(rpst):
+    c = torch.zeros(1, 2, 8, 8).cuda()
+    with pytest.raises(AssertionError):
+        rpst.adaptive_instance_normalization(c, c[:, :, :4])
+
+
+def test_non_contiguous_and_unaligned_inputs(rpst):
+    c, s = R.synth_features((2, 4, 40, 44), cfg=1)
+    cd = dev(c).transpose(2, 3).contiguous().transpose(2, 3)        # non-contiguous view
+    got = rpst.adaptive_instance_normalization(cd, dev(s))
+    assert R.rel_l2(got, R.adain(c, s, dtype=torch.float64)) < TIGHT
+    buf = torch.zeros(c.numel() + 1, device="cuda")
+    buf[1:] = dev(c).reshape(-1)
+    cu = buf[1:].view(c.shape)                                      # 4-byte aligned only -> scalar path
+    got = rpst.adaptive_instance_normalization(cu, dev(s))
+    assert R.rel_l2(got, R.adain(c, s, dtype=torch.float64)) < TIGHT
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (1, 2, 300, 300), (2, 2, 512, 512)])
+def test_backward_matches_autograd_of_the_reference_formula(rpst, shape):
+    c, s = R.synth_features(shape, cfg=5, signed=True)
+    prev = torch.randn(shape)
+    w = torch.randn(shape, generator=torch.Generator().manual_seed(4))
+
+    def ref(c, s, p):
+        n, ch = c.shape[:2]
+        def ms(x):
+            f = x.reshape(n, ch, -1)
+            return f.mean(2).view(n, ch, 1, 1), (f.var(2) + 1e-5).sqrt().view(n, ch, 1, 1)
+        mc, sc = ms(c)
+        m_s, ss = ms(s)
+        return (c - mc) / sc * ss + m_s + p
+
+    c64, s64, p64 = (t.double().requires_grad_() for t in (c, s, prev))
+    (ref(c64, s64, p64) * w.double()).sum().backward()
+    cd, sd, pd = (dev(t).requires_grad_() for t in (c, s, prev))
+    (rpst.adain_blend(pd, cd, sd) * dev(w)).sum().backward()
+    assert R.rel_l2(cd.grad, c64.grad) < 1e-4
+    assert R.rel_l2(sd.grad, s64.grad) < 1e-4
+    assert R.rel_l2(pd.grad, p64.grad) < 1e-6
+    # statistics with autograd (style loss path, network/adain_rp.py:84-88)
+    x64 = c.double().requires_grad_()
+    f = x64.reshape(shape[0], shape[1], -1)
+    (f.mean(2).sum() * 0.3 + ((f.var(2) + 1e-5).sqrt() * 1.7).sum()).backward()
+    xd = dev(c).requires_grad_()
+    m, sdev = rpst.calc_mean_std(xd)
+    (m.sum() * 0.3 + (sdev * 1.7).sum()).backward()
+    assert R.rel_l2(xd.grad, x64.grad) < 1e-4
+
+
+def test_properties_at_full_plane_size(rpst):
+    """Size-independent properties at BASELINE config #2's plane size (512x512), C=256, N=2:
+    statistics of AdaIN(c,s) equal those of s; AdaIN is invariant to an affine map of the content;
+    blend - plain == prev."""
+    shape = (2, 256, 512, 512)
+    c, s = R.synth_features(shape, cfg=2, device="cuda")
+    out = rpst.adaptive_instance_normalization(c, s)
+    mo, so = rpst.calc_mean_std(out)
+    ms_, ss = rpst.calc_mean_std(s)
+    assert R.rel_l2(mo, ms_) < 1e-5 and R.rel_l2(so, ss) < 1e-5
+    out2 = rpst.adaptive_instance_normalization(c * 3.0 + 2.0, s)
+    assert R.rel_l2(out2, out) < 1e-5
+    prev = torch.randn(shape, device="cuda")
+    assert R.rel_l2(rpst.adain_blend(prev, c, s) - out, prev) < 1e-5
+    # and one sample slice against the oracle
+    want = R.adain(c[:1, :8].cpu(), s[:1, :8].cpu(), dtype=torch.float64)
+    assert R.rel_l2(out[:1, :8], want) < TIGHT
+
+
+def test_tuning_variants_agree(rpst):
+    c, s = R.synth_features((2, 8, 512, 512), cfg=3, device="cuda")
+    base = rpst.adaptive_instance_normalization(c, s)
+    old = {k: rpst.get_tuning(k) for k in ("adain_lag_bytes", "adain_hints", "adain_ctas_per_sm")}
+    try:
+        for lag, hints, ctas in [(1 << 20, 0, 4), (64 << 20, 1, 3), (1, 1, 4)]:
+            rpst.set_tuning("adain_lag_bytes", lag)
+            rpst.set_tuning("adain_hints", hints)
+            rpst.set_tuning("adain_ctas_per_sm", ctas)
+            assert torch.equal(rpst.adaptive_instance_normalization(c, s), base)
+    finally:
+        for k, v in old.items():
+            rpst.set_tuning(k, v)
