@@ -45,7 +45,9 @@ RPST_API const char* rpst_last_error(void);
 /* Tuning knobs for experiments (name -> integer value); unknown names return RPST_ERR_INVALID.
  *   "adain_lag_bytes"  bytes of content kept L2-resident between the statistics and the apply phase
  *   "adain_hints"      0/1: L2 eviction-priority hints on the streaming loads/stores
- *   "adain_ctas_per_sm" persistent CTAs per SM for the pipelined kernel */
+ *   "adain_ctas_per_sm" persistent CTAs per SM for the register-staged pipelined kernel
+ *   "adain_path"       0: TMA-staged kernel when planes are 16-byte aligned (default), 1: register-staged
+ *   "adain_stages"     TMA shared-memory stages = consumer warp groups per CTA (2..7, 32 KiB each) */
 RPST_API int rpst_set_tuning(const char* name, int64_t value);
 RPST_API int64_t rpst_get_tuning(const char* name);
 
@@ -92,6 +94,28 @@ RPST_API int rpst_adain_bwd(const float* grad_out, const float* content, const f
  * ------------------------------------------------------------------------------------------ */
 RPST_API int rpst_plane_affine(const float* x, const float* scale, const float* shift, float* out,
                       int64_t planes, int64_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  adaptive_instance_normalization_with_segment(content_feat, style_feat, c_seg, s_seg)
+ *                                                                     network/base.py:494-530
+ *     compute_label_info (validity rule)                              network/base.py:421-439
+ *     do_mask_stylized (per-sample loop over the batch)               network/adain_rp.py:313-319
+ *
+ * Whole batch in one call; label maps are uint8 tensors already at feature resolution (the reference
+ * loads PNG paths and resizes them with PIL at network/base.py:450-451 — that I/O stays in Python).
+ *   content [n,c,hw_c], style [n,c,hw_s] (content and style may differ in H*W);
+ *   c_labels [n,hw_c], s_labels [n,hw_s]; prev [n,c,hw_c] or NULL (out = prev + seg-AdaIN);
+ *   out [n,c,hw_c].  For every label value present in a sample's CONTENT map that is usable
+ *   (cnt_c>10, cnt_s>10, cnt_c/cnt_s<100, cnt_s/cnt_c<100) the content pixels carrying it are
+ *   AdaIN'd with the masked statistics (unbiased variance, eps inside sqrt); all other pixels are
+ *   copied through bit-exactly.
+ *   label_info [n,256,3] int32 or NULL: (cnt_c, cnt_s, usable) per label value.
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_seg_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s);
+RPST_API int rpst_seg_adain_fwd(const float* content, const float* style, const uint8_t* c_labels,
+                       const uint8_t* s_labels, const float* prev, float* out, int64_t n, int64_t c,
+                       int64_t hw_c, int64_t hw_s, float eps, int32_t* label_info, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

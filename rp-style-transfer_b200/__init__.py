@@ -7,7 +7,11 @@ from ._lib import RpstError, get_tuning, set_tuning
 from .functional import (adain_blend, adain_concat, adaptive_instance_normalization, calc_mean_std,
                          mean_variance_norm, plane_affine)
 
+from .modules import SELayer
+from .segment import adaptive_instance_normalization_with_segment, do_mask_stylized, load_label_map, seg_adain_batch
+
 AdaIN = adaptive_instance_normalization
+AdaINSeg = adaptive_instance_normalization_with_segment
 
 
 def version() -> int:

@@ -6,33 +6,34 @@
 //    plane, content is read ONCE from HBM and stays in registers between the statistics and the
 //    apply phase.
 //  * adain_pipe_kernel    — larger planes (512x512 = 1 MiB, 1024x2048 = 8 MiB ...): a persistent
-//    kernel whose CTAs pull 32 KiB work items from a global ticket counter.  Statistics items of
+//    kernel whose warps each walk a static, ordered list of 4 KiB work items.  Statistics items of
 //    plane p+D are interleaved with apply items of plane p, so that the second read of the content
 //    (apply) is served by the 126 MB L2 (the content lines are loaded with an evict_last policy,
 //    every other stream with evict_first) and HBM sees each tensor exactly once: the algorithmic
 //    3*E*4 (AdaIN) / 4*E*4 (blend) bytes of SURVEY.md §8d.  An apply item waits on a per-plane
 //    release/acquire flag set by the CTA that finished the plane's last statistics item; items
-//    are issued in ticket order and statistics items never block, so the wait cannot deadlock.
+//    are walked in order by co-resident warps and statistics items never block, so the wait cannot deadlock.
 //
 // Numerics: unbiased variance, eps inside the sqrt (network/base.py:404-405);
 // moments are accumulated as (count, mean, M2) with a two-pass evaluation over each thread's
 // registers and Chan merges above that, never as raw sum/sum-of-squares.
 #include "common.cuh"
+#include "plane_io.cuh"
+#include "async.cuh"
 
 namespace rpst {
 namespace {
 
-constexpr int kBatch = 4;          // vectors per load batch
-constexpr int kBatches = 2;        // batches per thread per item
-constexpr int kPerThread = kBatch * kBatches;
-constexpr int kPipeThreads = 256;
-
 struct Tuning {
-    int64_t lag_bytes = 16ll << 20;
+    int64_t lag_bytes = 32ll << 20;
     int64_t hints = 1;
-    int64_t ctas_per_sm = 3;
+    int64_t ctas_per_sm = 4;
+    int64_t path = 0;    // 0: TMA-staged kernel when alignment allows, 1: register-staged kernel
+    int64_t stages = 6;  // TMA ring depth (32 KiB per stage)
 };
 Tuning g_tuning;
+
+constexpr int kItemElems = 4096;  // one work item: 16 KiB of each tensor (256 threads x 4 float4)
 
 struct AdainParams {
     const float* content;
@@ -48,100 +49,14 @@ struct AdainParams {
     int hints;
     // pipelined kernel only
     int ipp;             // items (chunks) per plane
+    int spp;             // statistics slots per plane
+    int slot_elems;      // elements summarised by one slot (last slot of a plane may be short)
     int lag;             // planes between statistics and apply
     unsigned total_items;
-    unsigned* ticket;
-    int* done;           // [planes]
-    int* ready;          // [planes]
-    float4* coef;        // [planes] (mu_c, a, mu_s, unused)
-    float2* part_c;      // [planes*ipp] (mean, m2)
-    float2* part_s;
+    unsigned* ticket;    // starts at 0xFFFFFFFF
+    float4* coef;        // [planes] (mu_c hi, a, mu_s, mu_c lo); 0xFF-filled = not merged yet
+    float4* part;        // [planes*ipp] (mean_c, m2_c, mean_s, m2_s); 0xFF-filled = not written yet
 };
-
-template <int VEC>
-struct VecT;
-template <>
-struct VecT<4> {
-    using type = float4;
-};
-template <>
-struct VecT<1> {
-    using type = float;
-};
-
-template <int VEC>
-__device__ __forceinline__ void load_vec(float (&dst)[VEC], const float* p, uint64_t pol, bool hint) {
-    if constexpr (VEC == 4) {
-        float4 v = hint ? ldg_f4_hint(p, pol) : __ldg(reinterpret_cast<const float4*>(p));
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-    } else {
-        dst[0] = hint ? ldg_f1_hint(p, pol) : __ldg(p);
-    }
-}
-template <int VEC>
-__device__ __forceinline__ void store_vec(float* p, const float (&src)[VEC], uint64_t pol, bool hint) {
-    if constexpr (VEC == 4) {
-        float4 v = make_float4(src[0], src[1], src[2], src[3]);
-        if (hint) stg_f4_hint(p, v, pol); else *reinterpret_cast<float4*>(p) = v;
-    } else {
-        if (hint) stg_f1_hint(p, src[0], pol); else *p = src[0];
-    }
-}
-
-// Load one batch (kBatch vectors, strided by THREADS vectors) of a chunk that holds `nvec` vectors.
-template <int VEC, int THREADS>
-__device__ __forceinline__ void load_batch(float (&v)[kBatch][VEC], const float* base, int batch, int nvec,
-                                           uint64_t pol, bool hint) {
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-        int idx = (batch * kBatch + j) * THREADS + threadIdx.x;
-        if (idx < nvec) {
-            load_vec<VEC>(v[j], base + (int64_t)idx * VEC, pol, hint);
-        } else {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v[j][e] = 0.f;
-        }
-    }
-}
-
-// Exact two-pass moments of the valid part of a register batch, merged into `acc`.
-template <int VEC, int THREADS>
-__device__ __forceinline__ void batch_moments(Moments& acc, const float (&v)[kBatch][VEC], int batch, int nvec) {
-    float sum = 0.f;
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-        int idx = (batch * kBatch + j) * THREADS + threadIdx.x;
-        if (idx < nvec) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) sum += v[j][e];
-            cnt += VEC;
-        }
-    }
-    if (cnt == 0) return;
-    Moments m;
-    m.n = (float)cnt;
-    m.mean = sum / m.n;
-    float m2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-        int idx = (batch * kBatch + j) * THREADS + threadIdx.x;
-        if (idx < nvec) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                float d = v[j][e] - m.mean;
-                m2 = fmaf(d, d, m2);
-            }
-        }
-    }
-    m.m2 = m2;
-    acc = merge(acc, m);
-}
-
-__device__ __forceinline__ float std_from(const Moments& m, float hw, float eps) {
-    // unbiased: divide by HW-1 (0/0 -> NaN for HW==1, like torch.var)
-    return sqrtf(m.m2 / (hw - 1.f) + eps);
-}
 
 // ------------------------------------------------------------------------------------------
 // direct kernel: one CTA per plane, content stays in registers
@@ -249,115 +164,220 @@ __device__ __forceinline__ Item decode_ticket(unsigned t, const AdainParams& p) 
     return it;
 }
 
+// Hand-off without fences or atomics.  A statistics item publishes its chunk moments as ONE
+// 16-byte slot {mean_c, M2_c, mean_s, M2_s}; the slot array is memset to 0xFF before the launch and a
+// component whose bits are still 0xFFFFFFFF means "not written yet" (a computed value is never that
+// bit pattern: results are canonicalised).  Data and "valid" marker being the same word, no ordering
+// between separate locations is needed, hence no __threadfence / counter / last-arriver logic.  An
+// apply item first looks at the plane's merged-coefficient slot (same sentinel scheme); on a miss its
+// warp 0 polls the plane's partial slots, merges them in fp64 and publishes the coefficients (every
+// merger computes bit-identical values, so concurrent publication is benign and deterministic).
+// Items are handed out in schedule order by a ticket counter (one atomic per item, prefetched);
+// statistics items never wait, so polling always terminates.  Exactly one __syncthreads per item.
+__device__ __forceinline__ bool slot_valid(const float4& v) {
+    return __float_as_uint(v.x) != 0xffffffffu && __float_as_uint(v.y) != 0xffffffffu &&
+           __float_as_uint(v.z) != 0xffffffffu && __float_as_uint(v.w) != 0xffffffffu;
+}
+__device__ __forceinline__ float canon(float v) {
+    return __float_as_uint(v) == 0xffffffffu ? __uint_as_float(0x7fc00000u) : v;
+}
+__device__ __forceinline__ float4 ld_slot(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_slot(float4* p, float4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(canon(v.x)), "f"(canon(v.y)), "f"(canon(v.z)), "f"(canon(v.w)) : "memory");
+}
+
+// schedule: prologue = statistics of the first `lag` planes; steady round r = [statistics of plane
+// r+lag][apply of plane r]; epilogue = apply of the last `lag` planes.
+__device__ __forceinline__ Item decode_item(unsigned t, const AdainParams& p) {
+    Item it;
+    const unsigned ipp = (unsigned)p.ipp;
+    if (p.stats_only) {
+        it.kind = 0; it.plane = t / ipp; it.chunk = (int)(t % ipp);
+        return it;
+    }
+    const unsigned planes = (unsigned)p.planes;
+    const unsigned lag = (unsigned)p.lag < planes ? (unsigned)p.lag : planes;
+    const unsigned pro = lag * ipp;
+    if (t < pro) {
+        it.kind = 0; it.plane = t / ipp; it.chunk = (int)(t % ipp);
+        return it;
+    }
+    t -= pro;
+    const unsigned steady = (planes - lag) * 2u * ipp;
+    if (t < steady) {
+        const unsigned r = t / (2u * ipp), u = t % (2u * ipp);
+        it.kind = u >= ipp;
+        it.chunk = (int)(it.kind ? u - ipp : u);
+        it.plane = it.kind ? r : r + lag;
+        return it;
+    }
+    t -= steady;
+    it.kind = 1; it.plane = (planes - lag) + t / ipp; it.chunk = (int)(t % ipp);
+    return it;
+}
+
+// Merge the chunk moments of one plane (full warp).  All arithmetic is fp32 but relative to the
+// first chunk's mean K, so the result keeps the plane mean to better than fp32 (returned as hi+lo):
+//   mean = K + d,  d = sum n_k (mean_k - K) / N,   M2 = sum M2_k + sum n_k (mean_k - K - d)^2
+// Every caller computes bit-identical values (fixed lane assignment, fixed reduction tree).
+__device__ __forceinline__ float4 merge_plane_coef(const AdainParams& p, int64_t plane, int lane) {
+    const float4* slots = p.part + plane * p.spp;
+    // pass 1 (polling): K = first chunk's means, d = sum n_k (mean_k - K) / N
+    float4 v0 = ld_slot(slots);
+    if (!slot_valid(v0)) {
+        const uint64_t t0 = global_timer_ns();
+        do {
+            __nanosleep(40);
+            v0 = ld_slot(slots);
+            if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+        } while (!slot_valid(v0));
+    }
+    const float kc = v0.x, ks = v0.z;
+    float dc = 0.f, ds = 0.f;
+    for (int k = lane; k < p.spp; k += 32) {
+        float4 v = ld_slot(slots + k);
+        if (!slot_valid(v)) {  // straggling statistics item: wait for it
+            const uint64_t t0 = global_timer_ns();
+            do {
+                __nanosleep(40);
+                v = ld_slot(slots + k);
+                if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+            } while (!slot_valid(v));
+        }
+        const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+        const float n = (float)(rem < p.slot_elems ? rem : p.slot_elems);
+        dc = fmaf(n, v.x - kc, dc);
+        ds = fmaf(n, v.z - ks, ds);
+    }
+    const float inv_n = 1.f / (float)p.hw;
+    dc = warp_sum(dc) * inv_n;
+    ds = warp_sum(ds) * inv_n;
+    // pass 2 (all slots are valid now; L2 hits)
+    float m2c = 0.f, m2s = 0.f;
+    for (int k = lane; k < p.spp; k += 32) {
+        const float4 v = ld_slot(slots + k);
+        const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+        const float n = (float)(rem < p.slot_elems ? rem : p.slot_elems);
+        const float ec = v.x - kc - dc, es = v.z - ks - ds;
+        m2c += fmaf(n * ec, ec, v.y);
+        m2s += fmaf(n * es, es, v.w);
+    }
+    m2c = warp_sum(m2c);
+    m2s = warp_sum(m2s);
+    const float mu_hi = kc + dc;
+    const float mu_lo = (kc - mu_hi) + dc;  // Fast2Sum remainder (|kc| >= |dc| in all but degenerate planes)
+    const float denom = (float)p.hw - 1.f;
+    const float sd_c = sqrtf(m2c / denom + p.eps);
+    float mu_s = 0.f, sd_s = 1.f;
+    if (p.style != nullptr) {
+        mu_s = ks + ds;
+        sd_s = sqrtf(m2s / denom + p.eps);
+    }
+    const float4 cf = make_float4(mu_hi, sd_s / sd_c, mu_s, mu_lo);
+    if (lane == 0) {
+        st_slot(&p.coef[plane], cf);
+        if (p.saved) reinterpret_cast<float4*>(p.saved)[plane] = make_float4(mu_hi, sd_c, mu_s, sd_s);
+    }
+    return cf;
+}
+
 template <int VEC, int MINB>
 __global__ void __launch_bounds__(kPipeThreads, MINB) adain_pipe_kernel(AdainParams p) {
     constexpr int T = kPipeThreads;
-    constexpr int CHUNK = T * kPerThread * VEC;
-    __shared__ Moments scratch[2][32];
-    __shared__ unsigned s_ticket;
-    __shared__ int s_last;
-    __shared__ float4 s_coef;
+    constexpr int NB = kItemElems / (T * kBatch * VEC);  // register batches per thread per tensor
+    static_assert(NB >= 1, "item too small");
+    __shared__ Moments scratch[2][2][T / 32];
+    __shared__ float4 s_coef[2];
+    __shared__ unsigned s_next[2];
 
     const uint64_t pol_first = policy_evict_first();
     const uint64_t pol_last = policy_evict_last();
     const bool hint = p.hints != 0;
-    const float hwf = (float)p.hw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool has_style = p.style != nullptr;
+    unsigned parity = 0;
 
-    if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1u);
+    // dynamic schedule: the ticket word starts at 0xFFFFFFFF (workspace memset), so old+1 counts from 0.
+    // The ticket of the NEXT item is requested at the top of an item (latency hidden behind the data
+    // loads) and broadcast through the item's single barrier.
+    if (threadIdx.x == 0) s_next[0] = atomicAdd(p.ticket, 1u) + 1u;
     __syncthreads();
-    unsigned t = s_ticket;
+    unsigned t = s_next[0];
 
-    while (t < p.total_items) {
-        unsigned next = 0;
-        if (threadIdx.x == 0) next = atomicAdd(p.ticket, 1u);  // latency hidden behind the item
-
-        const Item it = decode_ticket(t, p);
-        const int64_t e0 = (int64_t)it.chunk * CHUNK;
+    for (; t < p.total_items; t = s_next[parity ^ 1u], parity ^= 1u) {
+        unsigned nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(p.ticket, 1u) + 1u;
+        const Item it = decode_item(t, p);
+        const int64_t e0 = (int64_t)it.chunk * kItemElems;
         const int64_t rem = p.hw - e0;
-        const int nvec = (int)((rem < CHUNK ? rem : CHUNK) / VEC);
+        const int nvec = (int)((rem < kItemElems ? rem : kItemElems) / VEC);
         const float* cbase = p.content + it.plane * p.hw + e0;
 
         if (it.kind == 0) {
             // ---------------- statistics item
-            Moments mc = {0.f, 0.f, 0.f}, ms = {0.f, 0.f, 0.f};
+            float c[NB][kBatch][VEC], s[NB][kBatch][VEC];
             const uint64_t cpol = p.stats_only ? pol_first : pol_last;
-            {
-                float c[kBatches][kBatch][VEC];
 #pragma unroll
-                for (int b = 0; b < kBatches; ++b) load_batch<VEC, T>(c[b], cbase, b, nvec, cpol, hint);
-#pragma unroll
-                for (int b = 0; b < kBatches; ++b) batch_moments<VEC, T>(mc, c[b], b, nvec);
-            }
-            if (p.style != nullptr) {
+            for (int b = 0; b < NB; ++b) load_batch<VEC, T>(c[b], cbase, b, nvec, cpol, hint);
+            if (has_style) {
                 const float* sbase = p.style + it.plane * p.hw + e0;
-                float s[kBatches][kBatch][VEC];
 #pragma unroll
-                for (int b = 0; b < kBatches; ++b) load_batch<VEC, T>(s[b], sbase, b, nvec, pol_first, hint);
+                for (int b = 0; b < NB; ++b) load_batch<VEC, T>(s[b], sbase, b, nvec, pol_first, hint);
+            }
+            Moments mc = {0.f, 0.f, 0.f}, ms = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int b = 0; b < kBatches; ++b) batch_moments<VEC, T>(ms, s[b], b, nvec);
-                ms = block_merge<T>(ms, scratch[1]);
+            for (int b = 0; b < NB; ++b) batch_moments<VEC, T>(mc, c[b], b, nvec);
+            mc = warp_merge(mc);
+            if (has_style) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) batch_moments<VEC, T>(ms, s[b], b, nvec);
+                ms = warp_merge(ms);
             }
-            mc = block_merge<T>(mc, scratch[0]);
-
-            if (threadIdx.x == 0) {
-                const int64_t slot = it.plane * p.ipp + it.chunk;
-                __stcg(&p.part_c[slot], make_float2(mc.mean, mc.m2));
-                if (p.style != nullptr) __stcg(&p.part_s[slot], make_float2(ms.mean, ms.m2));
-                __threadfence();
-                int old = atomicAdd(&p.done[it.plane], 1);
-                s_last = (old == p.ipp - 1);
+            if (lane == 0) {
+                scratch[parity][0][warp] = mc;
+                scratch[parity][1][warp] = ms;
             }
+            if (threadIdx.x == 0) s_next[parity ^ 1u] = nxt;
             __syncthreads();
-            if (s_last && threadIdx.x < 32) {
-                // last statistics item of this plane: merge the chunk partials (one warp)
-                __threadfence();
-                Moments tc = {0.f, 0.f, 0.f}, ts = {0.f, 0.f, 0.f};
-                for (int k = threadIdx.x; k < p.ipp; k += 32) {
-                    int64_t r = p.hw - (int64_t)k * CHUNK;
-                    float n = (float)(r < CHUNK ? r : CHUNK);
-                    float2 pc = __ldcg(&p.part_c[it.plane * p.ipp + k]);
-                    tc = merge(tc, Moments{n, pc.x, pc.y});
-                    if (p.style != nullptr) {
-                        float2 ps = __ldcg(&p.part_s[it.plane * p.ipp + k]);
-                        ts = merge(ts, Moments{n, ps.x, ps.y});
-                    }
+            if (threadIdx.x == 0) {
+                Moments tc = scratch[parity][0][0], ts = scratch[parity][1][0];
+#pragma unroll
+                for (int w = 1; w < T / 32; ++w) {
+                    tc = merge(tc, scratch[parity][0][w]);
+                    ts = merge(ts, scratch[parity][1][w]);
                 }
-                tc = warp_merge(tc);
-                ts = warp_merge(ts);
-                if (threadIdx.x == 0) {
-                    float mu_c = tc.mean, sd_c = std_from(tc, hwf, p.eps);
-                    float mu_s = 0.f, sd_s = 1.f;
-                    if (p.style != nullptr) { mu_s = ts.mean; sd_s = std_from(ts, hwf, p.eps); }
-                    if (p.mean_out) p.mean_out[it.plane] = mu_c;
-                    if (p.std_out) p.std_out[it.plane] = sd_c;
-                    if (p.saved) reinterpret_cast<float4*>(p.saved)[it.plane] = make_float4(mu_c, sd_c, mu_s, sd_s);
-                    if (!p.stats_only) {
-                        __stcg(&p.coef[it.plane], make_float4(mu_c, sd_s / sd_c, mu_s, 0.f));
-                        __threadfence();
-                        st_release(&p.ready[it.plane], 1);
-                    }
-                }
+                st_slot(&p.part[it.plane * p.spp + it.chunk], make_float4(tc.mean, tc.m2, ts.mean, ts.m2));
             }
         } else {
             // ---------------- apply item: content comes back from L2, prev streams from HBM
             const float* pbase = p.prev ? p.prev + it.plane * p.hw + e0 : nullptr;
             const int64_t n_idx = it.plane / p.channels, ch = it.plane % p.channels;
             float* obase = p.out + n_idx * p.out_batch_stride + ch * p.hw + e0;
-            float c[kBatch][VEC], pv[kBatch][VEC];
-            load_batch<VEC, T>(c, cbase, 0, nvec, pol_first, hint);
-            if (pbase) load_batch<VEC, T>(pv, pbase, 0, nvec, pol_first, hint);
-            if (threadIdx.x == 0) {
-                while (ld_acquire(&p.ready[it.plane]) == 0) __nanosleep(100);
-                s_coef = __ldcg(&p.coef[it.plane]);
+            float c[NB][kBatch][VEC], pv[NB][kBatch][VEC];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                load_batch<VEC, T>(c[b], cbase, b, nvec, pol_first, hint);
+                if (pbase) load_batch<VEC, T>(pv[b], pbase, b, nvec, pol_first, hint);
+            }
+            if (warp == 0) {
+                float4 cf = ld_slot(&p.coef[it.plane]);
+                if (!slot_valid(cf)) cf = merge_plane_coef(p, it.plane, lane);
+                if (lane == 0) {
+                    s_coef[parity] = cf;
+                    s_next[parity ^ 1u] = nxt;
+                }
             }
             __syncthreads();
-            const float mu_c = s_coef.x, a = s_coef.y, mu_s = s_coef.z;
+            const float4 cf = s_coef[parity];
+            const float mu_hi = cf.x, a = cf.y, mu_s = cf.z, mu_lo = cf.w;
 #pragma unroll
-            for (int b = 0; b < kBatches; ++b) {
-                if (b > 0) {
-                    load_batch<VEC, T>(c, cbase, b, nvec, pol_first, hint);
-                    if (pbase) load_batch<VEC, T>(pv, pbase, b, nvec, pol_first, hint);
-                }
+            for (int b = 0; b < NB; ++b) {
 #pragma unroll
                 for (int j = 0; j < kBatch; ++j) {
                     int idx = (b * kBatch + j) * T + threadIdx.x;
@@ -365,18 +385,336 @@ __global__ void __launch_bounds__(kPipeThreads, MINB) adain_pipe_kernel(AdainPar
                         float o[VEC];
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) {
-                            float y = fmaf(c[j][e] - mu_c, a, mu_s);
-                            o[e] = pbase ? y + pv[j][e] : y;
+                            float y = fmaf((c[b][j][e] - mu_hi) - mu_lo, a, mu_s);
+                            o[e] = pbase ? y + pv[b][j][e] : y;
                         }
                         store_vec<VEC>(obase + (int64_t)idx * VEC, o, pol_first, hint);
                     }
                 }
             }
         }
-        __syncthreads();  // everyone is done with scratch / s_last / s_coef / s_ticket
-        if (threadIdx.x == 0) s_ticket = next;
-        __syncthreads();
-        t = s_ticket;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged pipelined kernel (the default for 16-byte-aligned planes).
+//
+// One persistent CTA per SM.  Warp 0 is the PRODUCER: one thread takes tickets (two at a time, the
+// next request always in flight), decodes them and streams the item's 16 KiB chunks into a ring of
+// shared-memory stages with cp.async.bulk (TMA, 1-D: planes are contiguous), completion counted on
+// the stage's `full` mbarrier.  So the bytes in flight live in shared memory (STAGES x 32 KiB, up to
+// 224 KiB per SM), not in registers, and nobody blocks on a global load.  Each stage has its own
+// CONSUMER group of four warps: statistics items reduce the chunk(s) to (mean, M2) and publish the
+// 16-byte slot; apply items read content (L2 hit) and prev from the stage, the plane coefficients
+// from the descriptor (the producer bulk-copied the 16-byte coefficient slot along with the data)
+// and store the result with 128-bit evict-first stores; the group then hands the stage back through
+// the `empty` mbarrier.  A third item kind, MERGE (one per plane, scheduled between the plane's
+// statistics and apply items), turns the chunk slots into the coefficient slot so that apply items
+// almost never have to wait.
+// ------------------------------------------------------------------------------------------
+constexpr int kTmaGroupWarps = 4;
+constexpr int kTmaGroupThreads = kTmaGroupWarps * 32;
+constexpr int kTmaSlotElems = kItemElems / kTmaGroupWarps;   // one warp summarises 1024 contiguous elements
+constexpr int kTmaVecs = kTmaSlotElems / 4 / 32;             // float4 per lane per tensor per item (8)
+constexpr int kTicketBatch = 8;
+
+// moments of 4*kTmaVecs register values per lane, then a warp tree.  `full` (warp-uniform): every lane
+// holds exactly 4*kTmaVecs valid values, so every merge joins equal counts and needs no division.
+__device__ __forceinline__ Moments warp_moments(const float4 (&v)[kTmaVecs], int valid_vecs, bool full) {
+    Moments m = {0.f, 0.f, 0.f};
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTmaVecs; ++j)
+        if (j < valid_vecs) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    m.n = 4.f * (float)valid_vecs;
+    m.mean = valid_vecs > 0 ? sum / m.n : 0.f;
+#pragma unroll
+    for (int j = 0; j < kTmaVecs; ++j) {
+        if (j < valid_vecs) {
+            const float d0 = v[j].x - m.mean, d1 = v[j].y - m.mean, d2 = v[j].z - m.mean, d3 = v[j].w - m.mean;
+            m.m2 = fmaf(d0, d0, m.m2);
+            m.m2 = fmaf(d1, d1, m.m2);
+            m.m2 = fmaf(d2, d2, m.m2);
+            m.m2 = fmaf(d3, d3, m.m2);
+        }
+    }
+    if (full) {
+        float half_n = 2.f * kTmaVecs;  // n/2 of the two sides being joined
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m.mean, o);
+            const float o2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+            const float d = om - m.mean;
+            m.mean = fmaf(d, 0.5f, m.mean);
+            m.m2 = fmaf(d * d, half_n, m.m2 + o2);
+            half_n *= 2.f;
+        }
+        m.n = 128.f * kTmaVecs;
+        return m;
+    }
+    return warp_merge(m);
+}
+
+struct __align__(16) StageDesc {
+    float4 coef;    // apply items: written by TMA
+    int64_t plane;
+    int kind;       // 0 statistics, 1 apply, 2 merge, -1 stop
+    int chunk;
+    int nvec;
+    int pad[3];
+};
+
+struct DecodedItem {
+    int64_t plane;
+    int kind, chunk;
+};
+
+__device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int& kind, int64_t& plane, int& chunk) {
+    const unsigned I = (unsigned)p.ipp;
+    if (p.stats_only) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
+    const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = L / 2;
+    // rounds: [S only] x (L-Lm), [S,M] x Lm, [S,M,A] x (P-L), [M,A] x (L-Lm), [A] x Lm
+    unsigned n = (L - Lm) * I;
+    if (t < n) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
+    t -= n; n = Lm * (I + 1);
+    if (t < n) {
+        const unsigned j = t / (I + 1), u = t % (I + 1);
+        if (u < I) { kind = 0; plane = (L - Lm) + j; chunk = (int)u; }
+        else { kind = 2; plane = j; chunk = 0; }
+        return;
+    }
+    t -= n; n = (P - L) * (2 * I + 1);
+    if (t < n) {
+        const unsigned j = t / (2 * I + 1), u = t % (2 * I + 1);
+        if (u < I) { kind = 0; plane = L + j; chunk = (int)u; }
+        else if (u == I) { kind = 2; plane = Lm + j; chunk = 0; }
+        else { kind = 1; plane = j; chunk = (int)(u - I - 1); }
+        return;
+    }
+    t -= n; n = (L - Lm) * (I + 1);
+    if (t < n) {
+        const unsigned j = t / (I + 1), u = t % (I + 1);
+        if (u == 0) { kind = 2; plane = (P - L + Lm) + j; chunk = 0; }
+        else { kind = 1; plane = (P - L) + j; chunk = (int)(u - 1); }
+        return;
+    }
+    t -= n;
+    kind = 1; plane = (P - Lm) + t / I; chunk = (int)(t % I);
+}
+
+// STAGES == number of consumer groups: group g owns stage g for the whole kernel, so the uses of a
+// stage are consumed in order by one group and the single-bit mbarrier parity can never alias (a group
+// that ran two phases ahead of a shared stage would pass the parity wait on stale data).
+template <int STAGES>
+__global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_kernel(AdainParams p) {
+    constexpr int kTmaGroups = STAGES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* bufs = reinterpret_cast<float*>(smem_raw);
+    StageDesc* desc = reinterpret_cast<StageDesc*>(smem_raw + (size_t)STAGES * 2 * kItemElems * sizeof(float));
+    uint64_t* full = reinterpret_cast<uint64_t*>(desc + STAGES);
+    uint64_t* empty = full + STAGES;
+    DecodedItem* dec = reinterpret_cast<DecodedItem*>(empty + STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTmaGroupWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================================================================ producer warp
+        // Tickets are taken kTicketBatch at a time (the next request is always in flight); lanes
+        // 0..kTicketBatch-1 decode one ticket each in parallel, lane 0 then issues them in order.
+        const uint64_t pol_first = policy_evict_first();
+        const uint64_t pol_last = policy_evict_last();
+        unsigned next_base = 0;
+        if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kTicketBatch) + 1u;
+        unsigned seq = 0;
+        for (;;) {
+            const unsigned base = __shfl_sync(0xffffffffu, next_base, 0);
+            if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kTicketBatch) + 1u;
+            if (lane < kTicketBatch) {
+                int kind = -1, chunk = 0;
+                int64_t plane = 0;
+                const unsigned t = base + (unsigned)lane;
+                if (t < p.total_items) decode_tma(t, p, kind, plane, chunk);
+                dec[lane].kind = kind; dec[lane].chunk = chunk; dec[lane].plane = plane;
+            }
+            __syncwarp();
+            bool finished = false;
+            if (lane == 0) {
+                for (int i = 0; i < kTicketBatch; ++i) {
+                    const int kind = dec[i].kind;
+                    if (kind < 0) {
+                        // out of work: one stop descriptor per consumer group (= per stage)
+                        for (int g = 0; g < kTmaGroups; ++g, ++seq) {
+                            const int stage = (int)(seq % STAGES);
+                            mbar_wait(&empty[stage], ((seq / STAGES) & 1u) ^ 1u);
+                            desc[stage].kind = -1;
+                            mbar_arrive(&full[stage]);
+                        }
+                        finished = true;
+                        break;
+                    }
+                    const int chunk = dec[i].chunk;
+                    const int64_t plane = dec[i].plane;
+                    const int stage = (int)(seq % STAGES);
+                    mbar_wait(&empty[stage], ((seq / STAGES) & 1u) ^ 1u);
+                    StageDesc* d = &desc[stage];
+                    const int64_t e0 = (int64_t)chunk * kItemElems;
+                    const int64_t rem = p.hw - e0;
+                    const int nvec = (int)((rem < kItemElems ? rem : kItemElems) / 4);
+                    const uint32_t bytes = (uint32_t)nvec * 16u;
+                    d->plane = plane; d->kind = kind; d->chunk = chunk; d->nvec = nvec;
+                    float* buf_a = bufs + (size_t)(stage * 2 + 0) * kItemElems;
+                    float* buf_b = bufs + (size_t)(stage * 2 + 1) * kItemElems;
+                    const float* csrc = p.content + plane * p.hw + e0;
+                    if (kind == 0) {
+                        const bool has_style = p.style != nullptr;
+                        mbar_arrive_expect_tx(&full[stage], has_style ? 2u * bytes : bytes);
+                        tma_load_1d(buf_a, csrc, bytes, &full[stage], p.stats_only ? pol_first : pol_last);
+                        if (has_style) tma_load_1d(buf_b, p.style + plane * p.hw + e0, bytes, &full[stage], pol_first);
+                    } else if (kind == 1) {
+                        const bool has_prev = p.prev != nullptr;
+                        mbar_arrive_expect_tx(&full[stage], (has_prev ? 2u * bytes : bytes) + 16u);
+                        tma_load_1d(buf_a, csrc, bytes, &full[stage], pol_first);
+                        if (has_prev) tma_load_1d(buf_b, p.prev + plane * p.hw + e0, bytes, &full[stage], pol_first);
+                        tma_load_1d(&d->coef, &p.coef[plane], 16u, &full[stage], pol_last);
+                    } else {
+                        mbar_arrive(&full[stage]);
+                    }
+                    ++seq;
+                }
+            }
+            finished = __shfl_sync(0xffffffffu, (int)finished, 0) != 0;
+            if (finished) return;
+            __syncwarp();
+        }
+    }
+
+    // ==================================================================== consumers
+    // Warp `gw` of a group owns vectors [gw*256, gw*256+256) of the item (a contiguous 4 KiB of each
+    // tensor) and publishes its own statistics slot: consumer warps never synchronise with each other.
+    const int group = (warp - 1) / kTmaGroupWarps;
+    const int gw = (warp - 1) % kTmaGroupWarps;
+    const uint64_t pol_first = policy_evict_first();
+    const bool has_style = p.style != nullptr;
+    const bool has_prev = p.prev != nullptr;
+
+    for (unsigned seq = group;; seq += kTmaGroups) {
+        const int stage = (int)(seq % STAGES);
+        const unsigned ph = (seq / STAGES) & 1u;
+        mbar_wait(&full[stage], ph);  // every lane observes the phase (async-proxy writes become visible to waiters)
+        const StageDesc* d = &desc[stage];
+        const int kind = d->kind;           // copy everything out of the descriptor: once the stage is
+        if (kind < 0) break;                // released the producer may overwrite it
+        const int64_t plane = d->plane;
+        const int chunk = d->chunk;
+        const int wvec = min(max(d->nvec - gw * (kTmaSlotElems / 4), 0), kTmaSlotElems / 4);  // this warp's vectors
+        const float4* a4 = reinterpret_cast<const float4*>(bufs + (size_t)(stage * 2 + 0) * kItemElems) + gw * (kTmaSlotElems / 4);
+        const float4* b4 = reinterpret_cast<const float4*>(bufs + (size_t)(stage * 2 + 1) * kItemElems) + gw * (kTmaSlotElems / 4);
+        // lane's vectors: j*32 + lane, j < kTmaVecs; valid while < wvec
+        const int my_vecs = wvec > lane ? min((wvec - lane + 31) / 32, kTmaVecs) : 0;
+        const bool full_warp = wvec == kTmaSlotElems / 4;
+
+        if (kind == 0) {
+            // ---------------- statistics: moments of this warp's 4 KiB of content (and style)
+            float4 v[kTmaVecs];
+#pragma unroll
+            for (int j = 0; j < kTmaVecs; ++j) v[j] = j < my_vecs ? a4[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const Moments mc = warp_moments(v, my_vecs, full_warp);
+            Moments ms = {0.f, 0.f, 0.f};
+            if (has_style) {
+#pragma unroll
+                for (int j = 0; j < kTmaVecs; ++j) v[j] = j < my_vecs ? b4[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                ms = warp_moments(v, my_vecs, full_warp);
+            }
+            // the stage has been consumed (the moments depend on every value read from it)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[stage]);
+                if (wvec > 0)
+                    st_slot(&p.part[plane * p.spp + (int64_t)chunk * kTmaGroupWarps + gw],
+                            make_float4(mc.mean, mc.m2, ms.mean, ms.m2));
+            }
+        } else if (kind == 1) {
+            // ---------------- apply: out = (c - mu_c) * a + mu_s (+ prev)
+            float4 cf = d->coef;
+            if (!slot_valid(cf)) {  // merge item still running somewhere: wait for its result
+                if (lane == 0) {
+                    const uint64_t t0 = global_timer_ns();
+                    do {
+                        __nanosleep(40);
+                        cf = ld_slot(&p.coef[plane]);
+                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                    } while (!slot_valid(cf));
+                }
+                cf.x = __shfl_sync(0xffffffffu, cf.x, 0);
+                cf.y = __shfl_sync(0xffffffffu, cf.y, 0);
+                cf.z = __shfl_sync(0xffffffffu, cf.z, 0);
+                cf.w = __shfl_sync(0xffffffffu, cf.w, 0);
+            }
+            const float mu_hi = cf.x, a = cf.y, mu_s = cf.z, mu_lo = cf.w;
+            const int64_t n_idx = plane / p.channels, ch = plane % p.channels;
+            float4* o4 = reinterpret_cast<float4*>(p.out + n_idx * p.out_batch_stride + ch * p.hw +
+                                                   (int64_t)chunk * kItemElems) + gw * (kTmaSlotElems / 4);
+#pragma unroll
+            for (int j = 0; j < kTmaVecs; ++j) {
+                if (j < my_vecs) {
+                    const float4 c = a4[j * 32 + lane];
+                    float4 o;
+                    o.x = fmaf((c.x - mu_hi) - mu_lo, a, mu_s);
+                    o.y = fmaf((c.y - mu_hi) - mu_lo, a, mu_s);
+                    o.z = fmaf((c.z - mu_hi) - mu_lo, a, mu_s);
+                    o.w = fmaf((c.w - mu_hi) - mu_lo, a, mu_s);
+                    if (has_prev) {
+                        const float4 q = b4[j * 32 + lane];
+                        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                    }
+                    stg_f4_hint(reinterpret_cast<float*>(o4 + j * 32 + lane), o, pol_first);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        } else {
+            // ---------------- merge: statistics slots of one plane -> coefficient slot
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (gw == 0) merge_plane_coef(p, plane, lane);
+        }
+    }
+}
+
+// statistics-only finalisation (calc_mean_std on large planes): one warp per plane merges the
+// chunk partials written by the preceding adain_pipe_kernel launch (stream order, no flags).
+__global__ void __launch_bounds__(256) stats_finalize_kernel(AdainParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t plane = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (plane >= p.planes) return;
+    // generic in ipp: two passes over the slots (they are final: previous launch in stream order)
+    const float4* slots = p.part + plane * p.spp;
+    const float k0 = __ldcg(slots).x;
+    float d = 0.f;
+    for (int k = lane; k < p.spp; k += 32) {
+        const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+        d = fmaf((float)(rem < p.slot_elems ? rem : p.slot_elems), __ldcg(slots + k).x - k0, d);
+    }
+    d = warp_sum(d) / (float)p.hw;
+    float m2 = 0.f;
+    for (int k = lane; k < p.spp; k += 32) {
+        const float4 v = __ldcg(slots + k);
+        const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+        const float e = v.x - k0 - d;
+        m2 += v.y + (float)(rem < p.slot_elems ? rem : p.slot_elems) * e * e;
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+        if (p.mean_out) p.mean_out[plane] = k0 + d;
+        if (p.std_out) p.std_out[plane] = sqrtf(m2 / ((float)p.hw - 1.f) + p.eps);
     }
 }
 
@@ -632,20 +970,15 @@ __global__ void __launch_bounds__(256) plane_affine_kernel(const float* __restri
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct PipeLayout {
-    size_t counters_bytes;  // ticket + done + ready (zeroed before launch)
-    size_t coef_off, part_c_off, part_s_off, total;
+    size_t coef_off, part_off, total;  // ticket, coef, partial slots; everything is memset to 0xFF
 };
 
 PipeLayout pipe_layout(int64_t planes, int64_t hw) {
-    // sized for the scalar (VEC=1) chunking, the smaller chunk => the larger item count
-    const int64_t chunk = (int64_t)kPipeThreads * kPerThread;
-    const int64_t ipp = (hw + chunk - 1) / chunk;
+    const int64_t spp = (hw + kTmaSlotElems - 1) / kTmaSlotElems;
     PipeLayout l;
-    l.counters_bytes = align_up(256 + (size_t)planes * 2 * sizeof(int), 256);
-    l.coef_off = l.counters_bytes;
-    l.part_c_off = align_up(l.coef_off + (size_t)planes * sizeof(float4), 256);
-    l.part_s_off = align_up(l.part_c_off + (size_t)planes * ipp * sizeof(float2), 256);
-    l.total = align_up(l.part_s_off + (size_t)planes * ipp * sizeof(float2), 256);
+    l.coef_off = 256;
+    l.part_off = align_up(l.coef_off + (size_t)planes * sizeof(float4), 256);
+    l.total = align_up(l.part_off + (size_t)planes * spp * sizeof(float4), 256);
     return l;
 }
 
@@ -661,9 +994,41 @@ int launch_direct(const AdainParams& p, cudaStream_t stream) {
     return RPST_OK;
 }
 
+template <int VEC, int MINB>
+int launch_pipe_variant(const AdainParams& p, cudaStream_t stream) {
+    // every CTA must be co-resident (apply items poll slots written by other CTAs)
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int nb = 0;
+        RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, adain_pipe_kernel<VEC, MINB>, kPipeThreads, 0));
+        blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    const int per_sm = blocks_per_sm < MINB ? blocks_per_sm : MINB;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    if (grid > (int64_t)p.total_items) grid = p.total_items;
+    adain_pipe_kernel<VEC, MINB><<<(int)grid, kPipeThreads, 0, stream>>>(p);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
+template <int STAGES>
+int launch_tma_variant(const AdainParams& p, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)STAGES * 2 * kItemElems * sizeof(float) + STAGES * sizeof(StageDesc) +
+                            2 * STAGES * sizeof(uint64_t) + kTicketBatch * sizeof(DecodedItem);
+    static bool configured = false;
+    if (!configured) {
+        RPST_CUDA(cudaFuncSetAttribute(adain_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t grid = sm_count();
+    if (grid > (int64_t)p.total_items) grid = p.total_items;
+    adain_tma_kernel<STAGES><<<(int)grid, 32 + STAGES * kTmaGroupThreads, smem, stream>>>(p);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
 template <int VEC>
 int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    constexpr int64_t CHUNK = (int64_t)kPipeThreads * kPerThread * VEC;
     const PipeLayout l = pipe_layout(p.planes, p.hw);
     if (ws == nullptr || ws_bytes < l.total) {
         set_error("adain: workspace too small (%zu < %zu bytes)", ws_bytes, l.total);
@@ -671,26 +1036,45 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     }
     RPST_CHECK_ARG(aligned16(ws), "adain: workspace must be 16-byte aligned");
     char* base = static_cast<char*>(ws);
-    p.ipp = (int)((p.hw + CHUNK - 1) / CHUNK);
+    p.ipp = (int)((p.hw + kItemElems - 1) / kItemElems);
     const int64_t plane_bytes = p.hw * (int64_t)sizeof(float);
     int64_t lag = (g_tuning.lag_bytes + plane_bytes - 1) / plane_bytes;
     if (lag < 3) lag = 3;
     p.lag = (int)(lag < p.planes ? lag : p.planes);
-    const int64_t total = p.planes * p.ipp * (p.stats_only ? 1 : 2);
+    const bool use_tma = VEC == 4 && g_tuning.path == 0;
+    p.slot_elems = use_tma ? kTmaSlotElems : kItemElems;
+    p.spp = (int)((p.hw + p.slot_elems - 1) / p.slot_elems);
+    const int64_t total = p.stats_only ? p.planes * p.ipp : p.planes * (2ll * p.ipp + (use_tma ? 1 : 0));
     RPST_CHECK_ARG(total < (1ll << 31), "adain: too many work items (%lld); split the call", (long long)total);
     p.total_items = (unsigned)total;
     p.ticket = reinterpret_cast<unsigned*>(base);
-    p.done = reinterpret_cast<int*>(base + 256);
-    p.ready = p.done + p.planes;
     p.coef = reinterpret_cast<float4*>(base + l.coef_off);
-    p.part_c = reinterpret_cast<float2*>(base + l.part_c_off);
-    p.part_s = reinterpret_cast<float2*>(base + l.part_s_off);
-    RPST_CUDA(cudaMemsetAsync(base, 0, l.counters_bytes, stream));
-    int64_t grid = (int64_t)sm_count() * g_tuning.ctas_per_sm;
-    if (grid > total) grid = total;
-    if (g_tuning.ctas_per_sm >= 4) adain_pipe_kernel<VEC, 4><<<(int)grid, kPipeThreads, 0, stream>>>(p);
-    else adain_pipe_kernel<VEC, 3><<<(int)grid, kPipeThreads, 0, stream>>>(p);
-    RPST_CUDA(cudaGetLastError());
+    p.part = reinterpret_cast<float4*>(base + l.part_off);
+    RPST_CUDA(cudaMemsetAsync(base, 0xff, l.part_off + (size_t)p.planes * p.spp * sizeof(float4), stream));
+    int rc;
+    if (use_tma) {
+        switch ((int)g_tuning.stages) {
+            case 2: rc = launch_tma_variant<2>(p, stream); break;
+            case 3: rc = launch_tma_variant<3>(p, stream); break;
+            case 4: rc = launch_tma_variant<4>(p, stream); break;
+            case 5: rc = launch_tma_variant<5>(p, stream); break;
+            case 7: rc = launch_tma_variant<7>(p, stream); break;
+            default: rc = launch_tma_variant<6>(p, stream); break;
+        }
+    } else {
+        switch ((int)g_tuning.ctas_per_sm) {
+            case 2: rc = launch_pipe_variant<VEC, 2>(p, stream); break;
+            case 3: rc = launch_pipe_variant<VEC, 3>(p, stream); break;
+            case 5: rc = launch_pipe_variant<VEC, 5>(p, stream); break;
+            case 6: rc = launch_pipe_variant<VEC, 6>(p, stream); break;
+            default: rc = launch_pipe_variant<VEC, 4>(p, stream); break;
+        }
+    }
+    if (rc != RPST_OK) return rc;
+    if (p.stats_only) {
+        stats_finalize_kernel<<<(unsigned)((p.planes + 7) / 8), 256, 0, stream>>>(p);
+        RPST_CUDA(cudaGetLastError());
+    }
     return RPST_OK;
 }
 
@@ -768,10 +1152,18 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     if (!strcmp(name, "adain_lag_bytes")) slot = &g_tuning.lag_bytes;
     else if (!strcmp(name, "adain_hints")) slot = &g_tuning.hints;
     else if (!strcmp(name, "adain_ctas_per_sm")) slot = &g_tuning.ctas_per_sm;
+    else if (!strcmp(name, "adain_path")) slot = &g_tuning.path;
+    else if (!strcmp(name, "adain_stages")) slot = &g_tuning.stages;
     if (!slot) return 0;
     if (set) *slot = v;
     if (out) *out = *slot;
     return 1;
+}
+
+int64_t adain_tuning_value(const char* name) {
+    int64_t v = 0;
+    set_adain_tuning(name, 0, false, &v);
+    return v;
 }
 
 }  // namespace rpst

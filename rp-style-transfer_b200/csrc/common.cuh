@@ -121,6 +121,32 @@ __device__ __forceinline__ Moments block_merge(Moments m, Moments* scratch) {
     return t;
 }
 
+struct MomentsD {
+    double n, mean, m2;
+};
+__device__ __forceinline__ MomentsD merge(MomentsD a, MomentsD b) {
+    double n = a.n + b.n;
+    double inv = n > 0.0 ? 1.0 / n : 0.0;
+    double d = b.mean - a.mean;
+    double w = b.n * inv;
+    MomentsD r;
+    r.n = n;
+    r.mean = a.mean + d * w;
+    r.m2 = a.m2 + b.m2 + d * d * a.n * w;
+    return r;
+}
+__device__ __forceinline__ MomentsD warp_merge(MomentsD m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MomentsD other;
+        other.n = __shfl_xor_sync(0xffffffffu, m.n, o);
+        other.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
+        other.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+        m = merge(m, other);
+    }
+    return m;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -71,7 +71,11 @@ def test_large_mean_small_std_is_stable(rpst):
     s = torch.randn(1, 2, 512, 512, generator=g)
     want = R.adain(c, s, dtype=torch.float64)
     got = rpst.adaptive_instance_normalization(dev(c), dev(s))
-    assert R.rel_l2(got, want) < 1e-3
+    # the reference's own fp32 path cannot represent the mean of such a plane better than ulp(1000);
+    # the kernel carries the mean as hi+lo and must do at least as well as eager fp32, and < 1e-3
+    eager_err = R.rel_l2(R.adain(c, s), want)
+    err = R.rel_l2(got, want)
+    assert err < 1e-3 and err <= max(eager_err, 1e-4), (err, eager_err)
 
 
 def test_concat_write_and_alias(rpst):
@@ -156,15 +160,24 @@ def test_properties_at_full_plane_size(rpst):
 
 
 def test_tuning_variants_agree(rpst):
+    """Scheduling knobs must not change results: bit-identical within a kernel path (the reduction
+    tree is fixed), and to fp32 rounding between the TMA-staged and the register-staged path."""
     c, s = R.synth_features((2, 8, 512, 512), cfg=3, device="cuda")
-    base = rpst.adaptive_instance_normalization(c, s)
-    old = {k: rpst.get_tuning(k) for k in ("adain_lag_bytes", "adain_hints", "adain_ctas_per_sm")}
+    keys = ("adain_lag_bytes", "adain_hints", "adain_ctas_per_sm", "adain_path", "adain_stages")
+    old = {k: rpst.get_tuning(k) for k in keys}
     try:
-        for lag, hints, ctas in [(1 << 20, 0, 4), (64 << 20, 1, 3), (1, 1, 4)]:
-            rpst.set_tuning("adain_lag_bytes", lag)
-            rpst.set_tuning("adain_hints", hints)
-            rpst.set_tuning("adain_ctas_per_sm", ctas)
-            assert torch.equal(rpst.adaptive_instance_normalization(c, s), base)
+        ref = {}
+        for lag, hints, ctas, path, stages in [(16 << 20, 1, 4, 1, 6), (1 << 20, 0, 4, 1, 6), (64 << 20, 1, 3, 1, 6),
+                                               (1, 1, 6, 1, 6), (16 << 20, 1, 4, 0, 6), (8 << 20, 1, 2, 0, 2),
+                                               (32 << 20, 0, 2, 0, 7), (1, 1, 2, 0, 4)]:
+            for k, v in zip(keys, (lag, hints, ctas, path, stages)):
+                rpst.set_tuning(k, v)
+            out = rpst.adaptive_instance_normalization(c, s)
+            if path in ref:
+                assert torch.equal(out, ref[path]), (lag, hints, ctas, path, stages)
+            else:
+                ref[path] = out
+        assert R.rel_l2(ref[0], ref[1]) < 1e-6
     finally:
         for k, v in old.items():
             rpst.set_tuning(k, v)

@@ -1,0 +1,112 @@
+"""GPU parity tests for segment AdaIN and the SE gate (a15)."""
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TIGHT = 5e-6
+
+
+@pytest.fixture(scope="module")
+def rpst():
+    import rpst as m
+    return m
+
+
+def test_golden(rpst, golden):
+    g = golden("seg_adain")
+    out = rpst.adaptive_instance_normalization_with_segment(g["content"].cuda(), g["style"].cuda(),
+                                                            g["c_labels"], g["s_labels"].numpy())
+    assert R.rel_l2(out, g["out"]) < TIGHT
+    valid = R.segment_label_validity(g["c_labels"], g["s_labels"])
+    for lab, ok in valid.items():
+        if not ok:  # pass-through pixels are bit-identical
+            m = (g["c_labels"] == lab).reshape(-1)
+            assert torch.equal(out.cpu().reshape(6, -1)[:, m], g["content"].reshape(6, -1)[:, m])
+
+
+@pytest.mark.parametrize("shape_c,shape_s,block", [((1, 4, 64, 64), (1, 4, 64, 64), 16), ((2, 3, 96, 128), (2, 3, 80, 60), 8),
+                                                   ((1, 2, 37, 41), (1, 2, 50, 33), 5), ((2, 2, 256, 512), (2, 2, 256, 512), 32),
+                                                   ((1, 2, 128, 128), (1, 2, 128, 128), 1)])
+def test_vs_oracle(rpst, shape_c, shape_s, block):
+    n = shape_c[0]
+    c = torch.relu(torch.randn(shape_c, generator=torch.Generator().manual_seed(1)) + 0.5)
+    s = torch.relu(torch.randn(shape_s, generator=torch.Generator().manual_seed(2)) * 2 + 1)
+    cl = R.synth_labels(n, shape_c[2], shape_c[3], classes=6, block=block, seed=4000)
+    sl = R.synth_labels(n, shape_s[2], shape_s[3], classes=6, block=block, seed=5000)
+    cl[:, :2, :3] = 255            # ignore label, tiny region -> unusable
+    cl[:, 5:, :] [cl[:, 5:, :] == 4] = 17   # a label absent from the style map
+    want = R.seg_adain_batch(c, s, cl, sl, dtype=torch.float64)
+    got, info = rpst.seg_adain_batch(c.cuda(), s.cuda(), cl.cuda(), sl.cuda(), return_info=True)
+    assert R.rel_l2(got, want) < TIGHT
+    prev = torch.randn(shape_c)
+    got2 = rpst.seg_adain_batch(c.cuda(), s.cuda(), cl.cuda(), sl.cuda(), prev=prev.cuda())
+    assert R.rel_l2(got2, want + prev.double()) < TIGHT
+    for i in range(n):
+        valid = R.segment_label_validity(cl[i], sl[i])
+        for lab in range(256):
+            assert int(info[i, lab, 0]) == int((cl[i] == lab).sum())
+            assert int(info[i, lab, 1]) == int((sl[i] == lab).sum())
+            if lab in valid:
+                assert bool(info[i, lab, 2]) == valid[lab]
+
+
+def test_do_mask_stylized_matches_per_sample_loop(rpst):
+    c, s = R.synth_features((3, 4, 64, 64), cfg=8)
+    cl = R.synth_labels(3, 64, 64, classes=4, block=16, seed=4001)
+    sl = R.synth_labels(3, 64, 64, classes=4, block=16, seed=5001)
+    got = rpst.do_mask_stylized(c.cuda(), s.cuda(), [m for m in cl], [m.numpy() for m in sl])
+    assert R.rel_l2(got, R.seg_adain_batch(c, s, cl, sl, dtype=torch.float64)) < TIGHT
+
+
+def test_large_offsets_per_label(rpst):
+    # label regions at very different levels: a single per-plane shift would lose the small one
+    c = torch.zeros(1, 1, 64, 64)
+    cl = torch.zeros(1, 64, 64, dtype=torch.uint8)
+    cl[:, :, 32:] = 1
+    g = torch.Generator().manual_seed(0)
+    c[..., :32] = 1000.0 + 0.5 * torch.randn(64, 32, generator=g)
+    c[..., 32:] = 0.01 * torch.randn(64, 32, generator=g)
+    s = torch.randn(1, 1, 64, 64, generator=g)
+    want = R.seg_adain_batch(c, s, cl, cl.clone(), dtype=torch.float64)
+    got = rpst.seg_adain_batch(c.cuda(), s.cuda(), cl.cuda(), cl.cuda())
+    assert R.rel_l2(got, want) < 1e-3
+
+
+def test_config5_plane_properties(rpst):
+    """1024x2048 planes (BASELINE configs[4]), 19 classes in 32x32 tiles: every usable label region
+    of the output carries the style region's statistics; unusable regions are untouched."""
+    n, ch, h, w = 1, 8, 1024, 2048
+    c, s = R.synth_features((n, ch, h, w), cfg=5, device="cuda")
+    cl = R.synth_labels(n, h, w, classes=19, block=32, seed=4000, device="cuda")
+    sl = R.synth_labels(n, h, w, classes=19, block=32, seed=5000, device="cuda")
+    cl[:, :3, :3] = 255
+    out, info = rpst.seg_adain_batch(c, s, cl, sl, return_info=True)
+    assert int(info[0, 255, 2]) == 0
+    m255 = (cl[0] == 255)
+    assert torch.equal(out[0][:, m255], c[0][:, m255])
+    for lab in (0, 7, 18):
+        assert int(info[0, lab, 2]) == 1
+        mo = out[0][:, cl[0] == lab].double()
+        ms = s[0][:, sl[0] == lab].double()
+        assert R.rel_l2(mo.mean(1), ms.mean(1)) < 1e-4
+        assert R.rel_l2(mo.std(1), ms.std(1)) < 1e-3
+    want = R.seg_adain(c[:, :1].cpu(), s[:, :1].cpu(), cl[0].cpu(), sl[0].cpu(), dtype=torch.float64)
+    assert R.rel_l2(out[:, :1], want) < TIGHT
+
+
+def test_se_layer(rpst, golden):
+    g = golden("se")
+    m = rpst.SELayer(32, reduction=16).cuda()
+    m.load_state_dict({"fc.0.weight": g["w1"], "fc.2.weight": g["w2"]})
+    with torch.no_grad():
+        out = m(g["x"].cuda())
+    assert R.rel_l2(out, g["out"]) < 1e-5
+    assert R.rel_l2(m.attention_map, g["gate"]) < 1e-5
+    x = g["x"].cuda().requires_grad_()
+    m(x).sum().backward()
+    xr = g["x"].double().requires_grad_()
+    gate = torch.sigmoid(torch.relu(xr.mean((2, 3)) @ g["w1"].double().t()) @ g["w2"].double().t())
+    (xr * gate[:, :, None, None]).sum().backward()
+    assert R.rel_l2(x.grad, xr.grad) < 1e-4
