@@ -117,6 +117,48 @@ RPST_API int rpst_seg_adain_fwd(const float* content, const float* style, const 
                        int64_t hw_c, int64_t hw_s, float eps, int32_t* label_info, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a12 cal_dist(A, B)                                                  network/base.py:349-360
+ *   a [d,m], b [d,n] (d-dimensional column vectors) -> out [m,n] = |a_i|^2 + |b_j|^2 - 2 a_i.b_j
+ *   (tensor cores, bf16x3 = fp32-grade accumulation).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_pairwise_sqdist_workspace_bytes(int64_t d, int64_t m, int64_t n);
+RPST_API int rpst_pairwise_sqdist(const float* a, const float* b, int64_t d, int64_t m, int64_t n, float* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a13 cal_affinity_map(content_feat, style_feat, k, reverse)          network/base.py:317-346
+ * a14 MRFLoss(k, mean).forward(content_feat, style_feat)              network/mrf_rp.py:12-23
+ *
+ * content/style [c, l] (one sample, l = H*W).  Channel-L2-normalise (eps 1e-12), l x l cosine map on
+ * the tensor cores, top-k along both axes:
+ *   idx_dim0 [k,l] int64  topk(map, k, dim=0).indices  (for every style position the best content ones)
+ *   idx_dim1 [l,k] int64  topk(map, k, dim=1).indices  (for every content position the best style ones)
+ *   affinity [l,l] or NULL: the dense binary map (1 where (i,j) is in either set)
+ *   loss     [1]   or NULL: sum(affinity * sqdist) / (l*k)   (loss_mean_over_all != 0: / (l*l))
+ * reverse != 0 negates the map first (network/base.py:326-327).  passes: 3 = bf16x3 (index-exact on
+ * tie-free inputs), 1 = plain bf16.  1 <= k <= 8.
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_mrf_workspace_bytes(int64_t c, int64_t l, int k);
+RPST_API int rpst_mrf_match(const float* content, const float* style, int64_t c, int64_t l, int k, int reverse,
+                   int passes, int64_t* idx_dim0, int64_t* idx_dim1, float* affinity, float* loss,
+                   int loss_mean_over_all, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks shared by the contraction kernels (exposed for tests and for callers that want to
+ * keep packed operands around): fp32 matrix -> bf16 hi/lo operand tiles, and D = alpha*A.B^T
+ * (+row_add[i] +col_add[j]) on tcgen05 with fp32 accumulation in TMEM.
+ *   x element (r, kk) is read at x[r*stride_r + kk*stride_k]; row_scale [rows] or NULL;
+ *   hi/lo: rpst_packed_operand_bytes(rows, k) bytes each, 128-byte aligned (lo may be NULL);
+ *   passes 1 (bf16) or 3 (bf16x3).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_packed_operand_bytes(int64_t rows, int64_t k);
+RPST_API int rpst_pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                      const float* row_scale, void* hi, void* lo, void* stream);
+RPST_API int rpst_gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out,
+                     int64_t m, int64_t n, int64_t k, int64_t ldo, int passes, float alpha,
+                     const float* row_add, const float* col_add, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ from .functional import (adain_blend, adain_concat, adaptive_instance_normalizat
                          mean_variance_norm, plane_affine)
 
 from .modules import SELayer
+from .mrf import MRFLoss, cal_affinity_map, cal_dist, mrf_match, packed_gemm
 from .segment import adaptive_instance_normalization_with_segment, do_mask_stylized, load_label_map, seg_adain_batch
 
 AdaIN = adaptive_instance_normalization

@@ -34,6 +34,13 @@ SIGNATURES = {
     "rpst_adain_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "rpst_plane_affine": (c_int, [P, P, P, P, c_int64, c_int64, P]),
     "rpst_seg_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "rpst_pairwise_sqdist_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_pairwise_sqdist": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, c_size_t, P]),
+    "rpst_mrf_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "rpst_mrf_match": (c_int, [P, P, c_int64, c_int64, c_int, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
+    "rpst_packed_operand_bytes": (c_size_t, [c_int64, c_int64]),
+    "rpst_pack_operand": (c_int, [P, c_int64, c_int64, c_int64, c_int64, P, P, P, P]),
+    "rpst_gemm_packed": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, P, P]),
     "rpst_seg_adain_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
 }
 

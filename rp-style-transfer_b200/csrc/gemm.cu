@@ -1,0 +1,263 @@
+// Dense-contraction building blocks on the 5th-gen tensor cores (tcgen05 + TMEM), used by the MRF
+// normalised-cross-correlation, the WCT colouring apply and (as a reference point) SANet:
+//
+//   pack_operand_kernel   fp32 matrix (any row/column stride, optional per-row scale) -> bf16 hi (+lo)
+//                         operand tiles in the K-major SW128 tile format of umma.cuh
+//   gemm_packed_kernel    D[M,N] (fp32) = alpha * A.B^T (+ row_add[i] + col_add[j]) with A [M,K], B [N,K]
+//                         given as packed tiles.  precision passes: 1 = bf16 x bf16; 3 = "bf16x3"
+//                         (hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM, ~2^-16 relative error,
+//                         i.e. fp32-grade results at one third of the bf16 tensor rate).
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 6 warps):
+//   warp 0 / 1 thread : TMA producer — one 1-D bulk copy per 16 KiB operand tile into a 4-stage ring
+//   warp 1            : allocates TMEM; 1 thread issues tcgen05.mma (4 x K=16 per stage) and commits
+//                       the stage back to the producer / the accumulator to the epilogue
+//   warps 2..5        : epilogue — tcgen05.ld (each warp its 32-lane TMEM quarter), scale/add, store
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace rpst {
+namespace {
+
+// ------------------------------------------------------------------------------------------ pack
+struct PackParams {
+    const float* x;
+    int64_t rows, k;            // logical extent
+    int64_t stride_r, stride_k; // element strides of x
+    const float* row_scale;     // may be null
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;          // may be null
+    int64_t row_tiles, k_tiles;
+};
+
+// One thread produces one 16-byte chunk (8 consecutive k of one row).  Threads of a warp walk the
+// unit-stride direction of the source so the fp32 reads coalesce.
+__global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
+    const int64_t tile = blockIdx.x;               // (row tile, k tile)
+    const int64_t rb = tile / p.k_tiles, kb = tile % p.k_tiles;
+    char* hi_tile = reinterpret_cast<char*>(p.hi) + tile * kTileBytes;
+    char* lo_tile = p.lo ? reinterpret_cast<char*>(p.lo) + tile * kTileBytes : nullptr;
+    for (int item = threadIdx.x; item < kTileRows * 8; item += blockDim.x) {
+        int r, c;
+        if (p.stride_r == 1) { r = item % kTileRows; c = item / kTileRows; }   // MN-major source
+        else { c = item % 8; r = item / 8; }                                   // K-major source
+        const int64_t row = rb * kTileRows + r;
+        const int64_t k0 = kb * kTileK + c * 8;
+        const float sc = (p.row_scale && row < p.rows) ? __ldg(p.row_scale + row) : 1.f;
+        __align__(16) __nv_bfloat16 h[8];
+        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = 0.f;
+            if (row < p.rows && k0 + e < p.k) v = __ldg(p.x + row * p.stride_r + (k0 + e) * p.stride_k) * sc;
+            split_bf16(v, h[e], l[e]);
+        }
+        const uint32_t off = tile_chunk_offset(r, c);
+        *reinterpret_cast<uint4*>(hi_tile + off) = *reinterpret_cast<const uint4*>(h);
+        if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ gemm
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 192;
+
+struct GemmParams {
+    const __nv_bfloat16* a_hi;
+    const __nv_bfloat16* a_lo;
+    const __nv_bfloat16* b_hi;
+    const __nv_bfloat16* b_lo;
+    float* out;
+    int64_t m, n;        // valid output extent
+    int64_t ldo;         // output row stride (elements)
+    int k_tiles;         // K / 64 (padded)
+    int passes;          // 1 or 3
+    float alpha;
+    const float* row_add;  // [m] or null
+    const float* col_add;  // [n] or null
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams p) {
+    constexpr int B_TILES = BN / kTileRows;                         // 16 KiB B tiles per stage
+    constexpr uint32_t STAGE_BYTES = kTileBytes * (1 + B_TILES);
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operand tiles must start on a 1024-byte boundary of the shared address space
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full[kGemmStages], empty[kGemmStages], acc_full;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.y, nb = blockIdx.x;
+    const int total_kb = p.k_tiles * p.passes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, BN);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_acc = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_last();   // operands are re-read by other CTAs: keep in L2
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait(&empty[s], ((kb / kGemmStages) & 1) ^ 1);
+                const int pass = kb / p.k_tiles, kk = kb % p.k_tiles;
+                const __nv_bfloat16* a_src = pass == 2 ? p.a_lo : p.a_hi;
+                const __nv_bfloat16* b_src = pass == 1 ? p.b_lo : p.b_hi;
+                unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_1d(st, reinterpret_cast<const char*>(a_src) + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
+                            kTileBytes, &full[s], pol);
+#pragma unroll
+                for (int t = 0; t < B_TILES; ++t)
+                    tma_load_1d(st + kTileBytes * (1 + t),
+                                reinterpret_cast<const char*>(b_src) +
+                                    (((int64_t)nb * B_TILES + t) * p.k_tiles + kk) * kTileBytes,
+                                kTileBytes, &full[s], pol);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait(&full[s], (kb / kGemmStages) & 1);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + kTileBytes;
+#pragma unroll
+                for (int k = 0; k < kTileK / kUmmaK; ++k) {
+                    // B rows beyond 128 live in the next 16 KiB tile: same SBO (1024 B per 8 rows) holds
+                    umma_bf16_ss(tmem_acc, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                                 umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, kb > 0 || k > 0);
+                }
+                umma_commit(&empty[s]);                      // stage free once these MMAs have read it
+                if (kb == total_kb - 1) umma_commit(&acc_full);  // accumulator complete
+            }
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int q = warp & 3;
+        mbar_wait(&acc_full, 0);
+        tcgen05_fence_after();
+        const int64_t row = (int64_t)mb * 128 + q * 32 + lane;
+        const float radd = (p.row_add && row < p.m) ? __ldg(p.row_add + row) : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int64_t col0 = (int64_t)nb * BN + c0;
+            if (row < p.m) {
+                float* dst = p.out + row * p.ldo + col0;
+                if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = fmaf(p.alpha, v[j + 0], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 0) : 0.f));
+                        o.y = fmaf(p.alpha, v[j + 1], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 1) : 0.f));
+                        o.z = fmaf(p.alpha, v[j + 2], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 2) : 0.f));
+                        o.w = fmaf(p.alpha, v[j + 3], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 3) : 0.f));
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.n)
+                            dst[j] = fmaf(p.alpha, v[j], radd + (p.col_add ? __ldg(p.col_add + col0 + j) : 0.f));
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_acc, BN);
+    }
+}
+
+}  // namespace
+
+// ---- internal host API (used by mrf.cu / wct.cu) -----------------------------------------------
+size_t packed_operand_bytes(int64_t rows, int64_t k) {
+    const int64_t rt = (rows + kTileRows - 1) / kTileRows, kt = (k + kTileK - 1) / kTileK;
+    return (size_t)rt * kt * kTileBytes;
+}
+
+int pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k, const float* row_scale,
+                 void* hi, void* lo, cudaStream_t stream) {
+    PackParams p{};
+    p.x = x; p.rows = rows; p.k = k; p.stride_r = stride_r; p.stride_k = stride_k; p.row_scale = row_scale;
+    p.hi = static_cast<__nv_bfloat16*>(hi);
+    p.lo = static_cast<__nv_bfloat16*>(lo);
+    p.row_tiles = (rows + kTileRows - 1) / kTileRows;
+    p.k_tiles = (k + kTileK - 1) / kTileK;
+    const int64_t tiles = p.row_tiles * p.k_tiles;
+    if (tiles == 0) return RPST_OK;
+    RPST_CHECK_ARG(tiles < (1ll << 31), "pack_operand: too many tiles");
+    pack_operand_kernel<<<(unsigned)tiles, 256, 0, stream>>>(p);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
+int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                const float* col_add, cudaStream_t stream) {
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "gemm_packed: passes must be 1 or 3");
+    RPST_CHECK_ARG(passes == 1 || (a_lo && b_lo), "gemm_packed: bf16x3 needs the lo operands");
+    if (m == 0 || n == 0) return RPST_OK;
+    RPST_CHECK_ARG(k > 0, "gemm_packed: K must be positive");
+    GemmParams p{};
+    p.a_hi = static_cast<const __nv_bfloat16*>(a_hi);
+    p.a_lo = static_cast<const __nv_bfloat16*>(a_lo);
+    p.b_hi = static_cast<const __nv_bfloat16*>(b_hi);
+    p.b_lo = static_cast<const __nv_bfloat16*>(b_lo);
+    p.out = out; p.m = m; p.n = n; p.ldo = ldo;
+    p.k_tiles = (int)((k + kTileK - 1) / kTileK);
+    p.passes = passes; p.alpha = alpha; p.row_add = row_add; p.col_add = col_add;
+    constexpr int BN = 128;
+    constexpr size_t smem = (size_t)kGemmStages * kTileBytes * (1 + BN / kTileRows) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + 127) / 128));
+    gemm_packed_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(p);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
+}  // namespace rpst
+
+using namespace rpst;
+
+extern "C" size_t rpst_packed_operand_bytes(int64_t rows, int64_t k) { return packed_operand_bytes(rows, k); }
+
+extern "C" int rpst_pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                                 const float* row_scale, void* hi, void* lo, void* stream) {
+    RPST_CHECK_ARG(rows >= 0 && k >= 0, "pack_operand: negative size");
+    RPST_CHECK_ARG(rows == 0 || k == 0 || (x && hi), "pack_operand: null pointer");
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(hi) & 127u) == 0 && (reinterpret_cast<uintptr_t>(lo) & 127u) == 0,
+                   "pack_operand: tile buffers must be 128-byte aligned");
+    return pack_operand(x, rows, k, stride_r, stride_k, row_scale, hi, lo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rpst_gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out,
+                                int64_t m, int64_t n, int64_t k, int64_t ldo, int passes, float alpha,
+                                const float* row_add, const float* col_add, void* stream) {
+    RPST_CHECK_ARG(m >= 0 && n >= 0 && k >= 0 && ldo >= n, "gemm_packed: bad shape");
+    RPST_CHECK_ARG(m == 0 || n == 0 || (a_hi && b_hi && out), "gemm_packed: null pointer");
+    return gemm_packed(a_hi, a_lo, b_hi, b_lo, out, m, n, k, ldo, passes, alpha, row_add, col_add,
+                       static_cast<cudaStream_t>(stream));
+}
