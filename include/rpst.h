@@ -145,6 +145,35 @@ RPST_API int rpst_mrf_match(const float* content, const float* style, int64_t c,
                    int loss_mean_over_all, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a5  matrix_sqrt(A) / matrix_inv_sqrt(A)                             network/wct_rp.py:7-40
+ * Batched symmetric eigen-decomposition (cluster-resident one-sided Jacobi, fp64, no host sync) and
+ * V diag(s^(+-1/2)) V^T, with the reference's conditioning: `diag_add` (1e-4 in the reference) is added
+ * to the diagonal first and eigenvalues below 1e-5 are dropped.
+ *   a [batch,n,n] fp64 symmetric positive semi-definite, n <= 512;
+ *   out_sqrt / out_inv_sqrt [batch,n,n] fp64 (either may be NULL); eigenvalues [batch,n] or NULL
+ *   (unsorted); sweeps [batch] int32 or NULL (Jacobi sweeps used).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_sym_eig_fn_workspace_bytes(int64_t batch, int64_t n);
+RPST_API int rpst_sym_eig_fn(const double* a, int64_t batch, int64_t n, double diag_add, double* out_sqrt,
+                    double* out_inv_sqrt, double* eigenvalues, int32_t* sweeps, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  WCTRPNet.whiten_and_color(cF, sF, method='closed-form')          network/wct_rp.py:82-114
+ * a7  WCTRPNet.fuse(content_feats, style_feats)                        network/wct_rp.py:157-166
+ * Whole batch, no gradient (the reference detaches): centre, covariances (+I on content), transform
+ *   method 0 'closed-form': T = C^-1/2 (C^1/2 S C^1/2)^1/2 C^-1/2      method 1 'original': T = S^1/2 C^-1/2
+ * and out = T (X - mu_c) + mu_s.
+ *   content [n,c,hw_c], style [n,c,hw_s] fp32 -> out [n,c,hw_c] fp32; c <= 512.
+ *   passes 3 = bf16x3 tensor-core products (fp32-grade, default), 1 = plain bf16.
+ *   transform_out [n,c,c] fp64 or NULL.
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_wct_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s);
+RPST_API int rpst_wct_fuse(const float* content, const float* style, float* out, int64_t n, int64_t c,
+                  int64_t hw_c, int64_t hw_s, int method, int passes, double* transform_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Building blocks shared by the contraction kernels (exposed for tests and for callers that want to
  * keep packed operands around): fp32 matrix -> bf16 hi/lo operand tiles, and D = alpha*A.B^T
  * (+row_add[i] +col_add[j]) on tcgen05 with fp32 accumulation in TMEM.

@@ -41,6 +41,10 @@ SIGNATURES = {
     "rpst_packed_operand_bytes": (c_size_t, [c_int64, c_int64]),
     "rpst_pack_operand": (c_int, [P, c_int64, c_int64, c_int64, c_int64, P, P, P, P]),
     "rpst_gemm_packed": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, P, P]),
+    "rpst_sym_eig_fn_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rpst_sym_eig_fn": (c_int, [P, c_int64, c_int64, c_double, P, P, P, P, P, c_size_t, P]),
+    "rpst_wct_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "rpst_wct_fuse": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_size_t, P]),
     "rpst_seg_adain_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
 }
 

@@ -25,6 +25,7 @@ struct PackParams {
     int64_t rows, k;            // logical extent
     int64_t stride_r, stride_k; // element strides of x
     const float* row_scale;     // may be null
+    const float* row_shift;     // may be null: value subtracted before scaling (centring)
     __nv_bfloat16* hi;
     __nv_bfloat16* lo;          // may be null
     int64_t row_tiles, k_tiles;
@@ -44,12 +45,13 @@ __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
         const int64_t row = rb * kTileRows + r;
         const int64_t k0 = kb * kTileK + c * 8;
         const float sc = (p.row_scale && row < p.rows) ? __ldg(p.row_scale + row) : 1.f;
+        const float sh = (p.row_shift && row < p.rows) ? __ldg(p.row_shift + row) : 0.f;
         __align__(16) __nv_bfloat16 h[8];
         __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float v = 0.f;
-            if (row < p.rows && k0 + e < p.k) v = __ldg(p.x + row * p.stride_r + (k0 + e) * p.stride_k) * sc;
+            if (row < p.rows && k0 + e < p.k) v = (__ldg(p.x + row * p.stride_r + (k0 + e) * p.stride_k) - sh) * sc;
             split_bf16(v, h[e], l[e]);
         }
         const uint32_t off = tile_chunk_offset(r, c);
@@ -70,7 +72,9 @@ struct GemmParams {
     float* out;
     int64_t m, n;        // valid output extent
     int64_t ldo;         // output row stride (elements)
-    int k_tiles;         // K / 64 (padded)
+    int k_tiles;         // K / 64 (padded): tile pitch of the packed operands
+    int k_per_split;     // k tiles handled by one blockIdx.z slice (== k_tiles without split-K)
+    int64_t split_stride;  // elements between the partial outputs of consecutive slices
     int passes;          // 1 or 3
     float alpha;
     const float* row_add;  // [m] or null
@@ -89,7 +93,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.y, nb = blockIdx.x;
-    const int total_kb = p.k_tiles * p.passes;
+    const int k_begin = blockIdx.z * p.k_per_split;
+    const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
+    const int total_kb = k_count * p.passes;
+    float* const out = p.out + (int64_t)blockIdx.z * p.split_stride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             for (int kb = 0; kb < total_kb; ++kb) {
                 const int s = kb % kGemmStages;
                 mbar_wait(&empty[s], ((kb / kGemmStages) & 1) ^ 1);
-                const int pass = kb / p.k_tiles, kk = kb % p.k_tiles;
+                const int pass = kb / k_count, kk = k_begin + kb % k_count;
                 const __nv_bfloat16* a_src = pass == 2 ? p.a_lo : p.a_hi;
                 const __nv_bfloat16* b_src = pass == 1 ? p.b_lo : p.b_hi;
                 unsigned char* st = smem + (size_t)s * STAGE_BYTES;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             const int64_t col0 = (int64_t)nb * BN + c0;
             if (row < p.m) {
-                float* dst = p.out + row * p.ldo + col0;
+                float* dst = out + row * p.ldo + col0;
                 if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -194,10 +201,11 @@ size_t packed_operand_bytes(int64_t rows, int64_t k) {
     return (size_t)rt * kt * kTileBytes;
 }
 
-int pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k, const float* row_scale,
-                 void* hi, void* lo, cudaStream_t stream) {
+int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                       const float* row_scale, const float* row_shift, void* hi, void* lo, cudaStream_t stream) {
     PackParams p{};
     p.x = x; p.rows = rows; p.k = k; p.stride_r = stride_r; p.stride_k = stride_k; p.row_scale = row_scale;
+    p.row_shift = row_shift;
     p.hi = static_cast<__nv_bfloat16*>(hi);
     p.lo = static_cast<__nv_bfloat16*>(lo);
     p.row_tiles = (rows + kTileRows - 1) / kTileRows;
@@ -210,9 +218,26 @@ int pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int6
     return RPST_OK;
 }
 
+int pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k, const float* row_scale,
+                 void* hi, void* lo, cudaStream_t stream) {
+    return pack_operand_shift(x, rows, k, stride_r, stride_k, row_scale, nullptr, hi, lo, stream);
+}
+
+int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                       int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                       const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
+
 int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                 int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                 const float* col_add, cudaStream_t stream) {
+    return gemm_packed_splitk(a_hi, a_lo, b_hi, b_lo, out, m, n, k, ldo, passes, alpha, row_add, col_add, 1, 0, stream);
+}
+
+// splits > 1: slice z of blockIdx.z reduces k tiles [z*kps, (z+1)*kps) into out + z*split_stride (the
+// caller sums the partial outputs; every slice is non-empty).
+int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                       int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                       const float* col_add, int splits, int64_t split_stride, cudaStream_t stream) {
     RPST_CHECK_ARG(passes == 1 || passes == 3, "gemm_packed: passes must be 1 or 3");
     RPST_CHECK_ARG(passes == 1 || (a_lo && b_lo), "gemm_packed: bf16x3 needs the lo operands");
     if (m == 0 || n == 0) return RPST_OK;
@@ -224,6 +249,11 @@ int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void
     p.b_lo = static_cast<const __nv_bfloat16*>(b_lo);
     p.out = out; p.m = m; p.n = n; p.ldo = ldo;
     p.k_tiles = (int)((k + kTileK - 1) / kTileK);
+    if (splits < 1) splits = 1;
+    if (splits > p.k_tiles) splits = p.k_tiles;
+    p.k_per_split = (p.k_tiles + splits - 1) / splits;
+    splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;   // no empty slice
+    p.split_stride = split_stride;
     p.passes = passes; p.alpha = alpha; p.row_add = row_add; p.col_add = col_add;
     constexpr int BN = 128;
     constexpr size_t smem = (size_t)kGemmStages * kTileBytes * (1 + BN / kTileRows) + 1024;
@@ -232,7 +262,7 @@ int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void
         RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + 127) / 128));
+    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + 127) / 128), (unsigned)splits);
     gemm_packed_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;

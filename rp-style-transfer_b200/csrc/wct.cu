@@ -1,0 +1,212 @@
+// WCT whitening / colouring — SURVEY.md §8 a6/a7; reference: network/wct_rp.py:82-114
+// (`whiten_and_color`) and :157-166 (`fuse`: per-sample Python loop, fp64 inside, three host SVDs with
+// 768 `.item()` syncs per sample).
+//
+// Device pipeline for a whole batch, no host synchronisation:
+//   1. channel means of content and style                (TMA-staged statistics kernel, adain.cu)
+//   2. per sample and tensor: centred bf16 hi/lo operand tiles, then Xc.Xc^T on the tensor cores
+//      (tcgen05, bf16x3 = fp32-grade, split-K over H*W across all SMs), reduced to fp64 covariance
+//      (/(HW-1), +I on the content covariance only, network/wct_rp.py:89,94)
+//   3. batched over samples: cluster-resident Jacobi eigensolver (eig.cu) -> C^(1/2), C^(-1/2); the
+//      closed-form (Lu et al., default) transform T = C^(-1/2) (C^(1/2) S C^(1/2))^(1/2) C^(-1/2) or the
+//      original (Li et al.) T = S^(1/2) C^(-1/2), small fp64 products on CUDA cores
+//   4. per sample: out = T.X + (mu_s - T.mu_c) as one tensor-core GEMM with a bias epilogue
+#include "common.cuh"
+
+namespace rpst {
+
+size_t packed_operand_bytes(int64_t rows, int64_t k);
+int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                       const float* row_scale, const float* row_shift, void* hi, void* lo, cudaStream_t stream);
+int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                       int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                       const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
+int eig_padded_order(int n);
+size_t eig_workspace_bytes(int64_t batch, int n);
+int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* ws, size_t ws_bytes, double** w_out,
+                  double** lam_out, int* sweeps, cudaStream_t stream);
+int eig_matfn(const double* w, const double* lam, int64_t batch, int n, double power, double cut, double* out,
+              cudaStream_t stream);
+int dgemm_small(const double* a, const double* b, double* c, int64_t batch, int n, cudaStream_t stream);
+
+namespace {
+
+// cov[i][j] = sum_z partial[z][i][j] / (hw-1) (+1 on the diagonal)
+__global__ void cov_reduce_kernel(const float* __restrict__ partial, int splits, int c, double inv_dof,
+                                  double diag_add, double* __restrict__ cov) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= c * c) return;
+    double acc = 0.0;
+    for (int z = 0; z < splits; ++z) acc += (double)partial[(size_t)z * c * c + idx];
+    const int i = idx / c, j = idx % c;
+    cov[idx] = acc * inv_dof + (i == j ? diag_add : 0.0);
+}
+
+// t32 = (float) T ; bias[i] = mu_s[i] - sum_j T[i][j] mu_c[j]
+__global__ void transform_finalize_kernel(const double* __restrict__ t, const float* __restrict__ mu_c,
+                                          const float* __restrict__ mu_s, int c, float* __restrict__ t32,
+                                          float* __restrict__ bias) {
+    const int i = blockIdx.x;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        const double v = t[(size_t)i * c + j];
+        t32[(size_t)i * c + j] = (float)v;
+        acc += v * (double)mu_c[j];
+    }
+    __shared__ double red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        bias[i] = (float)((double)mu_s[i] - s);
+    }
+}
+
+struct WctLayout {
+    size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, eig, mats[6], t32, bias,
+        t_hi, t_lo, x_hi, x_lo, total;
+    int splits;
+};
+
+int cov_splits(int64_t c, int64_t hw) {
+    const int64_t tiles = ((c + 127) / 128) * ((c + 127) / 128);
+    int64_t s = sm_count() / tiles;
+    if (s < 1) s = 1;
+    const int64_t kt = (hw + 63) / 64;
+    if (s > kt) s = kt;
+    const int64_t per = (kt + s - 1) / s;
+    return (int)((kt + per - 1) / per);
+}
+
+WctLayout wct_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
+    WctLayout l;
+    const int64_t hw_max = hw_c > hw_s ? hw_c : hw_s;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    l.stats = take(rpst_stats_workspace_bytes(n * c, hw_max));
+    l.mean_c = take((size_t)n * c * sizeof(float));
+    l.mean_s = take((size_t)n * c * sizeof(float));
+    l.cov_tiles_hi = take(packed_operand_bytes(c, hw_max));
+    l.cov_tiles_lo = take(packed_operand_bytes(c, hw_max));
+    const int sc = cov_splits(c, hw_c), ss = cov_splits(c, hw_s);
+    l.splits = sc > ss ? sc : ss;
+    l.partial = take((size_t)l.splits * c * c * sizeof(float));
+    l.cov_c = take((size_t)n * c * c * sizeof(double));
+    l.cov_s = take((size_t)n * c * c * sizeof(double));
+    l.eig = take(eig_workspace_bytes(n, (int)c));
+    for (int i = 0; i < 6; ++i) l.mats[i] = take((size_t)n * c * c * sizeof(double));
+    l.t32 = take((size_t)c * c * sizeof(float));
+    l.bias = take((size_t)c * sizeof(float));
+    l.t_hi = take(packed_operand_bytes(c, c));
+    l.t_lo = take(packed_operand_bytes(c, c));
+    l.x_hi = take(packed_operand_bytes(hw_c, c));
+    l.x_lo = take(packed_operand_bytes(hw_c, c));
+    l.total = o;
+    return l;
+}
+
+}  // namespace
+}  // namespace rpst
+
+using namespace rpst;
+
+extern "C" size_t rpst_wct_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
+    if (n <= 0 || c <= 0 || hw_c <= 0 || hw_s <= 0 || c > 512) return 256;
+    return wct_layout(n, c, hw_c, hw_s).total;
+}
+
+extern "C" int rpst_wct_fuse(const float* content, const float* style, float* out, int64_t n, int64_t c, int64_t hw_c,
+                             int64_t hw_s, int method, int passes, double* transform_out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(n >= 0 && c >= 0 && hw_c >= 0 && hw_s >= 0, "wct: negative size");
+    if (n == 0 || c == 0 || hw_c == 0) return RPST_OK;
+    RPST_CHECK_ARG(content && style && out, "wct: null pointer");
+    RPST_CHECK_ARG(hw_c >= 2 && hw_s >= 2, "wct: need at least two positions per feature map");
+    RPST_CHECK_ARG(c <= 512, "wct: at most 512 channels (got %lld)", (long long)c);
+    RPST_CHECK_ARG(method == 0 || method == 1, "wct: method must be 0 (closed-form) or 1 (original)");
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "wct: passes must be 1 (bf16) or 3 (bf16x3, fp32-grade)");
+    const WctLayout l = wct_layout(n, c, hw_c, hw_s);
+    if (!workspace || workspace_bytes < l.total) {
+        set_error("wct: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "wct: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    float* mean_c = reinterpret_cast<float*>(w + l.mean_c);
+    float* mean_s = reinterpret_cast<float*>(w + l.mean_s);
+    int rc;
+    // 1. channel means (network/wct_rp.py:85,92)
+    rc = rpst_stats_nchw(content, n * c, hw_c, 0.f, mean_c, nullptr, w + l.stats, l.mean_c - l.stats, stream);
+    if (rc) return rc;
+    rc = rpst_stats_nchw(style, n * c, hw_s, 0.f, mean_s, nullptr, w + l.stats, l.mean_c - l.stats, stream);
+    if (rc) return rc;
+    // 2. covariances
+    void* ct_hi = w + l.cov_tiles_hi;
+    void* ct_lo = w + l.cov_tiles_lo;
+    float* partial = reinterpret_cast<float*>(w + l.partial);
+    double* cov_c = reinterpret_cast<double*>(w + l.cov_c);
+    double* cov_s = reinterpret_cast<double*>(w + l.cov_s);
+    const int cc = (int)(c * c);
+    for (int64_t i = 0; i < n; ++i) {
+        for (int which = 0; which < 2; ++which) {
+            const int64_t hw = which ? hw_s : hw_c;
+            const float* x = (which ? style : content) + i * c * hw;
+            const float* mu = (which ? mean_s : mean_c) + i * c;
+            rc = pack_operand_shift(x, c, hw, hw, 1, nullptr, mu, ct_hi, passes == 3 ? ct_lo : nullptr, st);
+            if (rc) return rc;
+            const int splits = cov_splits(c, hw);
+            rc = gemm_packed_splitk(ct_hi, ct_lo, ct_hi, ct_lo, partial, c, c, hw, c, passes, 1.f, nullptr, nullptr,
+                                    splits, c * c, st);
+            if (rc) return rc;
+            cov_reduce_kernel<<<(cc + 255) / 256, 256, 0, st>>>(partial, splits, (int)c, 1.0 / ((double)hw - 1.0),
+                                                               which ? 0.0 : 1.0, (which ? cov_s : cov_c) + i * c * c);
+            RPST_CUDA(cudaGetLastError());
+        }
+    }
+    // 3. transform matrices, batched over samples (all fp64)
+    double* m[6];
+    for (int i = 0; i < 6; ++i) m[i] = reinterpret_cast<double*>(w + l.mats[i]);
+    double *ew, *el;
+    const size_t eig_bytes = l.mats[0] - l.eig;
+    double* T = m[5];
+    rc = eig_decompose(cov_c, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st);
+    if (rc) return rc;
+    double* iroot = m[1];
+    if ((rc = eig_matfn(ew, el, n, (int)c, -0.5, 1e-5, iroot, st))) return rc;
+    if (method == 0) {
+        double* root = m[0];
+        if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, root, st))) return rc;
+        if ((rc = dgemm_small(root, cov_s, m[2], n, (int)c, st))) return rc;       // C^1/2 S
+        if ((rc = dgemm_small(m[2], root, m[3], n, (int)c, st))) return rc;        // C^1/2 S C^1/2
+        if ((rc = eig_decompose(m[3], n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st))) return rc;
+        if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, m[4], st))) return rc;   // middle^(1/2)
+        if ((rc = dgemm_small(iroot, m[4], m[2], n, (int)c, st))) return rc;
+        if ((rc = dgemm_small(m[2], iroot, T, n, (int)c, st))) return rc;
+    } else {
+        if ((rc = eig_decompose(cov_s, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st))) return rc;
+        if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, m[4], st))) return rc;   // S^(1/2)
+        if ((rc = dgemm_small(m[4], iroot, T, n, (int)c, st))) return rc;
+    }
+    if (transform_out)
+        RPST_CUDA(cudaMemcpyAsync(transform_out, T, (size_t)n * c * c * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // 4. apply: out_i = T_i X_i + (mu_s - T_i mu_c)
+    float* t32 = reinterpret_cast<float*>(w + l.t32);
+    float* bias = reinterpret_cast<float*>(w + l.bias);
+    for (int64_t i = 0; i < n; ++i) {
+        transform_finalize_kernel<<<(unsigned)c, 128, 0, st>>>(T + i * c * c, mean_c + i * c, mean_s + i * c, (int)c, t32, bias);
+        RPST_CUDA(cudaGetLastError());
+        rc = pack_operand_shift(t32, c, c, c, 1, nullptr, nullptr, w + l.t_hi, w + l.t_lo, st);
+        if (rc) return rc;
+        rc = pack_operand_shift(content + i * c * hw_c, hw_c, c, 1, hw_c, nullptr, nullptr, w + l.x_hi,
+                                passes == 3 ? w + l.x_lo : nullptr, st);
+        if (rc) return rc;
+        rc = gemm_packed_splitk(w + l.t_hi, w + l.t_lo, w + l.x_hi, w + l.x_lo, out + i * c * hw_c, c, hw_c, c, hw_c,
+                                passes, 1.f, bias, nullptr, 1, 0, st);
+        if (rc) return rc;
+    }
+    return RPST_OK;
+}
