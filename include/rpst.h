@@ -174,6 +174,46 @@ RPST_API int rpst_wct_fuse(const float* content, const float* style, float* out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a9  SANet.forward attention core                                    network/sanet.py:85-94
+ *   f [b,c,lc] (queries, = f(mean_variance_norm(content))), g [b,c,ls] (keys), h [b,c,ls] (values),
+ *   all fp32 outputs of the module's own 1x1 convolutions (which stay in cuDNN).
+ *   S = softmax_j(sum_c f[c,i] g[c,j])  (no temperature),  out[b,c,i] = sum_j h[c,j] S[i,j].
+ *   attn_out [b,lc,ls] or NULL receives S.  passes: 3 = bf16x3 (fp32-grade, rel-L2 <= 1e-3 contract),
+ *   1 = bf16 (<= 1e-2 contract).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_sanet_attn_workspace_bytes(int64_t c, int64_t lc, int64_t ls);
+RPST_API int rpst_sanet_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t c,
+                        int64_t lc, int64_t ls, int passes, float* attn_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11 cal_affinity_matrix(content_feat, style_feat)                   network/sanet.py:12-18
+ *   out[b,i,j] = cosine similarity of the channel vectors (F.normalize eps 1e-12) of the RAW features.
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_cosine_affinity_workspace_bytes(int64_t c, int64_t lc, int64_t ls);
+RPST_API int rpst_cosine_affinity(const float* content, const float* style, float* out, int64_t b, int64_t c,
+                         int64_t lc, int64_t ls, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11 AdaptiveSANet.forward attention core with AEAModule / AEALReluModule
+ *                                                                     network/sanet.py:26-71,114-138
+ *   f,g,h as above; content_raw/style_raw [b,c_raw,l] raw features for the cosine affinity;
+ *   f_psi = Linear(l, lh) -> LeakyReLU(0.2) -> Linear(lh, 1): w0 [lh,l], b0 [lh], w2 [lh], b2 [1];
+ *   mode 1 'aea' : clamp = sigmoid(psi)*value_interval + from_value ; S' = sigmoid(scale_value*(S-clamp))
+ *   mode 2 'relu': clamp = (tanh(psi)+1)/2 ; S' = softmax_j(relu(S-clamp))
+ *   out[b,c,i] = sum_j h[c,j] S'[i,j].  claim_before (S) / claim_after (S') [b,l,l], claim_value [b,l]
+ *   are optional outputs (the reference stashes them for visualisation, network/sanet.py:126-137).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_sanet_adaptive_workspace_bytes(int64_t c, int64_t lc, int64_t ls, int64_t lh);
+RPST_API int rpst_sanet_attn_adaptive_fwd(const float* f, const float* g, const float* h, const float* content_raw,
+                                 const float* style_raw, int64_t c_raw, const float* w0, const float* b0,
+                                 const float* w2, const float* b2, int mode, float scale_value,
+                                 float from_value, float value_interval, float* out, float* claim_before,
+                                 float* claim_after, float* claim_value, int64_t b, int64_t c, int64_t lc,
+                                 int64_t ls, int64_t lh, int passes, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Building blocks shared by the contraction kernels (exposed for tests and for callers that want to
  * keep packed operands around): fp32 matrix -> bf16 hi/lo operand tiles, and D = alpha*A.B^T
  * (+row_add[i] +col_add[j]) on tcgen05 with fp32 accumulation in TMEM.

@@ -10,6 +10,8 @@ from .functional import (adain_blend, adain_concat, adaptive_instance_normalizat
 from .modules import SELayer
 from .mrf import MRFLoss, cal_affinity_map, cal_dist, mrf_match, packed_gemm
 from .wct import matrix_inv_sqrt, matrix_sqrt, wct_fuse, whiten_and_color
+from .sanet import (AdaptiveSANet, AdaptiveTransform, AEALReluModule, AEAModule, SANet, Transform, attention_core,
+                    cal_affinity_matrix)
 from .segment import adaptive_instance_normalization_with_segment, do_mask_stylized, load_label_map, seg_adain_batch
 
 AdaIN = adaptive_instance_normalization

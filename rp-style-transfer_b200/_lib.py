@@ -45,6 +45,13 @@ SIGNATURES = {
     "rpst_sym_eig_fn": (c_int, [P, c_int64, c_int64, c_double, P, P, P, P, P, c_size_t, P]),
     "rpst_wct_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "rpst_wct_fuse": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_size_t, P]),
+    "rpst_sanet_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_sanet_attn_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, P, c_size_t, P]),
+    "rpst_cosine_affinity_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_cosine_affinity": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, P, c_size_t, P]),
+    "rpst_sanet_adaptive_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "rpst_sanet_attn_adaptive_fwd": (c_int, [P, P, P, P, P, c_int64, P, P, P, P, c_int, c_float, c_float, c_float,
+                                             P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
     "rpst_seg_adain_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
 }
 

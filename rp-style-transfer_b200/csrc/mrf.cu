@@ -204,6 +204,14 @@ int topk_dispatch(int k, const float* mat, int64_t rows, int64_t cols, int64_t l
 }
 
 }  // namespace
+
+// per-position channel norms (shared with the adaptive SANet cosine affinity)
+int channel_norms(const float* x, int64_t c, int64_t l, float* sq, float* nrm, float* inv, cudaStream_t st) {
+    mrf_norm_kernel<<<(unsigned)((l + 127) / 128), 128, 0, st>>>(x, c, l, sq, nrm, inv);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
 }  // namespace rpst
 
 using namespace rpst;

@@ -1,0 +1,340 @@
+// SANet attention core, static and adaptive — SURVEY.md §8 a9/a11; reference: network/sanet.py:82-99
+// (`SANet.forward`), :12-18 (`cal_affinity_matrix`), :41-46 / :66-71 (AEA clamps), :114-138
+// (`AdaptiveSANet.forward`).  The 1x1 convolutions f/g/h/out_conv stay in cuDNN; this file owns
+//   S = F^T G            [Lc,Ls]   tensor cores (tcgen05, packed bf16 / bf16x3 operands)
+//   P = softmax_j(S)               one CTA per row; emits P directly as packed bf16 hi/lo operand tiles
+//   O = H P^T            [C,Lc]    tensor cores, written in the [C, Lc] layout the module returns
+// and for the adaptive variants the cosine affinity, the f_psi MLP (its Linear(L -> L/16) is a
+// tensor-core GEMM with a bias epilogue) and the clamped attention
+//   'aea' : P' = sigmoid(scale * (P - clamp_i)),  clamp_i = sigmoid(mlp_i) * interval + from   (not renormalised)
+//   'relu': P' = softmax_j(relu(P - clamp_i)),    clamp_i = (tanh(mlp_i) + 1) / 2
+// Softmax is over the STYLE axis without temperature (network/sanet.py:79,90-91).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace rpst {
+
+size_t packed_operand_bytes(int64_t rows, int64_t k);
+int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                       const float* row_scale, const float* row_shift, void* hi, void* lo, cudaStream_t stream);
+int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                       int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                       const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
+int channel_norms(const float* x, int64_t c, int64_t l, float* sq, float* nrm, float* inv, cudaStream_t st);
+
+namespace {
+
+constexpr int kRowThreads = 256;
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < kRowThreads / 32; ++w) r = fmaxf(r, red[w]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < kRowThreads / 32; ++w) r += red[w];
+    __syncthreads();
+    return r;
+}
+
+struct RowParams {
+    const float* in;      // [rows, cols]
+    float* out32;         // [rows, cols] or null (may alias `in`)
+    __nv_bfloat16* hi;    // packed [rows x cols(K)] tiles or null
+    __nv_bfloat16* lo;    // or null
+    const float* clamp;   // [rows] (modes 1, 2)
+    int64_t rows, cols;
+    int k_tiles;          // ceil(cols / 64)
+    int mode;             // 0 softmax(x); 1 sigmoid(scale*(x-clamp)); 2 softmax(relu(x-clamp))
+    float scale;
+};
+
+// One CTA per row; the row (<= 64 KiB) is re-read from L1/L2 between the passes.
+__global__ void __launch_bounds__(kRowThreads) attn_rows_kernel(RowParams p) {
+    __shared__ float red[kRowThreads / 32];
+    const int64_t row = blockIdx.x;
+    const float* x = p.in + row * p.cols;
+    const float cl = p.clamp ? __ldg(p.clamp + row) : 0.f;
+    float mx = 0.f, inv_sum = 1.f;
+    if (p.mode != 1) {
+        float m = -INFINITY;
+        for (int64_t j = threadIdx.x; j < p.cols; j += kRowThreads) {
+            float v = x[j];
+            if (p.mode == 2) v = fmaxf(v - cl, 0.f);
+            m = fmaxf(m, v);
+        }
+        mx = block_max(m, red);
+        float s = 0.f;
+        for (int64_t j = threadIdx.x; j < p.cols; j += kRowThreads) {
+            float v = x[j];
+            if (p.mode == 2) v = fmaxf(v - cl, 0.f);
+            s += expf(v - mx);
+        }
+        inv_sum = 1.f / block_sum(s, red);
+    }
+    const int64_t chunks = (p.cols + 7) / 8;
+    const int64_t rb = row / kTileRows;
+    const int r = (int)(row % kTileRows);
+    for (int64_t q = threadIdx.x; q < chunks; q += kRowThreads) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t j = q * 8 + e;
+            float v = 0.f;
+            if (j < p.cols) {
+                v = x[j];
+                if (p.mode == 0) v = expf(v - mx) * inv_sum;
+                else if (p.mode == 1) v = 1.f / (1.f + expf(-p.scale * (v - cl)));
+                else v = expf(fmaxf(v - cl, 0.f) - mx) * inv_sum;
+            }
+            y[e] = v;
+        }
+        if (p.out32) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (q * 8 + e < p.cols) p.out32[row * p.cols + q * 8 + e] = y[e];
+        }
+        if (p.hi) {
+            __align__(16) __nv_bfloat16 h[8];
+            __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(y[e], h[e], l[e]);
+            const int64_t tile = rb * p.k_tiles + (q >> 3);
+            const size_t off = (size_t)tile * kTileBytes + tile_chunk_offset(r, (int)(q & 7));
+            *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.hi) + off) = *reinterpret_cast<const uint4*>(h);
+            if (p.lo) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.lo) + off) = *reinterpret_cast<const uint4*>(l);
+        }
+    }
+}
+
+// f_psi head: z_i = sum_h leaky_relu(hidden[i,h], 0.2) * w2[h] + b2 ; clamp per mode. One warp per row.
+__global__ void __launch_bounds__(256) psi_head_kernel(const float* __restrict__ hidden, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, int64_t rows, int64_t lh, int mode,
+                                                       float from_value, float value_interval, float* __restrict__ clamp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float acc = 0.f;
+    for (int64_t h = lane; h < lh; h += 32) {
+        float v = hidden[row * lh + h];
+        v = v >= 0.f ? v : 0.2f * v;
+        acc = fmaf(v, __ldg(w2 + h), acc);
+    }
+    acc = warp_sum(acc) + __ldg(b2);
+    if (lane == 0)
+        clamp[row] = mode == 1 ? (1.f / (1.f + expf(-acc))) * value_interval + from_value : (tanhf(acc) + 1.f) * 0.5f;
+}
+
+struct AttnLayout {
+    size_t q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, s, p_hi, p_lo, total;
+};
+AttnLayout attn_layout(int64_t c, int64_t lc, int64_t ls) {
+    AttnLayout l;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    l.q_hi = take(packed_operand_bytes(lc, c)); l.q_lo = take(packed_operand_bytes(lc, c));
+    l.k_hi = take(packed_operand_bytes(ls, c)); l.k_lo = take(packed_operand_bytes(ls, c));
+    l.v_hi = take(packed_operand_bytes(c, ls)); l.v_lo = take(packed_operand_bytes(c, ls));
+    l.s = take((size_t)lc * ls * sizeof(float));
+    l.p_hi = take(packed_operand_bytes(lc, ls)); l.p_lo = take(packed_operand_bytes(lc, ls));
+    l.total = o;
+    return l;
+}
+
+struct AdaLayout {
+    AttnLayout a;
+    size_t aff, w_hi, w_lo, hidden, clamp, vec[6], total;
+};
+AdaLayout ada_layout(int64_t c, int64_t lc, int64_t ls, int64_t lh) {
+    AdaLayout l;
+    l.a = attn_layout(c, lc, ls);
+    size_t o = l.a.total;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    l.aff = take((size_t)lc * ls * sizeof(float));
+    l.w_hi = take(packed_operand_bytes(lh, ls)); l.w_lo = take(packed_operand_bytes(lh, ls));
+    l.hidden = take((size_t)lc * lh * sizeof(float));
+    l.clamp = take((size_t)lc * sizeof(float));
+    for (int i = 0; i < 6; ++i) l.vec[i] = take((size_t)(lc > ls ? lc : ls) * sizeof(float));
+    l.total = o;
+    return l;
+}
+
+int launch_rows(const float* in, float* out32, void* hi, void* lo, const float* clamp, int64_t rows, int64_t cols,
+                int mode, float scale, cudaStream_t st) {
+    RowParams p{};
+    p.in = in; p.out32 = out32; p.hi = static_cast<__nv_bfloat16*>(hi); p.lo = static_cast<__nv_bfloat16*>(lo);
+    p.clamp = clamp; p.rows = rows; p.cols = cols; p.k_tiles = (int)((cols + kTileK - 1) / kTileK);
+    p.mode = mode; p.scale = scale;
+    if (hi && (rows % kTileRows != 0 || cols % kTileK != 0)) {   // zero padding of the partial tiles
+        RPST_CUDA(cudaMemsetAsync(hi, 0, packed_operand_bytes(rows, cols), st));
+        if (lo) RPST_CUDA(cudaMemsetAsync(lo, 0, packed_operand_bytes(rows, cols), st));
+    }
+    attn_rows_kernel<<<(unsigned)rows, kRowThreads, 0, st>>>(p);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
+// S = F^T G for one sample into `s`
+int scores(const float* f, const float* g, int64_t c, int64_t lc, int64_t ls, int passes, char* w, const AttnLayout& l,
+           float* s, cudaStream_t st) {
+    int rc = pack_operand_shift(f, lc, c, 1, lc, nullptr, nullptr, w + l.q_hi, passes == 3 ? w + l.q_lo : nullptr, st);
+    if (rc) return rc;
+    rc = pack_operand_shift(g, ls, c, 1, ls, nullptr, nullptr, w + l.k_hi, passes == 3 ? w + l.k_lo : nullptr, st);
+    if (rc) return rc;
+    return gemm_packed_splitk(w + l.q_hi, w + l.q_lo, w + l.k_hi, w + l.k_lo, s, lc, ls, c, ls, passes, 1.f, nullptr,
+                              nullptr, 1, 0, st);
+}
+
+// O = H P^T for one sample (P already packed in the workspace)
+int weighted_values(const float* h, int64_t c, int64_t lc, int64_t ls, int passes, char* w, const AttnLayout& l,
+                    float* out, cudaStream_t st) {
+    int rc = pack_operand_shift(h, c, ls, ls, 1, nullptr, nullptr, w + l.v_hi, passes == 3 ? w + l.v_lo : nullptr, st);
+    if (rc) return rc;
+    return gemm_packed_splitk(w + l.v_hi, w + l.v_lo, w + l.p_hi, w + l.p_lo, out, c, lc, ls, lc, passes, 1.f, nullptr,
+                              nullptr, 1, 0, st);
+}
+
+}  // namespace
+}  // namespace rpst
+
+using namespace rpst;
+
+extern "C" size_t rpst_sanet_attn_workspace_bytes(int64_t c, int64_t lc, int64_t ls) {
+    if (c <= 0 || lc <= 0 || ls <= 0) return 256;
+    return attn_layout(c, lc, ls).total;
+}
+
+extern "C" int rpst_sanet_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t c,
+                                   int64_t lc, int64_t ls, int passes, float* attn_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(b >= 0 && c >= 0 && lc >= 0 && ls >= 0, "sanet: negative size");
+    if (b == 0 || c == 0 || lc == 0) return RPST_OK;
+    RPST_CHECK_ARG(ls > 0, "sanet: empty style map");
+    RPST_CHECK_ARG(f && g && h && out, "sanet: null pointer");
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet: passes must be 1 (bf16) or 3 (bf16x3, fp32-grade)");
+    const AttnLayout l = attn_layout(c, lc, ls);
+    if (!workspace || workspace_bytes < l.total) {
+        set_error("sanet: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    for (int64_t i = 0; i < b; ++i) {
+        float* s = attn_out ? attn_out + i * lc * ls : reinterpret_cast<float*>(w + l.s);
+        int rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l, s, st);
+        if (rc) return rc;
+        rc = launch_rows(s, attn_out ? s : nullptr, w + l.p_hi, passes == 3 ? w + l.p_lo : nullptr, nullptr, lc, ls, 0,
+                         0.f, st);
+        if (rc) return rc;
+        rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l, out + i * c * lc, st);
+        if (rc) return rc;
+    }
+    return RPST_OK;
+}
+
+extern "C" size_t rpst_sanet_adaptive_workspace_bytes(int64_t c, int64_t lc, int64_t ls, int64_t lh) {
+    if (c <= 0 || lc <= 0 || ls <= 0 || lh <= 0) return 256;
+    return ada_layout(c, lc, ls, lh).total;
+}
+
+extern "C" int rpst_sanet_attn_adaptive_fwd(const float* f, const float* g, const float* h, const float* content_raw,
+                                            const float* style_raw, int64_t c_raw, const float* w0, const float* b0,
+                                            const float* w2, const float* b2, int mode, float scale_value,
+                                            float from_value, float value_interval, float* out, float* claim_before,
+                                            float* claim_after, float* claim_value, int64_t b, int64_t c, int64_t lc,
+                                            int64_t ls, int64_t lh, int passes, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+    RPST_CHECK_ARG(b >= 0 && c > 0 && lc > 0 && ls > 0 && lh > 0 && c_raw > 0, "sanet_adaptive: bad size");
+    if (b == 0) return RPST_OK;
+    RPST_CHECK_ARG(f && g && h && content_raw && style_raw && w0 && b0 && w2 && b2 && out, "sanet_adaptive: null pointer");
+    RPST_CHECK_ARG(lc == ls, "sanet_adaptive: the reference asserts equal content/style sizes (network/sanet.py:14)");
+    RPST_CHECK_ARG(mode == 1 || mode == 2, "sanet_adaptive: mode must be 1 ('aea') or 2 ('relu')");
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet_adaptive: passes must be 1 or 3");
+    const AdaLayout l = ada_layout(c, lc, ls, lh);
+    if (!workspace || workspace_bytes < l.total) {
+        set_error("sanet_adaptive: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet_adaptive: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    float* vec[6];
+    for (int i = 0; i < 6; ++i) vec[i] = reinterpret_cast<float*>(w + l.vec[i]);
+    float* aff = reinterpret_cast<float*>(w + l.aff);
+    float* hidden = reinterpret_cast<float*>(w + l.hidden);
+    int rc;
+    // the Linear(L -> L/16) weight is shared by every sample: pack it once (rows = hidden units, K = L)
+    if ((rc = pack_operand_shift(w0, lh, ls, ls, 1, nullptr, nullptr, w + l.w_hi, w + l.w_lo, st))) return rc;
+    for (int64_t i = 0; i < b; ++i) {
+        float* before = claim_before ? claim_before + i * lc * ls : reinterpret_cast<float*>(w + l.a.s);
+        float* clampv = claim_value ? claim_value + i * lc : reinterpret_cast<float*>(w + l.clamp);
+        // cosine affinity of the RAW features (network/sanet.py:16-18), reusing the Q/K tile buffers
+        if ((rc = channel_norms(content_raw + i * c_raw * lc, c_raw, lc, vec[0], vec[1], vec[2], st))) return rc;
+        if ((rc = channel_norms(style_raw + i * c_raw * ls, c_raw, ls, vec[3], vec[4], vec[5], st))) return rc;
+        if ((rc = pack_operand_shift(content_raw + i * c_raw * lc, lc, c_raw, 1, lc, vec[2], nullptr, w + l.a.q_hi, w + l.a.q_lo, st))) return rc;
+        if ((rc = pack_operand_shift(style_raw + i * c_raw * ls, ls, c_raw, 1, ls, vec[5], nullptr, w + l.a.k_hi, w + l.a.k_lo, st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.a.q_hi, w + l.a.q_lo, w + l.a.k_hi, w + l.a.k_lo, aff, lc, ls, c_raw, ls, 3, 1.f,
+                                     nullptr, nullptr, 1, 0, st))) return rc;
+        // f_psi: hidden = aff @ W0^T + b0 (tensor cores, affinity rows packed into the P tile buffers)
+        if ((rc = pack_operand_shift(aff, lc, ls, ls, 1, nullptr, nullptr, w + l.a.p_hi, w + l.a.p_lo, st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.a.p_hi, w + l.a.p_lo, w + l.w_hi, w + l.w_lo, hidden, lc, lh, ls, lh, 3, 1.f,
+                                     nullptr, b0, 1, 0, st))) return rc;
+        psi_head_kernel<<<(unsigned)((lc + 7) / 8), 256, 0, st>>>(hidden, w2, b2, lc, lh, mode, from_value, value_interval, clampv);
+        RPST_CUDA(cudaGetLastError());
+        // plain attention first (claim_before), then the clamped one (claim_after) straight into operand tiles
+        if ((rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l.a, before, st))) return rc;
+        if ((rc = launch_rows(before, before, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;
+        if ((rc = launch_rows(before, claim_after ? claim_after + i * lc * ls : nullptr, w + l.a.p_hi,
+                              passes == 3 ? w + l.a.p_lo : nullptr, clampv, lc, ls, mode, scale_value, st))) return rc;
+        if ((rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l.a, out + i * c * lc, st))) return rc;
+    }
+    return RPST_OK;
+}
+
+extern "C" size_t rpst_cosine_affinity_workspace_bytes(int64_t c, int64_t lc, int64_t ls) {
+    if (c <= 0 || lc <= 0 || ls <= 0) return 256;
+    return 2 * align_up(packed_operand_bytes(lc, c), 256) + 2 * align_up(packed_operand_bytes(ls, c), 256) +
+           6 * align_up((size_t)(lc > ls ? lc : ls) * sizeof(float), 256);
+}
+
+extern "C" int rpst_cosine_affinity(const float* content, const float* style, float* out, int64_t b, int64_t c,
+                                    int64_t lc, int64_t ls, void* workspace, size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(b >= 0 && c > 0 && lc > 0 && ls > 0, "cosine_affinity: bad size");
+    if (b == 0) return RPST_OK;
+    RPST_CHECK_ARG(content && style && out, "cosine_affinity: null pointer");
+    const size_t need = rpst_cosine_affinity_workspace_bytes(c, lc, ls);
+    if (!workspace || workspace_bytes < need) {
+        set_error("cosine_affinity: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "cosine_affinity: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    const size_t ta = align_up(packed_operand_bytes(lc, c), 256), tb = align_up(packed_operand_bytes(ls, c), 256);
+    const size_t vb = align_up((size_t)(lc > ls ? lc : ls) * sizeof(float), 256);
+    char* v = w + 2 * ta + 2 * tb;
+    float* vec[6];
+    for (int i = 0; i < 6; ++i) vec[i] = reinterpret_cast<float*>(v + i * vb);
+    for (int64_t i = 0; i < b; ++i) {
+        int rc;
+        if ((rc = channel_norms(content + i * c * lc, c, lc, vec[0], vec[1], vec[2], st))) return rc;
+        if ((rc = channel_norms(style + i * c * ls, c, ls, vec[3], vec[4], vec[5], st))) return rc;
+        if ((rc = pack_operand_shift(content + i * c * lc, lc, c, 1, lc, vec[2], nullptr, w, w + ta, st))) return rc;
+        if ((rc = pack_operand_shift(style + i * c * ls, ls, c, 1, ls, vec[5], nullptr, w + 2 * ta, w + 2 * ta + tb, st))) return rc;
+        if ((rc = gemm_packed_splitk(w, w + ta, w + 2 * ta, w + 2 * ta + tb, out + i * lc * ls, lc, ls, c, ls, 3, 1.f,
+                                     nullptr, nullptr, 1, 0, st))) return rc;
+    }
+    return RPST_OK;
+}

@@ -1,0 +1,215 @@
+"""SANet / AdaptiveSANet / Transform — host-side mirrors of network/sanet.py:12-160 with identical
+constructor signatures, forward arguments and state-dict names (f, g, h, out_conv,
+attention_layer.f_psi.{0,2}, sanet4_1, sanet5_1, merge_conv), so reference checkpoints load unchanged.
+The 1x1 / 3x3 convolutions run in cuDNN through torch (they are out of the transform's scope,
+SURVEY.md §2 #9-10); normalisation and the attention core call librpst."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+from .functional import _prep, _ptr, _stream, mean_variance_norm
+
+PRECISION = {"fp32": 3, "bf16": 1}
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _no_grad_guard(*tensors):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "rpst: the attention core is forward-only in this round (attention backward is SURVEY.md §8f rank 2); "
+            "call it under torch.no_grad() (as `SAModel.test` does) or detach the inputs")
+
+
+def cal_affinity_matrix(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
+    """Drop-in for network/sanet.py:12 — [b,c,h,w] x2 -> [b,hw,hw] cosine affinity."""
+    assert content_feat.size() == style_feat.size()
+    c4, s4 = _prep(content_feat.detach(), "content_feat"), _prep(style_feat.detach(), "style_feat")
+    b, c, h, w = c4.shape
+    l = h * w
+    out = torch.empty(b, l, l, dtype=torch.float32, device=c4.device)
+    L = _lib.lib()
+    ws = _ws(L.rpst_cosine_affinity_workspace_bytes(c, l, l), c4.device)
+    _lib.check(L.rpst_cosine_affinity(c4.data_ptr(), s4.data_ptr(), out.data_ptr(), b, c, l, l, ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def attention_core(F: torch.Tensor, G: torch.Tensor, H: torch.Tensor, precision: str = "fp32", return_attn: bool = False):
+    """softmax(F^T G) applied to H: F [b,c,hc,wc], G/H [b,c,hs,ws] -> [b,c,hc,wc] (network/sanet.py:85-94)."""
+    _no_grad_guard(F, G, H)
+    F, G, H = _prep(F.detach(), "F"), _prep(G.detach(), "G"), _prep(H.detach(), "H")
+    b, c, hc, wc = F.shape
+    ls = G.shape[2] * G.shape[3]
+    lc = hc * wc
+    assert G.shape[:2] == (b, c) and H.shape == G.shape
+    out = torch.empty(b, c, hc, wc, dtype=torch.float32, device=F.device)
+    attn = torch.empty(b, lc, ls, dtype=torch.float32, device=F.device) if return_attn else None
+    L = _lib.lib()
+    ws = _ws(L.rpst_sanet_attn_workspace_bytes(c, lc, ls), F.device)
+    _lib.check(L.rpst_sanet_attn_fwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), out.data_ptr(), b, c, lc, ls,
+                                     PRECISION[precision], _ptr(attn), ws.data_ptr(), ws.numel(), _stream()))
+    return (out, attn) if return_attn else out
+
+
+class AEAModule(nn.Module):
+    """network/sanet.py:26-46."""
+
+    def __init__(self, inplanes, scale_value=50, from_value=0.4, value_interval=0.5):
+        super().__init__()
+        self.inplanes = inplanes
+        self.scale_value = scale_value
+        self.from_value = from_value
+        self.value_interval = value_interval
+        self.f_psi = nn.Sequential(
+            nn.Linear(self.inplanes, self.inplanes // 16),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Linear(self.inplanes // 16, 1),
+            nn.Sigmoid(),
+        )
+    mode = 1
+
+    def forward(self, x, f_x):
+        # stand-alone use (the fused path is AdaptiveSANet.forward): same algebra on the module's own layers
+        b, hw, c = x.size()
+        clamp_value = self.f_psi(x.view(b * hw, c)) * self.value_interval + self.from_value
+        clamp_value = clamp_value.view(b, hw, 1)
+        return torch.sigmoid(self.scale_value * (f_x - clamp_value)), clamp_value
+
+
+class AEALReluModule(nn.Module):
+    """network/sanet.py:49-71."""
+
+    def __init__(self, inplanes, scale_value=50, from_value=0.4, value_interval=0.5):
+        super().__init__()
+        self.inplanes = inplanes
+        self.scale_value = scale_value
+        self.from_value = from_value
+        self.value_interval = value_interval
+        self.f_psi = nn.Sequential(
+            nn.Linear(self.inplanes, self.inplanes // 16),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Linear(self.inplanes // 16, 1),
+            nn.Tanh(),
+        )
+        self.clamp_sig = nn.Sequential(nn.ReLU(inplace=True), nn.Softmax(dim=-1))
+    mode = 2
+
+    def forward(self, x, f_x):
+        b, hw, c = x.size()
+        clamp_value = ((self.f_psi(x.view(b * hw, c)) + 1) / 2).view(b, hw, 1)
+        return self.clamp_sig(f_x - clamp_value), clamp_value
+
+
+class SANet(nn.Module):
+    """network/sanet.py:73-99."""
+
+    def __init__(self, in_planes):
+        super().__init__()
+        self.f = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.g = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.h = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.sm = nn.Softmax(dim=-1)
+        self.out_conv = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.precision = "fp32"
+
+    def forward(self, content, style):
+        F = self.f(mean_variance_norm(content))
+        G = self.g(mean_variance_norm(style))
+        H = self.h(style)
+        O = attention_core(F, G, H, self.precision)
+        O = self.out_conv(O)
+        O += content
+        return O
+
+
+class AdaptiveSANet(nn.Module):
+    """network/sanet.py:100-138 (keeps claim_value / claim_before / claim_after for the visualisation
+    code at network/sanet.py:346-348)."""
+
+    def __init__(self, in_planes, spatial_dims, ada_module='aea'):
+        super().__init__()
+        self.f = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.g = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.h = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.sm = nn.Softmax(dim=-1)
+        self.out_conv = nn.Conv2d(in_planes, in_planes, (1, 1))
+        self.attention_layer = AEAModule(spatial_dims) if ada_module == 'aea' else AEALReluModule(spatial_dims)
+        self.claim_value = 0
+        self.claim_before = 0
+        self.claim_after = 0
+        self.claim_after_sm = 0
+        self.precision = "fp32"
+        self.keep_claims = True
+
+    def forward(self, content, style):
+        assert content.size() == style.size()
+        F = self.f(mean_variance_norm(content))
+        G = self.g(mean_variance_norm(style))
+        H = self.h(style)
+        _no_grad_guard(F, G, H, content, style)
+        F, G, H = (_prep(t.detach(), n) for t, n in ((F, "F"), (G, "G"), (H, "H")))
+        c_raw, s_raw = _prep(content.detach(), "content"), _prep(style.detach(), "style")
+        b, c, hh, ww = F.shape
+        l = hh * ww
+        al = self.attention_layer
+        lin0, lin2 = al.f_psi[0], al.f_psi[2]
+        assert lin0.in_features == l, f"spatial_dims={lin0.in_features} does not match H*W={l} (network/sanet.py:290-292)"
+        lh = lin0.out_features
+        dev = F.device
+        out = torch.empty(b, c, hh, ww, dtype=torch.float32, device=dev)
+        before = torch.empty(b, l, l, dtype=torch.float32, device=dev) if self.keep_claims else None
+        after = torch.empty(b, l, l, dtype=torch.float32, device=dev) if self.keep_claims else None
+        clamp = torch.empty(b, l, 1, dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        ws = _ws(L.rpst_sanet_adaptive_workspace_bytes(c, l, l, lh), dev)
+        w0 = lin0.weight.detach().contiguous()
+        b0 = lin0.bias.detach().contiguous()
+        w2 = lin2.weight.detach().reshape(-1).contiguous()
+        b2 = lin2.bias.detach().contiguous()
+        _lib.check(L.rpst_sanet_attn_adaptive_fwd(
+            F.data_ptr(), G.data_ptr(), H.data_ptr(), c_raw.data_ptr(), s_raw.data_ptr(), c_raw.shape[1],
+            w0.data_ptr(), b0.data_ptr(), w2.data_ptr(), b2.data_ptr(), al.mode, float(al.scale_value),
+            float(al.from_value), float(al.value_interval), out.data_ptr(), _ptr(before), _ptr(after), clamp.data_ptr(),
+            b, c, l, l, lh, PRECISION[self.precision], ws.data_ptr(), ws.numel(), _stream()))
+        self.claim_before = before
+        self.claim_after = after
+        O = self.out_conv(out)
+        O += content
+        self.claim_value = clamp
+        return O
+
+
+class Transform(nn.Module):
+    """network/sanet.py:140-149."""
+
+    def __init__(self, in_planes):
+        super().__init__()
+        self.sanet4_1 = SANet(in_planes=in_planes)
+        self.sanet5_1 = SANet(in_planes=in_planes)
+        self.upsample5_1 = nn.Upsample(scale_factor=2, mode='nearest')
+        self.merge_conv_pad = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.merge_conv = nn.Conv2d(in_planes, in_planes, (3, 3))
+
+    def forward(self, content4_1, style4_1, content5_1, style5_1):
+        return self.merge_conv(self.merge_conv_pad(
+            self.sanet4_1(content4_1, style4_1) + self.upsample5_1(self.sanet5_1(content5_1, style5_1))))
+
+
+class AdaptiveTransform(nn.Module):
+    """network/sanet.py:151-160."""
+
+    def __init__(self, in_planes, relu4_1_dims, relu5_1_dims, ada_module='aea'):
+        super().__init__()
+        self.sanet4_1 = AdaptiveSANet(in_planes=in_planes, spatial_dims=relu4_1_dims, ada_module=ada_module)
+        self.sanet5_1 = AdaptiveSANet(in_planes=in_planes, spatial_dims=relu5_1_dims, ada_module=ada_module)
+        self.upsample5_1 = nn.Upsample(scale_factor=2, mode='nearest')
+        self.merge_conv_pad = nn.ReflectionPad2d((1, 1, 1, 1))
+        self.merge_conv = nn.Conv2d(in_planes, in_planes, (3, 3))
+
+    def forward(self, content4_1, style4_1, content5_1, style5_1):
+        return self.merge_conv(self.merge_conv_pad(
+            self.sanet4_1(content4_1, style4_1) + self.upsample5_1(self.sanet5_1(content5_1, style5_1))))

@@ -1,0 +1,96 @@
+"""GPU parity tests for SANet / AdaptiveSANet / Transform."""
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TOL32 = 1e-3    # fp32 contract (bf16x3 tensor-core products)
+TOL16 = 1e-2    # bf16 contract
+
+
+@pytest.fixture(scope="module")
+def rpst():
+    import rpst as m
+    return m
+
+
+def _sub(g, prefix):
+    return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_golden_sanet_and_transform(rpst, golden):
+    g = golden("sanet")
+    with torch.no_grad():
+        m = rpst.SANet(16).cuda()
+        m.load_state_dict(_sub(g, "sanet."))
+        assert R.rel_l2(m(g["c4"].cuda(), g["s4"].cuda()), g["sanet_out"]) < TOL32
+        m.precision = "bf16"
+        assert R.rel_l2(m(g["c4"].cuda(), g["s4"].cuda()), g["sanet_out"]) < TOL16
+        tr = rpst.Transform(16).cuda()
+        tr.load_state_dict(_sub(g, "transform."))
+        out = tr(g["c4"].cuda(), g["s4"].cuda(), g["c5"].cuda(), g["s5"].cuda())
+        assert R.rel_l2(out, g["transform_out"]) < TOL32
+        assert R.rel_l2(rpst.cal_affinity_matrix(g["c4"].cuda(), g["s4"].cuda()), g["affinity"]) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["aea", "relu"])
+def test_golden_adaptive(rpst, golden, mode):
+    g = golden("sanet")
+    with torch.no_grad():
+        m = rpst.AdaptiveSANet(16, 64, ada_module=mode).cuda()
+        m.load_state_dict(_sub(g, f"ada_{mode}."))
+        out = m(g["c4"].cuda(), g["s4"].cuda())
+        assert R.rel_l2(m.claim_before, g[f"ada_{mode}_before"]) < TOL32
+        assert R.rel_l2(m.claim_value, g[f"ada_{mode}_clamp"]) < TOL32
+        assert R.rel_l2(m.claim_after, g[f"ada_{mode}_after"]) < 5e-3   # sigmoid(50 x) amplifies S errors
+        assert R.rel_l2(out, g[f"ada_{mode}_out"]) < 2e-3
+        at = rpst.AdaptiveTransform(16, 64, 16, ada_module=mode).cuda()
+        at.load_state_dict(_sub(g, f"adatr_{mode}."))
+        out = at(g["c4"].cuda(), g["s4"].cuda(), g["c5"].cuda(), g["s5"].cuda())
+        assert R.rel_l2(out, g[f"adatr_{mode}_out"]) < 2e-3
+
+
+@pytest.mark.parametrize("b,c,hc,wc,hs,ws", [(2, 32, 12, 12, 12, 12), (1, 64, 20, 24, 16, 18), (1, 512, 32, 32, 32, 32)])
+def test_attention_core_vs_oracle(rpst, b, c, hc, wc, hs, ws):
+    g = torch.Generator().manual_seed(c)
+    f = torch.randn(b, c, hc, wc, generator=g) * 0.5
+    k = torch.randn(b, c, hs, ws, generator=g) * 0.5
+    v = torch.randn(b, c, hs, ws, generator=g)
+    want = R.attention_core(f.reshape(b, c, -1).double(), k.reshape(b, c, -1).double(), v.reshape(b, c, -1).double())
+    got, attn = rpst.attention_core(f.cuda(), k.cuda(), v.cuda(), return_attn=True)
+    assert R.rel_l2(got.reshape(b, c, -1), want) < TOL32
+    # rows of the attention map are probability distributions
+    assert float((attn.sum(-1) - 1).abs().max()) < 1e-4
+    got16 = rpst.attention_core(f.cuda(), k.cuda(), v.cuda(), precision="bf16")
+    assert R.rel_l2(got16.reshape(b, c, -1), want) < 5e-2
+
+
+def test_sanet_relu4_1_size_vs_fp64(rpst):
+    """in_planes 512 at 64x64 (relu4_1 @512^2, L=4096): full module against an fp64 evaluation on the GPU."""
+    torch.manual_seed(0)
+    m = rpst.SANet(512).cuda()
+    c, s = R.synth_features((1, 512, 64, 64), cfg=4, device="cuda")
+    with torch.no_grad():
+        got = m(c, s)
+        sd = {k: v.double() for k, v in m.state_dict().items()}
+
+        def mvn(x):
+            f = x.reshape(1, 512, -1)
+            return ((f - f.mean(2, keepdim=True)) / (f.var(2, keepdim=True) + 1e-5).sqrt())
+        conv = lambda x, n: torch.einsum("oc,ncl->nol", sd[n + ".weight"].reshape(512, 512), x) + sd[n + ".bias"].reshape(1, -1, 1)
+        cd, sdd = c.double(), s.double()
+        F = conv(mvn(cd), "f")
+        G = conv(mvn(sdd), "g")
+        H = conv(sdd.reshape(1, 512, -1), "h")
+        P = torch.softmax(torch.bmm(F.transpose(1, 2), G), dim=-1)
+        O = torch.bmm(H, P.transpose(1, 2))
+        want = (conv(O, "out_conv") + cd.reshape(1, 512, -1)).reshape(1, 512, 64, 64)
+    assert R.rel_l2(got, want) < TOL32
+
+
+def test_requires_grad_is_refused_loudly(rpst):
+    m = rpst.SANet(8).cuda()
+    x = torch.randn(1, 8, 4, 4, device="cuda")
+    with pytest.raises(NotImplementedError):
+        m(x, x)
