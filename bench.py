@@ -262,10 +262,11 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "adain_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's 5 launches
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "adain_pipe_kernel<4,*> (5 launches/step: C=256 plain, C=128..16 blend)",
+    roofline = {"bound": "hbm", "kernel": "adain_tma_kernel<6> (5 launches/step: C=256 plain, C=128..16 blend; averaged over the launches)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
                 "frac_of_nominal_8TBs": achieved / 8000.0,

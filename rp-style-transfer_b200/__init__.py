@@ -14,6 +14,9 @@ from .sanet import (AdaptiveSANet, AdaptiveTransform, AEALReluModule, AEAModule,
                     cal_affinity_matrix)
 from .segment import adaptive_instance_normalization_with_segment, do_mask_stylized, load_label_map, seg_adain_batch
 
+from .decode import multiscale_transform
+from .install import install, uninstall
+
 AdaIN = adaptive_instance_normalization
 AdaINSeg = adaptive_instance_normalization_with_segment
 

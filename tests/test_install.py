@@ -1,0 +1,58 @@
+"""Drop-in installation into the real reference tree (development container only: needs
+/root/reference; no GPU, so only the rebinding is checked — the numerics of every replacement are
+covered by the -m gpu tests)."""
+import sys
+
+import pytest
+
+from oracle.reference_loader import load_reference, reference_available
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not reference_available(), reason="/root/reference not present")]
+
+
+def test_install_rebinds_every_namespace_and_restores():
+    import rpst
+    net = load_reference()
+    base, adain_rp, wct_rp, sanet, mrf_rp = (sys.modules[f"network.{n}"] for n in ("base", "adain_rp", "wct_rp", "sanet", "mrf_rp"))
+    orig_adain = base.adaptive_instance_normalization
+    orig_decode = adain_rp.MultiScaleAdaINRPNet.decode
+    counts = rpst.install()
+    try:
+        # import-time aliases in three modules (network/adain_rp.py:3-4, wct_rp.py:2, seg_adain_rp.py:3)
+        assert adain_rp.AdaIN is rpst.adaptive_instance_normalization
+        assert wct_rp.AdaIN is rpst.adaptive_instance_normalization
+        assert sys.modules["network.seg_adain_rp"].AdaIN is rpst.adaptive_instance_normalization
+        assert adain_rp.AdaINSeg is rpst.adaptive_instance_normalization_with_segment
+        assert counts["calc_mean_std"] >= 6 and counts["AdaIN"] >= 3
+        for mod in (base, adain_rp, wct_rp, sanet, mrf_rp):
+            assert mod.calc_mean_std is rpst.calc_mean_std
+        assert sanet.SANet is rpst.SANet and sanet.Transform is rpst.Transform
+        assert sanet.mean_variance_norm is rpst.mean_variance_norm
+        assert mrf_rp.MRFLoss is rpst.MRFLoss and base.cal_dist is rpst.cal_dist
+        assert wct_rp.matrix_sqrt is rpst.matrix_sqrt
+        assert wct_rp.WCTRPNet.fuse is not None and "WCTRPNet.fuse" in counts
+        assert adain_rp.MultiScaleAdaINRPNet.decode is not orig_decode
+        assert adain_rp.LDMSAdaINRPNet2.decode is adain_rp.LDMSAdaINRPNet.decode     # inherited patch
+        assert net.SELayer is rpst.SELayer or sys.modules["network.attention"].SELayer is rpst.SELayer
+        assert rpst.install() == {}                                                # idempotent
+    finally:
+        rpst.uninstall()
+    assert base.adaptive_instance_normalization is orig_adain
+    assert adain_rp.MultiScaleAdaINRPNet.decode is orig_decode
+
+
+def test_state_dict_names_match_reference():
+    import torch
+    import rpst
+    load_reference()
+    sanet = sys.modules["network.sanet"]
+    torch.manual_seed(0)
+    for ours, theirs in [(rpst.SANet(8), sanet.SANet(8)), (rpst.Transform(8), sanet.Transform(8)),
+                         (rpst.AdaptiveSANet(8, 64, "aea"), sanet.AdaptiveSANet(8, 64, "aea")),
+                         (rpst.AdaptiveTransform(8, 64, 16, "relu"), sanet.AdaptiveTransform(8, 64, 16, "relu")),
+                         (rpst.SELayer(32), sys.modules["network.attention"].SELayer(32))]:
+        a, b = ours.state_dict(), theirs.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+        ours.load_state_dict(b)   # reference checkpoints load unchanged

@@ -1,0 +1,140 @@
+"""Per-op measurements for the other BASELINE configs (one JSON line each): rpst kernels vs the
+reference's eager op sequence on the same GPU.  GPU box only.
+    python tools/bench_ops.py [adain1 seg wct sanet mrf bwd]"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rpst  # noqa: E402
+from oracle import restate as R  # noqa: E402  (bench tool: eager-GPU restatements for comparison)
+
+dev = torch.device("cuda")
+PEAK_GBS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+PEAK_TF = 1668.9
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def eager_stats(x):
+    n, c = x.shape[:2]
+    f = x.reshape(n, c, -1)
+    return f.mean(2).view(n, c, 1, 1), (f.var(2) + 1e-5).sqrt().view(n, c, 1, 1)
+
+
+def eager_adain(c, s):
+    ms, ss = eager_stats(s)
+    mc, sc = eager_stats(c)
+    return (c - mc) / sc * ss + ms
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def bench_adain1():
+    c, s = R.synth_features((1, 512, 64, 64), cfg=1, device=dev)
+    t = timeit(lambda: rpst.adaptive_instance_normalization(c, s), 50)
+    te = timeit(lambda: eager_adain(c, s), 50)
+    emit(op="adain config#1 1x512x64x64", rpst_us=t * 1e3, eager_gpu_us=te * 1e3, speedup=te / t,
+         note="launch-latency bound: 25 MB algorithmic = 3.9 us at the HBM peak")
+
+
+def bench_bwd():
+    shape = (8, 256, 512, 512)
+    c, s = R.synth_features(shape, cfg=2, device=dev)
+    c.requires_grad_(); s.requires_grad_()
+    g = torch.randn(shape, device=dev)
+    out = rpst.adaptive_instance_normalization(c, s)
+    t = timeit(lambda: torch.autograd.grad(out, (c, s), g, retain_graph=True), 5)
+    E = c.numel() * 4
+    emit(op="adain backward 8x256x512x512", ms=t, GBs=5 * E / t / 1e6, frac_of_peak=5 * E / t / 1e6 / PEAK_GBS)
+
+
+def bench_seg():
+    n, ch, h, w = 1, 256, 1024, 2048
+    c, s = R.synth_features((n, ch, h, w), cfg=5, device=dev)
+    cl = R.synth_labels(n, h, w, seed=4000, device=dev)
+    sl = R.synth_labels(n, h, w, seed=5000, device=dev)
+    t = timeit(lambda: rpst.seg_adain_batch(c, s, cl, sl), 5)
+    E = c.numel() * 4
+    emit(op="seg-adain config#5 1x256x1024x2048, 19 labels", ms=t, GBs=(3 * E + 2 * h * w) / t / 1e6,
+         frac_of_peak=(3 * E + 2 * h * w) / t / 1e6 / PEAK_GBS)
+
+
+def bench_wct():
+    n, ch, h, w = 4, 256, 512, 512
+    c, s = R.synth_features((n, ch, h, w), cfg=3, device=dev)
+    t = timeit(lambda: rpst.wct_fuse(c, s), 3, 1)
+    t16 = timeit(lambda: rpst.wct_fuse(c, s, precision="bf16"), 3, 1)
+
+    def eager_one():   # the reference's fp64 eager path for ONE sample (network/wct_rp.py:157-166)
+        cf = c[0].reshape(ch, -1).double(); sf = s[0].reshape(ch, -1).double()
+        return R.whiten_and_color(cf, sf).float()
+    te = timeit(eager_one, 1, 1)
+    flops = 3 * 2 * ch * ch * h * w * n
+    emit(op="wct config#3 (4 of 16 samples) 256x512x512", ms_per_sample=t / n, bf16_ms_per_sample=t16 / n,
+         eager_gpu_fp64_ms_per_sample=te, speedup_vs_eager=te / (t / n), algorithmic_TFLOPs=flops / t / 1e9,
+         algorithmic_GBs=4 * c.numel() * 4 / t / 1e6)
+
+
+def bench_sanet():
+    for (b, l_side) in ((2, 64), (1, 128)):
+        ch = 512
+        g = torch.Generator(device=dev).manual_seed(4)
+        f = torch.randn(b, ch, l_side, l_side, device=dev, generator=g) * 0.3
+        k = torch.randn(b, ch, l_side, l_side, device=dev, generator=g) * 0.3
+        v = torch.randn(b, ch, l_side, l_side, device=dev, generator=g)
+        L = l_side * l_side
+        t3 = timeit(lambda: rpst.attention_core(f, k, v), 3, 1)
+        t1 = timeit(lambda: rpst.attention_core(f, k, v, precision="bf16"), 3, 1)
+
+        def eager():
+            F = f.reshape(b, ch, -1); G = k.reshape(b, ch, -1); H = v.reshape(b, ch, -1)
+            S = torch.softmax(torch.bmm(F.transpose(1, 2), G), -1)
+            return torch.bmm(H, S.transpose(1, 2))
+        te = timeit(eager, 3, 1)
+        flops = 4 * L * L * ch * b
+        emit(op=f"sanet attention core config#4 b={b} L={L} C=512", fp32grade_ms=t3, bf16_ms=t1, eager_gpu_fp32_ms=te,
+             algorithmic_TFLOPs_fp32grade=flops / t3 / 1e9, algorithmic_TFLOPs_bf16=flops / t1 / 1e9,
+             speedup_fp32grade=te / t3, speedup_bf16=te / t1)
+
+
+def bench_mrf():
+    ch, side, k = 512, 64, 5
+    c, s = R.synth_features((1, ch, side, side), cfg=6, device=dev)
+    t = timeit(lambda: rpst.mrf_match(c, s, k, want_loss=True), 5)
+
+    def eager():
+        a = c.view(ch, -1); b = s.view(ch, -1)
+        an = torch.nn.functional.normalize(a, dim=0); bn = torch.nn.functional.normalize(b, dim=0)
+        m = an.t() @ bn
+        aff = torch.zeros_like(m)
+        aff.scatter_(0, torch.topk(m, k, 0)[1], 1.0); aff.scatter_(1, torch.topk(m, k, 1)[1], 1.0)
+        d = (a * a).sum(0)[:, None] + (b * b).sum(0)[None] - 2 * a.t() @ b
+        return (aff * d).sum() / (side * side * k)
+    te = timeit(eager, 5)
+    emit(op="mrf match+loss C=512 L=4096 k=5", rpst_ms=t, eager_gpu_ms=te, speedup=te / t)
+
+
+ALL = {"adain1": bench_adain1, "bwd": bench_bwd, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "mrf": bench_mrf}
+for name in (sys.argv[1:] or list(ALL)):
+    try:
+        ALL[name]()
+    except Exception as e:  # keep going: one op failing must not hide the others
+        emit(op=name, error=repr(e)[:300])
