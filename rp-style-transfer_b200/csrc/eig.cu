@@ -80,14 +80,19 @@ __device__ __forceinline__ double rotate_pair(double* x, double* y, int lane) {
     aa = warp_sum_f64(aa);
     bb = warp_sum_f64(bb);
     gg = warp_sum_f64(gg);
-    const double denom = sqrt(aa * bb);
-    if (!(denom > 0.0)) return 0.0;
-    const double rel = fabs(gg) / denom;
-    if (rel <= 1e-15) return rel;
-    const double zeta = (bb - aa) / (2.0 * gg);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    const double c = 1.0 / sqrt(1.0 + t * t);
+    // The rotation ANGLE only steers convergence (Jacobi is self-correcting), so it is evaluated in fp32;
+    // orthogonality of the rotation (c^2 + s^2 = 1) is what preserves the spectrum, so c, s are fp64.
+    const float aaf = (float)aa, bbf = (float)bb, ggf = (float)gg;
+    const float prod = aaf * bbf;
+    if (!(prod > 0.f)) return 0.0;
+    const float relf = fabsf(ggf) * rsqrtf(prod);
+    if (relf <= 1e-15f) return (double)relf;
+    const float zeta = (float)(bb - aa) / (2.f * ggf);   // difference in fp64: near-degenerate pairs cancel in fp32
+    const float tf = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+    const double t = (double)tf;
+    const double c = rsqrt(fma(t, t, 1.0));
     const double s = c * t;
+    const double rel = (double)relf;
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
         x[i * 32 + lane] = c * xv[i] - s * yv[i];

@@ -8,11 +8,13 @@
 //                         (hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM, ~2^-16 relative error,
 //                         i.e. fp32-grade results at one third of the bf16 tensor rate).
 //
-// Kernel anatomy (one 128 x BN output tile per CTA, 6 warps):
+// Kernel anatomy (persistent, one CTA per SM walking 128 x 256 output tiles, 6 warps):
 //   warp 0 / 1 thread : TMA producer — one 1-D bulk copy per 16 KiB operand tile into a 4-stage ring
-//   warp 1            : allocates TMEM; 1 thread issues tcgen05.mma (4 x K=16 per stage) and commits
-//                       the stage back to the producer / the accumulator to the epilogue
-//   warps 2..5        : epilogue — tcgen05.ld (each warp its 32-lane TMEM quarter), scale/add, store
+//   warp 1            : allocates TMEM (2 x 256 columns); 1 thread issues tcgen05.mma (M=128, N=256, K=16,
+//                       4 per stage), commits the stage back to the producer and the finished
+//                       accumulator to the epilogue
+//   warps 2..5        : epilogue — tcgen05.ld (each warp its 32-lane TMEM quarter), scale/add, store;
+//                       runs concurrently with the MMAs of the next tile (double-buffered accumulator)
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -63,6 +65,9 @@ __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
 // ------------------------------------------------------------------------------------------ gemm
 constexpr int kGemmStages = 4;
 constexpr int kGemmThreads = 192;
+constexpr int kGemmBN = 256;                         // output tile: 128 x 256
+constexpr int kGemmBTiles = kGemmBN / kTileRows;     // 16 KiB B tiles per stage
+constexpr uint32_t kGemmStageBytes = kTileBytes * (1 + kGemmBTiles);
 
 struct GemmParams {
     const __nv_bfloat16* a_hi;
@@ -73,123 +78,159 @@ struct GemmParams {
     int64_t m, n;        // valid output extent
     int64_t ldo;         // output row stride (elements)
     int k_tiles;         // K / 64 (padded): tile pitch of the packed operands
-    int k_per_split;     // k tiles handled by one blockIdx.z slice (== k_tiles without split-K)
+    int k_per_split;     // k tiles handled by one split-K slice (== k_tiles without split-K)
+    int splits;
     int64_t split_stride;  // elements between the partial outputs of consecutive slices
+    int m_tiles, n_tiles;  // 128-row A tiles; 256-column output tiles
+    int n_tiles128;        // 128-row B tiles actually present in the packed operand
     int passes;          // 1 or 3
     float alpha;
     const float* row_add;  // [m] or null
     const float* col_add;  // [n] or null
 };
 
-template <int BN>
+// Persistent: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (A-tile-major order so that
+// concurrently running CTAs share operand tiles in L2).  Two 256-column TMEM accumulators: the epilogue
+// of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams p) {
-    constexpr int B_TILES = BN / kTileRows;                         // 16 KiB B tiles per stage
-    constexpr uint32_t STAGE_BYTES = kTileBytes * (1 + B_TILES);
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles must start on a 1024-byte boundary of the shared address space
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t full[kGemmStages], empty[kGemmStages], acc_full;
+    __shared__ uint64_t full[kGemmStages], empty[kGemmStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = blockIdx.y, nb = blockIdx.x;
-    const int k_begin = blockIdx.z * p.k_per_split;
-    const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
-    const int total_kb = k_count * p.passes;
-    float* const out = p.out + (int64_t)blockIdx.z * p.split_stride;
+    const int tiles_per_split = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_per_split * p.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(&acc_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);   // one arrival per epilogue warp
+        }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, BN);
+    if (warp == 1) tmem_alloc(&tmem_slot, 2 * kGemmBN);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_acc = tmem_slot;
+    const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             const uint64_t pol = policy_evict_last();   // operands are re-read by other CTAs: keep in L2
-            for (int kb = 0; kb < total_kb; ++kb) {
-                const int s = kb % kGemmStages;
-                mbar_wait(&empty[s], ((kb / kGemmStages) & 1) ^ 1);
-                const int pass = kb / k_count, kk = k_begin + kb % k_count;
-                const __nv_bfloat16* a_src = pass == 2 ? p.a_lo : p.a_hi;
-                const __nv_bfloat16* b_src = pass == 1 ? p.b_lo : p.b_hi;
-                unsigned char* st = smem + (size_t)s * STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_1d(st, reinterpret_cast<const char*>(a_src) + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
-                            kTileBytes, &full[s], pol);
-#pragma unroll
-                for (int t = 0; t < B_TILES; ++t)
-                    tma_load_1d(st + kTileBytes * (1 + t),
-                                reinterpret_cast<const char*>(b_src) +
-                                    (((int64_t)nb * B_TILES + t) * p.k_tiles + kk) * kTileBytes,
+            uint32_t it = 0;                             // running k-block counter across tiles
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int z = t / tiles_per_split, rem = t % tiles_per_split;
+                const int mb = rem / p.n_tiles, nb = rem % p.n_tiles;
+                const int k_begin = z * p.k_per_split;
+                const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
+                const int nsub = min(kGemmBTiles, p.n_tiles128 - nb * kGemmBTiles);
+                for (int kb = 0; kb < k_count * p.passes; ++kb, ++it) {
+                    const int s = it % kGemmStages;
+                    mbar_wait(&empty[s], ((it / kGemmStages) & 1) ^ 1);
+                    const int pass = kb / k_count, kk = k_begin + kb % k_count;
+                    const __nv_bfloat16* a_src = pass == 2 ? p.a_lo : p.a_hi;
+                    const __nv_bfloat16* b_src = pass == 1 ? p.b_lo : p.b_hi;
+                    unsigned char* st = smem + (size_t)s * kGemmStageBytes;
+                    mbar_arrive_expect_tx(&full[s], kTileBytes * (1 + nsub));
+                    tma_load_1d(st, reinterpret_cast<const char*>(a_src) + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
                                 kTileBytes, &full[s], pol);
+                    for (int sub = 0; sub < nsub; ++sub)
+                        tma_load_1d(st + kTileBytes * (1 + sub),
+                                    reinterpret_cast<const char*>(b_src) +
+                                        (((int64_t)nb * kGemmBTiles + sub) * p.k_tiles + kk) * kTileBytes,
+                                    kTileBytes, &full[s], pol);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-            for (int kb = 0; kb < total_kb; ++kb) {
-                const int s = kb % kGemmStages;
-                mbar_wait(&full[s], (kb / kGemmStages) & 1);
+            uint32_t it = 0;
+            int ti = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+                const int z = t / tiles_per_split, rem = t % tiles_per_split;
+                const int nb = rem % p.n_tiles;
+                const int k_begin = z * p.k_per_split;
+                const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
+                const int nsub = min(kGemmBTiles, p.n_tiles128 - nb * kGemmBTiles);
+                const uint32_t idesc = umma_idesc_bf16(128, 128 * nsub);
+                const int buf = ti & 1;
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * kGemmBN);
+                mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);    // epilogue drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + kTileBytes;
+                const int total_kb = k_count * p.passes;
+                for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                    const int s = it % kGemmStages;
+                    mbar_wait(&full[s], (it / kGemmStages) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * kGemmStageBytes);
+                    const uint32_t b_addr = a_addr + kTileBytes;
 #pragma unroll
-                for (int k = 0; k < kTileK / kUmmaK; ++k) {
-                    // B rows beyond 128 live in the next 16 KiB tile: same SBO (1024 B per 8 rows) holds
-                    umma_bf16_ss(tmem_acc, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
-                                 umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, kb > 0 || k > 0);
+                    for (int k = 0; k < kTileK / kUmmaK; ++k) {
+                        // B rows 128..255 live in the next 16 KiB tile: the 1024-byte group stride still holds
+                        umma_bf16_ss(tmem_acc, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                                     umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, kb > 0 || k > 0);
+                    }
+                    umma_commit(&empty[s]);                           // stage free once these MMAs have read it
+                    if (kb == total_kb - 1) umma_commit(&acc_full[buf]);  // accumulator complete
                 }
-                umma_commit(&empty[s]);                      // stage free once these MMAs have read it
-                if (kb == total_kb - 1) umma_commit(&acc_full);  // accumulator complete
             }
         }
     } else {
         // epilogue warps 2..5: TMEM lane quarter = warp % 4
         const int q = warp & 3;
-        mbar_wait(&acc_full, 0);
-        tcgen05_fence_after();
-        const int64_t row = (int64_t)mb * 128 + q * 32 + lane;
-        const float radd = (p.row_add && row < p.m) ? __ldg(p.row_add + row) : 0.f;
+        int ti = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const int z = t / tiles_per_split, rem = t % tiles_per_split;
+            const int mb = rem / p.n_tiles, nb = rem % p.n_tiles;
+            const int buf = ti & 1;
+            float* const out = p.out + (int64_t)z * p.split_stride;
+            mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+            tcgen05_fence_after();
+            const int64_t row = (int64_t)mb * 128 + q * 32 + lane;
+            const float radd = (p.row_add && row < p.m) ? __ldg(p.row_add + row) : 0.f;
+            const int ncols = (int)min((int64_t)kGemmBN, p.n - (int64_t)nb * kGemmBN);   // valid columns of this tile
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int64_t col0 = (int64_t)nb * BN + c0;
-            if (row < p.m) {
-                float* dst = out + row * p.ldo + col0;
-                if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t)(buf * kGemmBN) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                const int64_t col0 = (int64_t)nb * kGemmBN + c0;
+                if (row < p.m) {
+                    float* dst = out + row * p.ldo + col0;
+                    if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o;
-                        o.x = fmaf(p.alpha, v[j + 0], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 0) : 0.f));
-                        o.y = fmaf(p.alpha, v[j + 1], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 1) : 0.f));
-                        o.z = fmaf(p.alpha, v[j + 2], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 2) : 0.f));
-                        o.w = fmaf(p.alpha, v[j + 3], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 3) : 0.f));
-                        *reinterpret_cast<float4*>(dst + j) = o;
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = fmaf(p.alpha, v[j + 0], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 0) : 0.f));
+                            o.y = fmaf(p.alpha, v[j + 1], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 1) : 0.f));
+                            o.z = fmaf(p.alpha, v[j + 2], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 2) : 0.f));
+                            o.w = fmaf(p.alpha, v[j + 3], radd + (p.col_add ? __ldg(p.col_add + col0 + j + 3) : 0.f));
+                            *reinterpret_cast<float4*>(dst + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.n)
+                                dst[j] = fmaf(p.alpha, v[j], radd + (p.col_add ? __ldg(p.col_add + col0 + j) : 0.f));
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.n)
-                            dst[j] = fmaf(p.alpha, v[j], radd + (p.col_add ? __ldg(p.col_add + col0 + j) : 0.f));
                 }
             }
+            // hand the accumulator back to the MMA thread
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_acc, BN);
+        tmem_dealloc(tmem_base, 2 * kGemmBN);
     }
 }
 
@@ -253,17 +294,23 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
     if (splits > p.k_tiles) splits = p.k_tiles;
     p.k_per_split = (p.k_tiles + splits - 1) / splits;
     splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;   // no empty slice
+    p.splits = splits;
     p.split_stride = split_stride;
+    p.m_tiles = (int)((m + 127) / 128);
+    p.n_tiles = (int)((n + kGemmBN - 1) / kGemmBN);
+    p.n_tiles128 = (int)((n + 127) / 128);
     p.passes = passes; p.alpha = alpha; p.row_add = row_add; p.col_add = col_add;
-    constexpr int BN = 128;
-    constexpr size_t smem = (size_t)kGemmStages * kTileBytes * (1 + BN / kTileRows) + 1024;
+    constexpr size_t smem = (size_t)kGemmStages * kGemmStageBytes + 1024;
     static bool configured = false;
     if (!configured) {
-        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + 127) / 128), (unsigned)splits);
-    gemm_packed_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(p);
+    const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * splits;
+    RPST_CHECK_ARG(total_tiles < (1ll << 30), "gemm_packed: too many output tiles");
+    int64_t grid = sm_count();
+    if (grid > total_tiles) grid = total_tiles;
+    gemm_packed_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }

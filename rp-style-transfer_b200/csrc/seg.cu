@@ -17,6 +17,7 @@
 // unusable labels are copied through bit-exactly.
 #include "common.cuh"
 #include "plane_io.cuh"
+#include "async.cuh"
 
 namespace rpst {
 namespace {
@@ -309,6 +310,393 @@ __global__ void __launch_bounds__(kPipeThreads, 3) seg_pipe_kernel(SegParams p) 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-staged segment kernel (16-byte aligned planes): the structure of adain_tma_kernel — producer
+// warp + one shared-memory stage per consumer group — with three differences:
+//  * an item also carries its 4 KiB label chunk; per-lane (label, S1, S2) run accumulation with a
+//    whole-float4 fast path when the four labels equal the running label (real maps are blocky);
+//  * statistics go to per-(plane, tensor, label) fp64 accumulators with a few REDs per warp-item, the
+//    plane's completion is a counter of warp-items (release fence per warp-item; the consumer is
+//    waiting for its next TMA stage anyway, so the fence latency is off the critical path);
+//  * the MERGE item turns accumulators into a per-plane coefficient table [256] that apply items
+//    cache in shared memory per consumer group and re-load only when the plane changes.
+// ------------------------------------------------------------------------------------------
+constexpr int kSegItemElems = 4096;
+constexpr int kSegGroupWarps = 4;
+constexpr int kSegGroupThreads = kSegGroupWarps * 32;
+constexpr int kSegWarpVecs = kSegItemElems / 4 / kSegGroupWarps;   // 256 float4 per warp per item
+constexpr int kSegLaneVecs = kSegWarpVecs / 32;                    // 8
+constexpr int kSegTicketBatch = 8;
+
+struct SegTmaParams {
+    const float* content;
+    const float* style;
+    const uint8_t* c_lab;
+    const uint8_t* s_lab;
+    const float* prev;
+    float* out;
+    int64_t n, channels, hw_c, hw_s;
+    float eps;
+    int ic, is, lag;             // content / style chunks per plane, statistics lead in planes
+    unsigned total_items;
+    unsigned* ticket;            // starts at 0xFFFFFFFF
+    int* done;                   // [planes] warp-items finished
+    int* ready;                  // [planes] coefficient table published
+    const int* cnt;              // [n][2][256]
+    const int* first;            // [n][2][256]
+    float* shift;                // [planes][2][256]  K_l = first pixel of label l in that plane
+    double2* gsum;               // [planes][2][256] (S1, S2)
+    float4* coef;                // [planes][256] (mu_c, a, mu_s, usable)
+};
+
+struct __align__(16) SegDesc {
+    int64_t plane;
+    int kind;      // 0 content statistics, 1 style statistics, 2 apply, 3 merge, -1 stop
+    int chunk;
+    int nvec;
+    int pad;
+};
+
+struct SegDecoded {
+    int64_t plane;
+    int kind, chunk;
+};
+
+__global__ void seg_shift_kernel(SegTmaParams p) {
+    const int64_t planes = p.n * p.channels;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= planes * 2 * kLabels) return;
+    const int l = (int)(idx % kLabels), which = (int)((idx / kLabels) & 1);
+    const int64_t plane = idx / (2 * kLabels), sample = plane / p.channels;
+    const int slot = (int)((sample * 2 + which) * kLabels + l);
+    float v = 0.f;
+    if (p.cnt[slot] > 0) {
+        const int64_t hw = which ? p.hw_s : p.hw_c;
+        v = (which ? p.style : p.content)[plane * hw + p.first[slot]];
+    }
+    p.shift[idx] = v;
+}
+
+__device__ __forceinline__ void seg_decode(unsigned t, const SegTmaParams& p, int& kind, int64_t& plane, int& chunk) {
+    const unsigned P = (unsigned)(p.n * p.channels), L = (unsigned)p.lag, Lm = L / 2;
+    const unsigned Ic = (unsigned)p.ic, St = (unsigned)(p.ic + p.is);
+    auto stat = [&](unsigned pl, unsigned u) {
+        plane = pl;
+        if (u < Ic) { kind = 0; chunk = (int)u; } else { kind = 1; chunk = (int)(u - Ic); }
+    };
+    unsigned n = (L - Lm) * St;
+    if (t < n) { stat(t / St, t % St); return; }
+    t -= n; n = Lm * (St + 1);
+    if (t < n) {
+        const unsigned j = t / (St + 1), u = t % (St + 1);
+        if (u < St) stat((L - Lm) + j, u); else { kind = 3; plane = j; chunk = 0; }
+        return;
+    }
+    t -= n; n = (P - L) * (St + 1 + Ic);
+    if (t < n) {
+        const unsigned j = t / (St + 1 + Ic), u = t % (St + 1 + Ic);
+        if (u < St) stat(L + j, u);
+        else if (u == St) { kind = 3; plane = Lm + j; chunk = 0; }
+        else { kind = 2; plane = j; chunk = (int)(u - St - 1); }
+        return;
+    }
+    t -= n; n = (L - Lm) * (1 + Ic);
+    if (t < n) {
+        const unsigned j = t / (1 + Ic), u = t % (1 + Ic);
+        if (u == 0) { kind = 3; plane = (P - L + Lm) + j; chunk = 0; }
+        else { kind = 2; plane = (P - L) + j; chunk = (int)(u - 1); }
+        return;
+    }
+    t -= n;
+    kind = 2; plane = (P - Lm) + t / Ic; chunk = (int)(t % Ic);
+}
+
+template <int G>
+__global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(SegTmaParams p) {
+    constexpr int STAGE_BYTES = 2 * kSegItemElems * 4 + kSegItemElems;          // data, prev, labels
+    constexpr int CACHE_BYTES = kLabels * (int)(sizeof(float4) + sizeof(float) + 1) ;  // coef, shift, usable
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* stages = smem_raw;
+    unsigned char* caches = smem_raw + (size_t)G * STAGE_BYTES;
+    SegDesc* desc = reinterpret_cast<SegDesc*>(caches + (size_t)G * ((CACHE_BYTES + 127) / 128 * 128));
+    uint64_t* full = reinterpret_cast<uint64_t*>(desc + G);
+    uint64_t* empty = full + G;
+    SegDecoded* dec = reinterpret_cast<SegDecoded*>(empty + G);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kSegGroupWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================================================================ producer warp
+        const uint64_t pol_first = policy_evict_first();
+        const uint64_t pol_last = policy_evict_last();
+        unsigned next_base = 0;
+        if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kSegTicketBatch) + 1u;
+        unsigned seq = 0;
+        for (;;) {
+            const unsigned base = __shfl_sync(0xffffffffu, next_base, 0);
+            if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kSegTicketBatch) + 1u;
+            if (lane < kSegTicketBatch) {
+                int kind = -1, chunk = 0;
+                int64_t plane = 0;
+                const unsigned t = base + (unsigned)lane;
+                if (t < p.total_items) seg_decode(t, p, kind, plane, chunk);
+                dec[lane].kind = kind; dec[lane].chunk = chunk; dec[lane].plane = plane;
+            }
+            __syncwarp();
+            bool finished = false;
+            if (lane == 0) {
+                for (int i = 0; i < kSegTicketBatch; ++i) {
+                    const int kind = dec[i].kind;
+                    if (kind < 0) {
+                        for (int g = 0; g < G; ++g, ++seq) {
+                            const int stage = (int)(seq % G);
+                            mbar_wait(&empty[stage], ((seq / G) & 1u) ^ 1u);
+                            desc[stage].kind = -1;
+                            mbar_arrive(&full[stage]);
+                        }
+                        finished = true;
+                        break;
+                    }
+                    const int chunk = dec[i].chunk;
+                    const int64_t plane = dec[i].plane;
+                    const int stage = (int)(seq % G);
+                    mbar_wait(&empty[stage], ((seq / G) & 1u) ^ 1u);
+                    SegDesc* d = &desc[stage];
+                    d->plane = plane; d->kind = kind; d->chunk = chunk;
+                    if (kind == 3) {
+                        d->nvec = 0;
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        const bool is_style = kind == 1;
+                        const int64_t hw = is_style ? p.hw_s : p.hw_c;
+                        const int64_t e0 = (int64_t)chunk * kSegItemElems;
+                        const int64_t rem = hw - e0;
+                        const int nvec = (int)((rem < kSegItemElems ? rem : kSegItemElems) / 4);
+                        d->nvec = nvec;
+                        const uint32_t bytes = (uint32_t)nvec * 16u;
+                        unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
+                        const int64_t sample = plane / p.channels;
+                        const float* src = (is_style ? p.style : p.content) + plane * hw + e0;
+                        const uint8_t* lab = (is_style ? p.s_lab : p.c_lab) + sample * hw + e0;
+                        const bool has_prev = kind == 2 && p.prev != nullptr;
+                        mbar_arrive_expect_tx(&full[stage], bytes + (has_prev ? bytes : 0u) + (uint32_t)nvec * 4u);
+                        tma_load_1d(st, src, bytes, &full[stage], kind == 0 ? pol_last : pol_first);
+                        if (has_prev)
+                            tma_load_1d(st + kSegItemElems * 4, p.prev + plane * hw + e0, bytes, &full[stage], pol_first);
+                        tma_load_1d(st + 2 * kSegItemElems * 4, lab, (uint32_t)nvec * 4u, &full[stage], pol_last);
+                    }
+                    ++seq;
+                }
+            }
+            finished = __shfl_sync(0xffffffffu, (int)finished, 0) != 0;
+            if (finished) return;
+            __syncwarp();
+        }
+    }
+
+    // ==================================================================== consumers
+    const int group = (warp - 1) / kSegGroupWarps;
+    const int gw = (warp - 1) % kSegGroupWarps;
+    const int gt = gw * 32 + lane;
+    unsigned char* cache = caches + (size_t)group * ((CACHE_BYTES + 127) / 128 * 128);
+    float4* c_coef = reinterpret_cast<float4*>(cache);
+    float* c_shift = reinterpret_cast<float*>(cache + kLabels * sizeof(float4));
+    unsigned char* c_use = cache + kLabels * (sizeof(float4) + sizeof(float));
+    const uint64_t pol_first = policy_evict_first();
+    const int stat_target = kSegGroupWarps * (p.ic + p.is);
+    int64_t cached_stat = -1;    // plane*2+which whose shift table is in the cache
+    int64_t cached_apply = -1;   // plane whose coefficient table is in the cache
+
+    for (unsigned seq = group;; seq += G) {
+        const int stage = (int)(seq % G);
+        mbar_wait(&full[stage], (seq / G) & 1u);
+        const SegDesc* d = &desc[stage];
+        const int kind = d->kind;
+        if (kind < 0) break;
+        const int64_t plane = d->plane;
+        const int chunk = d->chunk;
+        const int wvec = min(max(d->nvec - gw * kSegWarpVecs, 0), kSegWarpVecs);
+        const int64_t sample = plane / p.channels;
+        const unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
+        const float4* a4 = reinterpret_cast<const float4*>(st) + gw * kSegWarpVecs;
+        const float4* b4 = reinterpret_cast<const float4*>(st + kSegItemElems * 4) + gw * kSegWarpVecs;
+        const uint32_t* l4 = reinterpret_cast<const uint32_t*>(st + 2 * kSegItemElems * 4) + gw * kSegWarpVecs;
+
+        if (kind <= 1) {
+            // ---------------- statistics of this warp's 1024 pixels, per label
+            const int64_t key = plane * 2 + kind;
+            if (key != cached_stat) {     // group-uniform: (re)load shift table and usable flags
+                named_bar_sync(1 + group, kSegGroupThreads);
+                for (int l = gt; l < kLabels; l += kSegGroupThreads) {
+                    c_shift[l] = __ldg(p.shift + key * kLabels + l);
+                    c_use[l] = label_usable(__ldg(p.cnt + (sample * 2 + 0) * kLabels + l),
+                                            __ldg(p.cnt + (sample * 2 + 1) * kLabels + l));
+                }
+                named_bar_sync(1 + group, kSegGroupThreads);
+                cached_stat = key;
+            }
+            double2* gs = p.gsum + key * kLabels;
+            int cur = -1;
+            uint32_t cur4 = 0xffffffffu;   // never equals a label word while cur < 0 (cur4 is reset with cur)
+            float shift = 0.f, a1 = 0.f, a2 = 0.f;
+            bool flushed = false;
+            // Each lane owns 32 CONTIGUOUS pixels (8 float4) so that label runs stay long on blocky maps;
+            // the 8 vectors are visited in a lane-rotated order, which keeps the 128-byte-strided
+            // shared-memory reads of a quarter warp on distinct banks.
+#pragma unroll
+            for (int j = 0; j < kSegLaneVecs; ++j) {
+                const int idx = lane * kSegLaneVecs + ((j + lane) & (kSegLaneVecs - 1));
+                if (idx < wvec) {
+                    const float4 v = a4[idx];
+                    const uint32_t lw = l4[idx];
+                    if (lw == cur4 && cur >= 0) {
+                        const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
+                        a1 += (d0 + d1) + (d2 + d3);
+                        a2 = fmaf(d0, d0, a2); a2 = fmaf(d1, d1, a2); a2 = fmaf(d2, d2, a2); a2 = fmaf(d3, d3, a2);
+                    } else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int l = (int)((lw >> (8 * q)) & 0xffu);
+                            if (l != cur) {
+                                if (cur >= 0) {   // label run ended inside the item: flush it
+                                    atomicAdd(&gs[cur].x, (double)a1);
+                                    atomicAdd(&gs[cur].y, (double)a2);
+                                    flushed = true;
+                                }
+                                if (c_use[l]) { cur = l; shift = c_shift[l]; cur4 = (uint32_t)l * 0x01010101u; }
+                                else { cur = -1; cur4 = 0xffffffffu; }
+                                a1 = 0.f; a2 = 0.f;
+                            }
+                            if (cur >= 0) {
+                                const float dd = e[q] - shift;
+                                a1 += dd;
+                                a2 = fmaf(dd, dd, a2);
+                            }
+                        }
+                    }
+                }
+            }
+            // the stage has been consumed
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            // final flush, aggregated per distinct label inside the warp; lane 0 issues the REDs
+            unsigned remaining = __ballot_sync(0xffffffffu, cur >= 0);
+            while (remaining) {
+                const int leader = __ffs(remaining) - 1;
+                const int l = __shfl_sync(0xffffffffu, cur, leader);
+                const bool mine = cur == l;
+                const float r1 = warp_sum(mine ? a1 : 0.f);
+                const float r2 = warp_sum(mine ? a2 : 0.f);
+                if (lane == 0) {
+                    atomicAdd(&gs[l].x, (double)r1);
+                    atomicAdd(&gs[l].y, (double)r2);
+                }
+                remaining &= ~__ballot_sync(0xffffffffu, mine);
+            }
+            if (flushed) __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(&p.done[plane], 1);
+            }
+        } else if (kind == 2) {
+            // ---------------- apply
+            if (plane != cached_apply) {   // group-uniform: wait for the merge item, cache the coefficient table
+                if (lane == 0 && ld_acquire(&p.ready[plane]) == 0) {
+                    const uint64_t t0 = global_timer_ns();
+                    while (ld_acquire(&p.ready[plane]) == 0) {
+                        __nanosleep(64);
+                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                    }
+                }
+                named_bar_sync(1 + group, kSegGroupThreads);
+                for (int l = gt; l < kLabels; l += kSegGroupThreads) c_coef[l] = __ldcg(&p.coef[plane * kLabels + l]);
+                named_bar_sync(1 + group, kSegGroupThreads);
+                cached_apply = plane;
+            }
+            const bool has_prev = p.prev != nullptr;
+            float4* o4 = reinterpret_cast<float4*>(p.out + plane * p.hw_c + (int64_t)chunk * kSegItemElems) + gw * kSegWarpVecs;
+            uint32_t last_w = 0;
+            float4 cf = c_coef[0];
+            bool have = false;
+#pragma unroll
+            for (int j = 0; j < kSegLaneVecs; ++j) {
+                const int idx = j * 32 + lane;
+                if (idx < wvec) {
+                    const float4 v = a4[idx];
+                    const uint32_t lw = l4[idx];
+                    float4 o;
+                    const uint32_t b0 = lw & 0xffu;
+                    if (lw == b0 * 0x01010101u) {   // all four pixels carry the same label
+                        if (!have || lw != last_w) { cf = c_coef[b0]; last_w = lw; have = true; }
+                        o.x = fmaf(v.x - cf.x, cf.y, cf.z);
+                        o.y = fmaf(v.y - cf.x, cf.y, cf.z);
+                        o.z = fmaf(v.z - cf.x, cf.y, cf.z);
+                        o.w = fmaf(v.w - cf.x, cf.y, cf.z);
+                    } else {
+                        const float4 c0 = c_coef[b0], c1 = c_coef[(lw >> 8) & 0xffu], c2 = c_coef[(lw >> 16) & 0xffu],
+                                     c3 = c_coef[lw >> 24];
+                        o.x = fmaf(v.x - c0.x, c0.y, c0.z);
+                        o.y = fmaf(v.y - c1.x, c1.y, c1.z);
+                        o.z = fmaf(v.z - c2.x, c2.y, c2.z);
+                        o.w = fmaf(v.w - c3.x, c3.y, c3.z);
+                    }
+                    if (has_prev) {
+                        const float4 q = b4[idx];
+                        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                    }
+                    stg_f4_hint(reinterpret_cast<float*>(o4 + idx), o, pol_first);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        } else {
+            // ---------------- merge: accumulators of one plane -> coefficient table
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (gw == 0) {
+                if (lane == 0 && ld_acquire(&p.done[plane]) != stat_target) {
+                    const uint64_t t0 = global_timer_ns();
+                    while (ld_acquire(&p.done[plane]) != stat_target) {
+                        __nanosleep(64);
+                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                    }
+                }
+                __syncwarp();
+                __threadfence();
+                for (int l = lane; l < kLabels; l += 32) {
+                    const int nc = __ldg(p.cnt + (sample * 2 + 0) * kLabels + l), ns = __ldg(p.cnt + (sample * 2 + 1) * kLabels + l);
+                    float4 cf = make_float4(0.f, 1.f, 0.f, 0.f);   // identity: (c-0)*1+0 == c bit-exactly
+                    if (label_usable(nc, ns)) {
+                        const double2 gc = __ldcg(p.gsum + (plane * 2 + 0) * kLabels + l);
+                        const double2 gsv = __ldcg(p.gsum + (plane * 2 + 1) * kLabels + l);
+                        const double kc = (double)__ldg(p.shift + (plane * 2 + 0) * kLabels + l);
+                        const double ks = (double)__ldg(p.shift + (plane * 2 + 1) * kLabels + l);
+                        const double dnc = (double)nc, dns = (double)ns;
+                        const double mu_c = kc + gc.x / dnc, mu_s = ks + gsv.x / dns;
+                        const double m2c = fmax(gc.y - gc.x * gc.x / dnc, 0.0), m2s = fmax(gsv.y - gsv.x * gsv.x / dns, 0.0);
+                        const double sd_c = sqrt(m2c / (dnc - 1.0) + (double)p.eps), sd_s = sqrt(m2s / (dns - 1.0) + (double)p.eps);
+                        cf = make_float4((float)mu_c, (float)(sd_s / sd_c), (float)mu_s, 1.f);
+                    }
+                    __stcg(&p.coef[plane * kLabels + l], cf);
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_release(&p.ready[plane], 1);
+            }
+        }
+    }
+}
+
 __global__ void seg_export_info_kernel(const int* __restrict__ cnt, int32_t* __restrict__ info, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n * kLabels) return;
@@ -341,6 +729,46 @@ SegLayout seg_layout(int64_t n, int64_t c) {
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+struct SegTmaLayout {
+    size_t ticket, zero_beg, done, cnt, gsum, zero_end, first, first_bytes, shift, coef, total;
+};
+SegTmaLayout seg_tma_layout(int64_t n, int64_t c) {
+    const size_t planes = (size_t)(n * c);
+    SegTmaLayout l;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    l.ticket = take(256);
+    l.zero_beg = o;
+    l.done = take(planes * 2 * sizeof(int));           // done + ready
+    l.cnt = take((size_t)n * 2 * kLabels * sizeof(int));
+    l.gsum = take(planes * 2 * kLabels * sizeof(double2));
+    l.zero_end = o;
+    l.first_bytes = align_up((size_t)n * 2 * kLabels * sizeof(int), 256);
+    l.first = take(l.first_bytes);
+    l.shift = take(planes * 2 * kLabels * sizeof(float));
+    l.coef = take(planes * kLabels * sizeof(float4));
+    l.total = o;
+    return l;
+}
+
+template <int G>
+int launch_seg_tma(const SegTmaParams& p, cudaStream_t st) {
+    constexpr size_t stage = 2 * kSegItemElems * 4 + kSegItemElems;
+    constexpr size_t cache = (kLabels * (sizeof(float4) + sizeof(float) + 1) + 127) / 128 * 128;
+    constexpr size_t smem = G * (stage + cache) + G * sizeof(SegDesc) + 2 * G * sizeof(uint64_t) +
+                            kSegTicketBatch * sizeof(SegDecoded);
+    static bool configured = false;
+    if (!configured) {
+        RPST_CUDA(cudaFuncSetAttribute(seg_tma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t grid = sm_count();
+    if (grid > (int64_t)p.total_items) grid = p.total_items;
+    seg_tma_kernel<G><<<(int)grid, 32 + G * kSegGroupThreads, smem, st>>>(p);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
 }  // namespace
 
 int64_t adain_tuning_value(const char* name);
@@ -352,7 +780,8 @@ using namespace rpst;
 extern "C" size_t rpst_seg_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     (void)hw_c; (void)hw_s;
     if (n <= 0 || c <= 0) return 256;
-    return seg_layout(n, c).total;
+    const size_t a = seg_layout(n, c).total, b = seg_tma_layout(n, c).total;
+    return a > b ? a : b;
 }
 
 extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, const uint8_t* c_labels,
@@ -365,14 +794,59 @@ extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, cons
     RPST_CHECK_ARG(hw_s > 0, "seg_adain: empty style map");
     RPST_CHECK_ARG(hw_c < (1ll << 31) && hw_s < (1ll << 31), "seg_adain: plane too large");
     RPST_CHECK_ARG(out != content && out != style && out != prev, "seg_adain: out must not alias an input");
-    const SegLayout l = seg_layout(n, c);
-    if (workspace == nullptr || workspace_bytes < l.total) {
-        set_error("seg_adain: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+    const size_t need = rpst_seg_adain_workspace_bytes(n, c, hw_c, hw_s);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("seg_adain: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
         return RPST_ERR_WORKSPACE;
     }
-    RPST_CHECK_ARG(aligned(workspace, 16), "seg_adain: workspace must be 16-byte aligned");
+    RPST_CHECK_ARG(aligned(workspace, 256), "seg_adain: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* base = static_cast<char*>(workspace);
+    const int64_t hw_max0 = hw_c > hw_s ? hw_c : hw_s;
+    int hist_blocks0 = (int)((hw_max0 + 16383) / 16384);
+    if (hist_blocks0 > 256) hist_blocks0 = 256;
+    const bool tma_ok = adain_tuning_value("adain_path") == 0 && hw_c % 16 == 0 && hw_s % 16 == 0 &&
+                        aligned(content, 16) && aligned(style, 16) && aligned(out, 16) && (!prev || aligned(prev, 16)) &&
+                        aligned(c_labels, 16) && aligned(s_labels, 16);
+    if (tma_ok) {
+        const SegTmaLayout t = seg_tma_layout(n, c);
+        SegTmaParams q{};
+        q.content = content; q.style = style; q.c_lab = c_labels; q.s_lab = s_labels; q.prev = prev; q.out = out;
+        q.n = n; q.channels = c; q.hw_c = hw_c; q.hw_s = hw_s; q.eps = eps;
+        q.ticket = reinterpret_cast<unsigned*>(base + t.ticket);
+        q.done = reinterpret_cast<int*>(base + t.done);
+        q.ready = q.done + n * c;
+        int* cnt = reinterpret_cast<int*>(base + t.cnt);
+        int* first = reinterpret_cast<int*>(base + t.first);
+        q.cnt = cnt; q.first = first;
+        q.gsum = reinterpret_cast<double2*>(base + t.gsum);
+        q.shift = reinterpret_cast<float*>(base + t.shift);
+        q.coef = reinterpret_cast<float4*>(base + t.coef);
+        RPST_CUDA(cudaMemsetAsync(base + t.ticket, 0xff, 256, st));
+        RPST_CUDA(cudaMemsetAsync(base + t.zero_beg, 0, t.zero_end - t.zero_beg, st));
+        RPST_CUDA(cudaMemsetAsync(base + t.first, 0x7f, t.first_bytes, st));
+        seg_hist_kernel<<<dim3(hist_blocks0, (unsigned)n, 2), 256, 0, st>>>(c_labels, s_labels, hw_c, hw_s, cnt, first);
+        RPST_CUDA(cudaGetLastError());
+        if (label_info) {
+            const int64_t tot = n * kLabels;
+            seg_export_info_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cnt, label_info, n);
+            RPST_CUDA(cudaGetLastError());
+        }
+        const int64_t planes = n * c;
+        seg_shift_kernel<<<(unsigned)((planes * 2 * kLabels + 255) / 256), 256, 0, st>>>(q);
+        RPST_CUDA(cudaGetLastError());
+        q.ic = (int)((hw_c + kSegItemElems - 1) / kSegItemElems);
+        q.is = (int)((hw_s + kSegItemElems - 1) / kSegItemElems);
+        const int64_t plane_bytes = hw_c * (int64_t)sizeof(float);
+        int64_t lag = (adain_tuning_value("adain_lag_bytes") + plane_bytes - 1) / plane_bytes;
+        if (lag < 3) lag = 3;
+        q.lag = (int)(lag < planes ? lag : planes);
+        const int64_t total = planes * (2ll * q.ic + q.is + 1);
+        RPST_CHECK_ARG(total < (1ll << 31), "seg_adain: too many work items (%lld); split the call", (long long)total);
+        q.total_items = (unsigned)total;
+        return launch_seg_tma<5>(q, st);
+    }
+    const SegLayout l = seg_layout(n, c);
     SegParams p{};
     p.content = content; p.style = style; p.c_lab = c_labels; p.s_lab = s_labels; p.prev = prev; p.out = out;
     p.n = n; p.channels = c; p.hw_c = hw_c; p.hw_s = hw_s; p.eps = eps;

@@ -72,7 +72,7 @@ struct WctLayout {
 };
 
 int cov_splits(int64_t c, int64_t hw) {
-    const int64_t tiles = ((c + 127) / 128) * ((c + 127) / 128);
+    const int64_t tiles = ((c + 127) / 128) * ((c + 255) / 256);   // 128 x 256 output tiles of the GEMM
     int64_t s = sm_count() / tiles;
     if (s < 1) s = 1;
     const int64_t kt = (hw + 63) / 64;

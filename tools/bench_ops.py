@@ -83,9 +83,21 @@ def bench_wct():
     t = timeit(lambda: rpst.wct_fuse(c, s), 3, 1)
     t16 = timeit(lambda: rpst.wct_fuse(c, s, precision="bf16"), 3, 1)
 
-    def eager_one():   # the reference's fp64 eager path for ONE sample (network/wct_rp.py:157-166)
+    def msqrt(a, p):
+        a = a.clone(); a.diagonal().add_(1e-4)
+        _, e, vh = torch.linalg.svd(a)
+        v = vh.t()
+        return (v * e.pow(p)) @ v.t()
+
+    def eager_one():   # the reference's fp64 eager op sequence for ONE sample (network/wct_rp.py:82-114,157-166)
         cf = c[0].reshape(ch, -1).double(); sf = s[0].reshape(ch, -1).double()
-        return R.whiten_and_color(cf, sf).float()
+        cm = cf.mean(1, keepdim=True); xc = cf - cm
+        cc = xc @ xc.t() / (xc.shape[1] - 1) + torch.eye(ch, dtype=torch.float64, device=dev)
+        sm = sf.mean(1, keepdim=True); xs = sf - sm
+        cs = xs @ xs.t() / (xs.shape[1] - 1)
+        r, ir = msqrt(cc, 0.5), msqrt(cc, -0.5)
+        t_ = ir @ msqrt(r @ cs @ r, 0.5) @ ir
+        return (t_ @ xc + sm).float()
     te = timeit(eager_one, 1, 1)
     flops = 3 * 2 * ch * ch * h * w * n
     emit(op="wct config#3 (4 of 16 samples) 256x512x512", ms_per_sample=t / n, bf16_ms_per_sample=t16 / n,
