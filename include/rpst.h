@@ -47,6 +47,7 @@ RPST_API const char* rpst_last_error(void);
  *   "adain_hints"      0/1: L2 eviction-priority hints on the streaming loads/stores
  *   "adain_ctas_per_sm" persistent CTAs per SM for the register-staged pipelined kernel
  *   "adain_path"       0: TMA-staged kernel when planes are 16-byte aligned (default), 1: register-staged
+ *   "seg_lag_bytes"    segment AdaIN: bytes of content between a plane's statistics and its apply
  *   "adain_stages"     TMA shared-memory stages = consumer warp groups per CTA (2..7, 32 KiB each) */
 RPST_API int rpst_set_tuning(const char* name, int64_t value);
 RPST_API int64_t rpst_get_tuning(const char* name);

@@ -30,6 +30,7 @@ struct Tuning {
     int64_t ctas_per_sm = 4;
     int64_t path = 0;    // 0: TMA-staged kernel when alignment allows, 1: register-staged kernel
     int64_t stages = 6;  // TMA ring depth (32 KiB per stage)
+    int64_t seg_lag_bytes = 256ll << 20;  // segment AdaIN: content bytes between statistics and apply
 };
 Tuning g_tuning;
 
@@ -1154,6 +1155,7 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     else if (!strcmp(name, "adain_ctas_per_sm")) slot = &g_tuning.ctas_per_sm;
     else if (!strcmp(name, "adain_path")) slot = &g_tuning.path;
     else if (!strcmp(name, "adain_stages")) slot = &g_tuning.stages;
+    else if (!strcmp(name, "seg_lag_bytes")) slot = &g_tuning.seg_lag_bytes;
     if (!slot) return 0;
     if (set) *slot = v;
     if (out) *out = *slot;

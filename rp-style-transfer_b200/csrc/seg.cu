@@ -2,19 +2,18 @@
 // loop network/adain_rp.py:313-319.
 //
 // The reference walks the label set on the host (np.where per label, index_select gather, ~12
-// launches, index_copy_ scatter; per label, per level, per sample).  Here the whole batch is two
-// launches:
-//   seg_hist_kernel  — per sample: pixel count and first pixel index of every label value (0..255)
-//                      in the content and in the style map (labels are shared by all channels).
-//   seg_pipe_kernel  — the ticket-pipelined structure of adain.cu: statistics items (content and
-//                      style chunks of plane p+D) run ahead of apply items (plane p), the content
-//                      is re-read from L2.  Statistics are per (plane,label) shifted sums
-//                      S1 = sum(x-K_l), S2 = sum((x-K_l)^2) with K_l = the first pixel of label l in
-//                      that plane, accumulated run-length-compressed in registers, warp-aggregated,
-//                      reduced in shared memory and finally with one fp32 atomic per (item,label).
+// launches, index_copy_ scatter; per label, per level, per sample).  Here the whole batch is:
+//   seg_hist_kernel   per sample: pixel count and first pixel index of every label value (0..255) in the
+//                     content and in the style map (labels are shared by all channels)
+//   seg_dense_kernel  dense ids of the usable labels (validity rule evaluated on the device)
+//   seg_shift_kernel  per (plane, tensor, label) shift K_l = first pixel of the label in that plane
+//   seg_tma_kernel    TMA-staged pipeline (16-byte aligned planes, <= 64 usable labels per sample);
+//                     statistics are per-label shifted sums S1 = sum(x-K_l), S2 = sum((x-K_l)^2)
+//   seg_pipe_kernel   register-staged fallback (unaligned shapes, or > 64 usable labels: chosen on the
+//                     device through a flag, without host synchronisation)
 // The validity rule (network/base.py:435: label taken from the CONTENT map; cnt_c>10, cnt_s>10,
-// cnt_c/cnt_s<100, cnt_s/cnt_c<100) is evaluated on the device from the histogram; pixels of
-// unusable labels are copied through bit-exactly.
+// cnt_c/cnt_s<100, cnt_s/cnt_c<100) uses exact integer comparisons; pixels of unusable labels are
+// copied through bit-exactly.
 #include "common.cuh"
 #include "plane_io.cuh"
 #include "async.cuh"
@@ -45,6 +44,7 @@ struct SegParams {
     int* first;             // [n][2][256]
     float2* gsum;           // [planes][2][256] (S1, S2)
     float4* coef;           // [planes][256] (mu_c, a, mu_s, valid)
+    const int* run_flag;    // null: always run; else run only if *run_flag != 0 (slot-path overflow)
 };
 
 __global__ void __launch_bounds__(256) seg_hist_kernel(const uint8_t* __restrict__ c_lab, const uint8_t* __restrict__ s_lab,
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kPipeThreads, 3) seg_pipe_kernel(SegParams p) 
     const uint64_t pol_last = policy_evict_last();
     const bool hint = p.hints != 0;
     const int lane = threadIdx.x & 31;
+    if (p.run_flag != nullptr && __ldg(p.run_flag) == 0) return;
 
     if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1u);
     __syncthreads();
@@ -315,11 +316,14 @@ __global__ void __launch_bounds__(kPipeThreads, 3) seg_pipe_kernel(SegParams p) 
 // warp + one shared-memory stage per consumer group — with three differences:
 //  * an item also carries its 4 KiB label chunk; per-lane (label, S1, S2) run accumulation with a
 //    whole-float4 fast path when the four labels equal the running label (real maps are blocky);
-//  * statistics go to per-(plane, tensor, label) fp64 accumulators with a few REDs per warp-item, the
-//    plane's completion is a counter of warp-items (release fence per warp-item; the consumer is
-//    waiting for its next TMA stage anyway, so the fence latency is off the critical path);
-//  * the MERGE item turns accumulators into a per-plane coefficient table [256] that apply items
-//    cache in shared memory per consumer group and re-load only when the plane changes.
+//  * the four warps of a group add their runs into a shared-memory table indexed by dense label id and
+//    publish one self-validating 8-byte slot per usable label and item (no fence, no global atomic);
+//  * MERGE tickets bypass the stage ring: two dedicated merge warps per CTA (one thread per dense label)
+//    sum a plane's slots in fp64 in a fixed order (deterministic) and publish the per-plane coefficient
+//    table [256]; merges therefore never queue behind apply items that wait for them;
+//  * apply items cache the coefficient table in shared memory per group, re-loaded when the plane changes.
+//  The statistics->apply lag is long (seg_lag_bytes, 256 MiB) because a plane's merge walks ~1000 slots;
+//  at 1024x2048 the content re-read therefore comes from HBM (4E instead of 3E bytes): next round's item.
 // ------------------------------------------------------------------------------------------
 constexpr int kSegItemElems = 4096;
 constexpr int kSegGroupWarps = 4;
@@ -327,6 +331,7 @@ constexpr int kSegGroupThreads = kSegGroupWarps * 32;
 constexpr int kSegWarpVecs = kSegItemElems / 4 / kSegGroupWarps;   // 256 float4 per warp per item
 constexpr int kSegLaneVecs = kSegWarpVecs / 32;                    // 8
 constexpr int kSegTicketBatch = 8;
+constexpr int kMaxDense = 64;    // usable labels per sample handled by the slot path
 
 struct SegTmaParams {
     const float* content;
@@ -340,12 +345,16 @@ struct SegTmaParams {
     int ic, is, lag;             // content / style chunks per plane, statistics lead in planes
     unsigned total_items;
     unsigned* ticket;            // starts at 0xFFFFFFFF
-    int* done;                   // [planes] warp-items finished
     int* ready;                  // [planes] coefficient table published
     const int* cnt;              // [n][2][256]
     const int* first;            // [n][2][256]
     float* shift;                // [planes][2][256]  K_l = first pixel of label l in that plane
-    double2* gsum;               // [planes][2][256] (S1, S2)
+    const unsigned char* dense;  // [n][256] dense id of a usable label (255: unusable)
+    const unsigned char* label_of;  // [n][kMaxDense] inverse map
+    const int* dense_count;      // [n] usable labels of the sample
+    const int* overflow;         // != 0: some sample has more than kMaxDense usable labels -> fallback kernel runs
+    float2* slots;               // [planes][2][imax][kMaxDense] (S1, S2) per item; 0xFF-filled = not written
+    int imax;                    // max(ic, is)
     float4* coef;                // [planes][256] (mu_c, a, mu_s, usable)
 };
 
@@ -362,6 +371,30 @@ struct SegDecoded {
     int kind, chunk;
 };
 
+// one block per sample: dense ids of the usable labels (increasing label order), inverse map, count
+__global__ void __launch_bounds__(kLabels) seg_dense_kernel(const int* __restrict__ cnt, unsigned char* __restrict__ dense,
+                                                            unsigned char* __restrict__ label_of,
+                                                            int* __restrict__ dense_count, int* __restrict__ overflow) {
+    __shared__ int warp_cnt[kLabels / 32];
+    const int sample = blockIdx.x, l = threadIdx.x, lane = l & 31, w = l >> 5;
+    const bool use = label_usable(cnt[(sample * 2 + 0) * kLabels + l], cnt[(sample * 2 + 1) * kLabels + l]);
+    const unsigned m = __ballot_sync(0xffffffffu, use);
+    if (lane == 0) warp_cnt[w] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int i = 0; i < kLabels / 32; ++i) {
+        if (i < w) base += warp_cnt[i];
+        total += warp_cnt[i];
+    }
+    const int id = base + __popc(m & ((1u << lane) - 1u));
+    dense[sample * kLabels + l] = (use && id < kMaxDense) ? (unsigned char)id : (unsigned char)255;
+    if (use && id < kMaxDense) label_of[sample * kMaxDense + id] = (unsigned char)l;
+    if (l == 0) {
+        dense_count[sample] = total < kMaxDense ? total : kMaxDense;
+        if (total > kMaxDense) atomicOr(overflow, 1);
+    }
+}
+
 __global__ void seg_shift_kernel(SegTmaParams p) {
     const int64_t planes = p.n * p.channels;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -377,8 +410,30 @@ __global__ void seg_shift_kernel(SegTmaParams p) {
     p.shift[idx] = v;
 }
 
+__device__ __forceinline__ bool slot2_valid(double2 v) {
+    return (unsigned)(__double_as_longlong(v.x) >> 32) != 0xffffffffu && (unsigned)(__double_as_longlong(v.y) >> 32) != 0xffffffffu;
+}
+__device__ __forceinline__ double2 ld_slot2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ld_slot1(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool slot1_valid(float2 v) {
+    return __float_as_uint(v.x) != 0xffffffffu && __float_as_uint(v.y) != 0xffffffffu;
+}
+
+__device__ __forceinline__ float canon_f(float v) {
+    return __float_as_uint(v) == 0xffffffffu ? __uint_as_float(0x7fc00000u) : v;
+}
+
 __device__ __forceinline__ void seg_decode(unsigned t, const SegTmaParams& p, int& kind, int64_t& plane, int& chunk) {
-    const unsigned P = (unsigned)(p.n * p.channels), L = (unsigned)p.lag, Lm = L / 2;
+    // the merge of a plane follows its statistics by one plane; the apply trails by L planes
+    const unsigned P = (unsigned)(p.n * p.channels), L = (unsigned)p.lag, Lm = L - 1;
     const unsigned Ic = (unsigned)p.ic, St = (unsigned)(p.ic + p.is);
     auto stat = [&](unsigned pl, unsigned u) {
         plane = pl;
@@ -411,23 +466,34 @@ __device__ __forceinline__ void seg_decode(unsigned t, const SegTmaParams& p, in
     kind = 2; plane = (P - Lm) + t / Ic; chunk = (int)(t % Ic);
 }
 
+constexpr int kSegMergeThreads = 64;   // two dedicated merge warps per CTA (one thread per dense label)
+constexpr int kSegMailbox = 8;
+
 template <int G>
-__global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(SegTmaParams p) {
+__global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 1) seg_tma_kernel(SegTmaParams p) {
     constexpr int STAGE_BYTES = 2 * kSegItemElems * 4 + kSegItemElems;          // data, prev, labels
-    constexpr int CACHE_BYTES = kLabels * (int)(sizeof(float4) + sizeof(float) + 1) ;  // coef, shift, usable
+    constexpr int CACHE_BYTES = kLabels * (int)(sizeof(float4) + sizeof(float) + 1) + 2 * kMaxDense * 2 * (int)sizeof(float);  // coef, shift, dense id, accumulators
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
     unsigned char* caches = smem_raw + (size_t)G * STAGE_BYTES;
     SegDesc* desc = reinterpret_cast<SegDesc*>(caches + (size_t)G * ((CACHE_BYTES + 127) / 128 * 128));
     uint64_t* full = reinterpret_cast<uint64_t*>(desc + G);
     uint64_t* empty = full + G;
-    SegDecoded* dec = reinterpret_cast<SegDecoded*>(empty + G);
+    uint64_t* mfull = empty + G;              // merge mailbox: producer -> merge warps
+    uint64_t* mempty = mfull + kSegMailbox;
+    int64_t* mbox = reinterpret_cast<int64_t*>(mempty + kSegMailbox);   // plane id, -1 = stop
+    SegDecoded* dec = reinterpret_cast<SegDecoded*>(mbox + kSegMailbox);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (__ldg(p.overflow) != 0) return;   // more usable labels than slot capacity: the fallback kernel handles the call
     if (threadIdx.x == 0) {
         for (int s = 0; s < G; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kSegGroupWarps);
+        }
+        for (int s = 0; s < kSegMailbox; ++s) {
+            mbar_init(&mfull[s], 1);
+            mbar_init(&mempty[s], kSegMergeThreads / 32);
         }
         mbar_fence_init();
     }
@@ -439,7 +505,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
         const uint64_t pol_last = policy_evict_last();
         unsigned next_base = 0;
         if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kSegTicketBatch) + 1u;
-        unsigned seq = 0;
+        unsigned seq = 0, mseq = 0;
         for (;;) {
             const unsigned base = __shfl_sync(0xffffffffu, next_base, 0);
             if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kSegTicketBatch) + 1u;
@@ -453,8 +519,20 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
             __syncwarp();
             bool finished = false;
             if (lane == 0) {
+                // merges first: they bypass the stage ring and must never wait behind a busy stage (their own
+                // dependencies, the plane's statistics items, are a whole round older than this batch)
+                for (int i = 0; i < kSegTicketBatch; ++i) {
+                    if (dec[i].kind == 3) {
+                        const int ms = (int)(mseq % kSegMailbox);
+                        mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
+                        mbox[ms] = dec[i].plane;
+                        mbar_arrive(&mfull[ms]);
+                        ++mseq;
+                    }
+                }
                 for (int i = 0; i < kSegTicketBatch; ++i) {
                     const int kind = dec[i].kind;
+                    if (kind == 3) continue;
                     if (kind < 0) {
                         for (int g = 0; g < G; ++g, ++seq) {
                             const int stage = (int)(seq % G);
@@ -462,6 +540,10 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
                             desc[stage].kind = -1;
                             mbar_arrive(&full[stage]);
                         }
+                        const int ms = (int)(mseq % kSegMailbox);
+                        mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
+                        mbox[ms] = -1;
+                        mbar_arrive(&mfull[ms]);
                         finished = true;
                         break;
                     }
@@ -471,10 +553,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
                     mbar_wait(&empty[stage], ((seq / G) & 1u) ^ 1u);
                     SegDesc* d = &desc[stage];
                     d->plane = plane; d->kind = kind; d->chunk = chunk;
-                    if (kind == 3) {
-                        d->nvec = 0;
-                        mbar_arrive(&full[stage]);
-                    } else {
+                    {
                         const bool is_style = kind == 1;
                         const int64_t hw = is_style ? p.hw_s : p.hw_c;
                         const int64_t e0 = (int64_t)chunk * kSegItemElems;
@@ -502,6 +581,72 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
         }
     }
 
+    if (warp > G * kSegGroupWarps) {
+        // ================================================================ merge warps
+        // thread dn owns dense label dn: it sums that label's (S1, S2) over every item slot of the plane
+        // (content then style, fixed order, fp64, 32 loads in flight) and writes the label's coefficients.
+        const int dn = threadIdx.x - (32 + G * kSegGroupThreads);
+        for (unsigned mseq = 0;; ++mseq) {
+            const int ms = (int)(mseq % kSegMailbox);
+            mbar_wait(&mfull[ms], (mseq / kSegMailbox) & 1u);
+            const int64_t plane = mbox[ms];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mempty[ms]);
+            if (plane < 0) break;
+            const int64_t sample = plane / p.channels;
+            const int dcount = __ldg(p.dense_count + sample);
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+            if (dn < dcount) {
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    const int items = which ? p.is : p.ic;
+                    const float2* base = p.slots + ((plane * 2 + which) * p.imax) * kMaxDense + dn;
+                    constexpr int kUnroll = 32;
+                    for (int c0 = 0; c0 < items; c0 += kUnroll) {
+                        float2 v[kUnroll];
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u) {
+                            v[u] = make_float2(0.f, 0.f);
+                            if (c0 + u < items) v[u] = ld_slot1(base + (int64_t)(c0 + u) * kMaxDense);
+                        }
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u) {
+                            if (c0 + u < items) {
+                                if (!slot1_valid(v[u])) {
+                                    const float2* sp = base + (int64_t)(c0 + u) * kMaxDense;
+                                    const uint64_t t0 = global_timer_ns();
+                                    do {   // straggling statistics item
+                                        __nanosleep(64);
+                                        v[u] = ld_slot1(sp);
+                                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                                    } while (!slot1_valid(v[u]));
+                                }
+                                s4[which * 2 + 0] += (double)v[u].x;
+                                s4[which * 2 + 1] += (double)v[u].y;
+                            }
+                        }
+                    }
+                }
+                const int l = __ldg(p.label_of + sample * kMaxDense + dn);
+                const double dnc = (double)__ldg(p.cnt + (sample * 2 + 0) * kLabels + l);
+                const double dns = (double)__ldg(p.cnt + (sample * 2 + 1) * kLabels + l);
+                const double kc = (double)__ldg(p.shift + (plane * 2 + 0) * kLabels + l);
+                const double ks = (double)__ldg(p.shift + (plane * 2 + 1) * kLabels + l);
+                const double mu_c = kc + s4[0] / dnc, mu_s = ks + s4[2] / dns;
+                const double m2c = fmax(s4[1] - s4[0] * s4[0] / dnc, 0.0), m2s = fmax(s4[3] - s4[2] * s4[2] / dns, 0.0);
+                const double sd_c = sqrt(m2c / (dnc - 1.0) + (double)p.eps), sd_s = sqrt(m2s / (dns - 1.0) + (double)p.eps);
+                __stcg(&p.coef[plane * kLabels + l], make_float4((float)mu_c, (float)(sd_s / sd_c), (float)mu_s, 1.f));
+            }
+            // identity for every unusable label: (c-0)*1+0 == c bit-exactly
+            for (int l = dn; l < kLabels; l += kSegMergeThreads)
+                if (__ldg(p.dense + sample * kLabels + l) == 255) __stcg(&p.coef[plane * kLabels + l], make_float4(0.f, 1.f, 0.f, 0.f));
+            __threadfence();
+            named_bar_sync(15, kSegMergeThreads);
+            if (dn == 0) st_release(&p.ready[plane], 1);
+        }
+        return;
+    }
+
     // ==================================================================== consumers
     const int group = (warp - 1) / kSegGroupWarps;
     const int gw = (warp - 1) % kSegGroupWarps;
@@ -509,11 +654,16 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
     unsigned char* cache = caches + (size_t)group * ((CACHE_BYTES + 127) / 128 * 128);
     float4* c_coef = reinterpret_cast<float4*>(cache);
     float* c_shift = reinterpret_cast<float*>(cache + kLabels * sizeof(float4));
-    unsigned char* c_use = cache + kLabels * (sizeof(float4) + sizeof(float));
+    unsigned char* c_dense = cache + kLabels * (sizeof(float4) + sizeof(float));
+    float* c_acc = reinterpret_cast<float*>(cache + kLabels * (sizeof(float4) + sizeof(float) + 1));  // [2][kMaxDense][2]
     const uint64_t pol_first = policy_evict_first();
-    const int stat_target = kSegGroupWarps * (p.ic + p.is);
     int64_t cached_stat = -1;    // plane*2+which whose shift table is in the cache
     int64_t cached_apply = -1;   // plane whose coefficient table is in the cache
+    int64_t cached_sample = -1;  // sample whose dense-id map is in the cache
+    int dcount = 0;
+    unsigned sparity = 0;        // accumulator double buffering (per statistics item)
+    for (int i = gt; i < 2 * kMaxDense * 2; i += kSegGroupThreads) c_acc[i] = 0.f;
+    named_bar_sync(1 + group, kSegGroupThreads);
 
     for (unsigned seq = group;; seq += G) {
         const int stage = (int)(seq % G);
@@ -525,29 +675,34 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
         const int chunk = d->chunk;
         const int wvec = min(max(d->nvec - gw * kSegWarpVecs, 0), kSegWarpVecs);
         const int64_t sample = plane / p.channels;
-        const unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
+        unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
         const float4* a4 = reinterpret_cast<const float4*>(st) + gw * kSegWarpVecs;
         const float4* b4 = reinterpret_cast<const float4*>(st + kSegItemElems * 4) + gw * kSegWarpVecs;
         const uint32_t* l4 = reinterpret_cast<const uint32_t*>(st + 2 * kSegItemElems * 4) + gw * kSegWarpVecs;
 
         if (kind <= 1) {
-            // ---------------- statistics of this warp's 1024 pixels, per label
-            const int64_t key = plane * 2 + kind;
-            if (key != cached_stat) {     // group-uniform: (re)load shift table and usable flags
+            if (sample != cached_sample) {   // group-uniform: dense-id map of this sample
                 named_bar_sync(1 + group, kSegGroupThreads);
-                for (int l = gt; l < kLabels; l += kSegGroupThreads) {
-                    c_shift[l] = __ldg(p.shift + key * kLabels + l);
-                    c_use[l] = label_usable(__ldg(p.cnt + (sample * 2 + 0) * kLabels + l),
-                                            __ldg(p.cnt + (sample * 2 + 1) * kLabels + l));
-                }
+                for (int l = gt; l < kLabels; l += kSegGroupThreads) c_dense[l] = __ldg(p.dense + sample * kLabels + l);
+                dcount = __ldg(p.dense_count + sample);
+                named_bar_sync(1 + group, kSegGroupThreads);
+                cached_sample = sample;
+            }
+        }
+
+        if (kind <= 1) {
+            // ---------------- statistics of this group's 4096 pixels, per (dense) label
+            const int64_t key = plane * 2 + kind;
+            if (key != cached_stat) {     // group-uniform: shift table of this plane/tensor
+                named_bar_sync(1 + group, kSegGroupThreads);
+                for (int l = gt; l < kLabels; l += kSegGroupThreads) c_shift[l] = __ldg(p.shift + key * kLabels + l);
                 named_bar_sync(1 + group, kSegGroupThreads);
                 cached_stat = key;
             }
-            double2* gs = p.gsum + key * kLabels;
-            int cur = -1;
-            uint32_t cur4 = 0xffffffffu;   // never equals a label word while cur < 0 (cur4 is reset with cur)
+            float* acc = c_acc + sparity * (kMaxDense * 2);
+            int cur = -1;                  // dense id of the running label (-1: unusable, skipped)
+            uint32_t cur4 = 0xffffffffu;   // its label value replicated x4; never matches while cur < 0
             float shift = 0.f, a1 = 0.f, a2 = 0.f;
-            bool flushed = false;
             // Each lane owns 32 CONTIGUOUS pixels (8 float4) so that label runs stay long on blocky maps;
             // the 8 vectors are visited in a lane-rotated order, which keeps the 128-byte-strided
             // shared-memory reads of a quarter warp on distinct banks.
@@ -563,16 +718,18 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
                         a2 = fmaf(d0, d0, a2); a2 = fmaf(d1, d1, a2); a2 = fmaf(d2, d2, a2); a2 = fmaf(d3, d3, a2);
                     } else {
                         const float e[4] = {v.x, v.y, v.z, v.w};
+                        int curl = cur >= 0 ? (int)(cur4 & 0xffu) : -1;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int l = (int)((lw >> (8 * q)) & 0xffu);
-                            if (l != cur) {
+                            if (l != curl) {
                                 if (cur >= 0) {   // label run ended inside the item: flush it
-                                    atomicAdd(&gs[cur].x, (double)a1);
-                                    atomicAdd(&gs[cur].y, (double)a2);
-                                    flushed = true;
+                                    atomicAdd(&acc[cur * 2 + 0], a1);
+                                    atomicAdd(&acc[cur * 2 + 1], a2);
                                 }
-                                if (c_use[l]) { cur = l; shift = c_shift[l]; cur4 = (uint32_t)l * 0x01010101u; }
+                                const int dn = c_dense[l];
+                                curl = l;
+                                if (dn != 255) { cur = dn; shift = c_shift[l]; cur4 = (uint32_t)l * 0x01010101u; }
                                 else { cur = -1; cur4 = 0xffffffffu; }
                                 a1 = 0.f; a2 = 0.f;
                             }
@@ -588,26 +745,23 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
             // the stage has been consumed
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
-            // final flush, aggregated per distinct label inside the warp; lane 0 issues the REDs
-            unsigned remaining = __ballot_sync(0xffffffffu, cur >= 0);
-            while (remaining) {
-                const int leader = __ffs(remaining) - 1;
-                const int l = __shfl_sync(0xffffffffu, cur, leader);
-                const bool mine = cur == l;
-                const float r1 = warp_sum(mine ? a1 : 0.f);
-                const float r2 = warp_sum(mine ? a2 : 0.f);
-                if (lane == 0) {
-                    atomicAdd(&gs[l].x, (double)r1);
-                    atomicAdd(&gs[l].y, (double)r2);
-                }
-                remaining &= ~__ballot_sync(0xffffffffu, mine);
+            // final flush into the group's shared accumulators.  Shared-memory atomics cost one pass per
+            // distinct address, which beats a shuffle tree per distinct label on fine-grained maps and is
+            // a single 32-way same-address pass on blocky ones.
+            if (cur >= 0) {
+                atomicAdd(&acc[cur * 2 + 0], a1);
+                atomicAdd(&acc[cur * 2 + 1], a2);
             }
-            if (flushed) __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                atomicAdd(&p.done[plane], 1);
+            named_bar_sync(1 + group, kSegGroupThreads);
+            // publish: one self-validating 8-byte slot per usable label (no fence, no atomic, no counter)
+            if (gt < dcount) {
+                const float s1 = canon_f(acc[gt * 2 + 0]), s2 = canon_f(acc[gt * 2 + 1]);
+                acc[gt * 2 + 0] = 0.f;
+                acc[gt * 2 + 1] = 0.f;
+                float2* slot = p.slots + ((key * p.imax + chunk) * kMaxDense + gt);
+                asm volatile("st.global.cg.v2.f32 [%0], {%1,%2};" :: "l"(slot), "f"(s1), "f"(s2) : "memory");
             }
+            sparity ^= 1u;
         } else if (kind == 2) {
             // ---------------- apply
             if (plane != cached_apply) {   // group-uniform: wait for the merge item, cache the coefficient table
@@ -659,40 +813,6 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads, 1) seg_tma_kernel(S
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
-        } else {
-            // ---------------- merge: accumulators of one plane -> coefficient table
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (gw == 0) {
-                if (lane == 0 && ld_acquire(&p.done[plane]) != stat_target) {
-                    const uint64_t t0 = global_timer_ns();
-                    while (ld_acquire(&p.done[plane]) != stat_target) {
-                        __nanosleep(64);
-                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
-                    }
-                }
-                __syncwarp();
-                __threadfence();
-                for (int l = lane; l < kLabels; l += 32) {
-                    const int nc = __ldg(p.cnt + (sample * 2 + 0) * kLabels + l), ns = __ldg(p.cnt + (sample * 2 + 1) * kLabels + l);
-                    float4 cf = make_float4(0.f, 1.f, 0.f, 0.f);   // identity: (c-0)*1+0 == c bit-exactly
-                    if (label_usable(nc, ns)) {
-                        const double2 gc = __ldcg(p.gsum + (plane * 2 + 0) * kLabels + l);
-                        const double2 gsv = __ldcg(p.gsum + (plane * 2 + 1) * kLabels + l);
-                        const double kc = (double)__ldg(p.shift + (plane * 2 + 0) * kLabels + l);
-                        const double ks = (double)__ldg(p.shift + (plane * 2 + 1) * kLabels + l);
-                        const double dnc = (double)nc, dns = (double)ns;
-                        const double mu_c = kc + gc.x / dnc, mu_s = ks + gsv.x / dns;
-                        const double m2c = fmax(gc.y - gc.x * gc.x / dnc, 0.0), m2s = fmax(gsv.y - gsv.x * gsv.x / dns, 0.0);
-                        const double sd_c = sqrt(m2c / (dnc - 1.0) + (double)p.eps), sd_s = sqrt(m2s / (dns - 1.0) + (double)p.eps);
-                        cf = make_float4((float)mu_c, (float)(sd_s / sd_c), (float)mu_s, 1.f);
-                    }
-                    __stcg(&p.coef[plane * kLabels + l], cf);
-                }
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) st_release(&p.ready[plane], 1);
-            }
         }
     }
 }
@@ -730,23 +850,31 @@ SegLayout seg_layout(int64_t n, int64_t c) {
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 struct SegTmaLayout {
-    size_t ticket, zero_beg, done, cnt, gsum, zero_end, first, first_bytes, shift, coef, total;
+    size_t ticket, zero_beg, ready, cnt, dcount, overflow, zero_end, first, first_bytes, shift, dense, label_of, coef,
+        slots, slots_bytes, total;
 };
-SegTmaLayout seg_tma_layout(int64_t n, int64_t c) {
+SegTmaLayout seg_tma_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     const size_t planes = (size_t)(n * c);
+    const size_t ic = (size_t)((hw_c + kSegItemElems - 1) / kSegItemElems), is = (size_t)((hw_s + kSegItemElems - 1) / kSegItemElems);
+    const size_t imax = ic > is ? ic : is;
     SegTmaLayout l;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
     l.ticket = take(256);
     l.zero_beg = o;
-    l.done = take(planes * 2 * sizeof(int));           // done + ready
+    l.ready = take(planes * sizeof(int));
     l.cnt = take((size_t)n * 2 * kLabels * sizeof(int));
-    l.gsum = take(planes * 2 * kLabels * sizeof(double2));
+    l.dcount = take((size_t)n * sizeof(int));
+    l.overflow = take(sizeof(int));
     l.zero_end = o;
     l.first_bytes = align_up((size_t)n * 2 * kLabels * sizeof(int), 256);
     l.first = take(l.first_bytes);
     l.shift = take(planes * 2 * kLabels * sizeof(float));
+    l.dense = take((size_t)n * kLabels);
+    l.label_of = take((size_t)n * kMaxDense);
     l.coef = take(planes * kLabels * sizeof(float4));
+    l.slots_bytes = planes * 2 * imax * kMaxDense * sizeof(float2);
+    l.slots = take(l.slots_bytes);
     l.total = o;
     return l;
 }
@@ -754,8 +882,9 @@ SegTmaLayout seg_tma_layout(int64_t n, int64_t c) {
 template <int G>
 int launch_seg_tma(const SegTmaParams& p, cudaStream_t st) {
     constexpr size_t stage = 2 * kSegItemElems * 4 + kSegItemElems;
-    constexpr size_t cache = (kLabels * (sizeof(float4) + sizeof(float) + 1) + 127) / 128 * 128;
+    constexpr size_t cache = (kLabels * (sizeof(float4) + sizeof(float) + 1) + 2 * kMaxDense * 2 * sizeof(float) + 127) / 128 * 128;
     constexpr size_t smem = G * (stage + cache) + G * sizeof(SegDesc) + 2 * G * sizeof(uint64_t) +
+                            2 * kSegMailbox * sizeof(uint64_t) + kSegMailbox * sizeof(int64_t) +
                             kSegTicketBatch * sizeof(SegDecoded);
     static bool configured = false;
     if (!configured) {
@@ -764,7 +893,7 @@ int launch_seg_tma(const SegTmaParams& p, cudaStream_t st) {
     }
     int64_t grid = sm_count();
     if (grid > (int64_t)p.total_items) grid = p.total_items;
-    seg_tma_kernel<G><<<(int)grid, 32 + G * kSegGroupThreads, smem, st>>>(p);
+    seg_tma_kernel<G><<<(int)grid, 32 + G * kSegGroupThreads + kSegMergeThreads, smem, st>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
@@ -778,10 +907,9 @@ int64_t adain_tuning_value(const char* name);
 using namespace rpst;
 
 extern "C" size_t rpst_seg_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
-    (void)hw_c; (void)hw_s;
     if (n <= 0 || c <= 0) return 256;
-    const size_t a = seg_layout(n, c).total, b = seg_tma_layout(n, c).total;
-    return a > b ? a : b;
+    return seg_layout(n, c).total + seg_tma_layout(n, c, hw_c, hw_s).total;   // slot path + fallback path
+
 }
 
 extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, const uint8_t* c_labels,
@@ -808,43 +936,57 @@ extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, cons
     const bool tma_ok = adain_tuning_value("adain_path") == 0 && hw_c % 16 == 0 && hw_s % 16 == 0 &&
                         aligned(content, 16) && aligned(style, 16) && aligned(out, 16) && (!prev || aligned(prev, 16)) &&
                         aligned(c_labels, 16) && aligned(s_labels, 16);
+    const int* run_flag = nullptr;
     if (tma_ok) {
-        const SegTmaLayout t = seg_tma_layout(n, c);
+        const SegTmaLayout t = seg_tma_layout(n, c, hw_c, hw_s);
         SegTmaParams q{};
         q.content = content; q.style = style; q.c_lab = c_labels; q.s_lab = s_labels; q.prev = prev; q.out = out;
         q.n = n; q.channels = c; q.hw_c = hw_c; q.hw_s = hw_s; q.eps = eps;
         q.ticket = reinterpret_cast<unsigned*>(base + t.ticket);
-        q.done = reinterpret_cast<int*>(base + t.done);
-        q.ready = q.done + n * c;
+        q.ready = reinterpret_cast<int*>(base + t.ready);
         int* cnt = reinterpret_cast<int*>(base + t.cnt);
         int* first = reinterpret_cast<int*>(base + t.first);
-        q.cnt = cnt; q.first = first;
-        q.gsum = reinterpret_cast<double2*>(base + t.gsum);
+        int* dcount = reinterpret_cast<int*>(base + t.dcount);
+        int* overflow = reinterpret_cast<int*>(base + t.overflow);
+        unsigned char* dense = reinterpret_cast<unsigned char*>(base + t.dense);
+        unsigned char* label_of = reinterpret_cast<unsigned char*>(base + t.label_of);
+        q.cnt = cnt; q.first = first; q.dense = dense; q.label_of = label_of; q.dense_count = dcount; q.overflow = overflow;
         q.shift = reinterpret_cast<float*>(base + t.shift);
         q.coef = reinterpret_cast<float4*>(base + t.coef);
+        q.slots = reinterpret_cast<float2*>(base + t.slots);
         RPST_CUDA(cudaMemsetAsync(base + t.ticket, 0xff, 256, st));
         RPST_CUDA(cudaMemsetAsync(base + t.zero_beg, 0, t.zero_end - t.zero_beg, st));
         RPST_CUDA(cudaMemsetAsync(base + t.first, 0x7f, t.first_bytes, st));
+        RPST_CUDA(cudaMemsetAsync(base + t.slots, 0xff, t.slots_bytes, st));
         seg_hist_kernel<<<dim3(hist_blocks0, (unsigned)n, 2), 256, 0, st>>>(c_labels, s_labels, hw_c, hw_s, cnt, first);
+        RPST_CUDA(cudaGetLastError());
+        seg_dense_kernel<<<(unsigned)n, kLabels, 0, st>>>(cnt, dense, label_of, dcount, overflow);
         RPST_CUDA(cudaGetLastError());
         if (label_info) {
             const int64_t tot = n * kLabels;
             seg_export_info_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cnt, label_info, n);
             RPST_CUDA(cudaGetLastError());
+            label_info = nullptr;   // the fallback path below must not export it again
         }
         const int64_t planes = n * c;
         seg_shift_kernel<<<(unsigned)((planes * 2 * kLabels + 255) / 256), 256, 0, st>>>(q);
         RPST_CUDA(cudaGetLastError());
         q.ic = (int)((hw_c + kSegItemElems - 1) / kSegItemElems);
         q.is = (int)((hw_s + kSegItemElems - 1) / kSegItemElems);
+        q.imax = q.ic > q.is ? q.ic : q.is;
         const int64_t plane_bytes = hw_c * (int64_t)sizeof(float);
-        int64_t lag = (adain_tuning_value("adain_lag_bytes") + plane_bytes - 1) / plane_bytes;
+        int64_t lag = (adain_tuning_value("seg_lag_bytes") + plane_bytes - 1) / plane_bytes;
         if (lag < 3) lag = 3;
         q.lag = (int)(lag < planes ? lag : planes);
         const int64_t total = planes * (2ll * q.ic + q.is + 1);
         RPST_CHECK_ARG(total < (1ll << 31), "seg_adain: too many work items (%lld); split the call", (long long)total);
         q.total_items = (unsigned)total;
-        return launch_seg_tma<5>(q, st);
+        const int rc = launch_seg_tma<5>(q, st);
+        if (rc) return rc;
+        // a sample with more than kMaxDense usable labels makes the slot kernel exit at once and the
+        // register-staged kernel below run instead (device-side decision: no host synchronisation)
+        run_flag = overflow;
+        base += t.total;
     }
     const SegLayout l = seg_layout(n, c);
     SegParams p{};
@@ -858,6 +1000,7 @@ extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, cons
     p.gsum = reinterpret_cast<float2*>(base + l.gsum_off);
     p.first = reinterpret_cast<int*>(base + l.first_off);
     p.coef = reinterpret_cast<float4*>(base + l.coef_off);
+    p.run_flag = run_flag;
     RPST_CUDA(cudaMemsetAsync(base, 0, l.zero_bytes, st));
     RPST_CUDA(cudaMemsetAsync(base + l.first_off, 0x7f, l.first_bytes, st));
 
