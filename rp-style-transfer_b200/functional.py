@@ -32,8 +32,24 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_DIRECT_MAX_HW = 16384   # planes up to this size take the register-resident kernel: no workspace needed
+_tiny_ws = {}
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _plane_workspace(query, args, hw: int, device) -> torch.Tensor:
+    """Workspace for the plane kernels; small planes never touch it, so a cached 256-byte buffer is
+    passed and the size query is skipped (config #1 is launch-latency bound, every host us counts)."""
+    if hw <= _DIRECT_MAX_HW:
+        key = (device.type, device.index)
+        ws = _tiny_ws.get(key)
+        if ws is None:
+            ws = _tiny_ws[key] = torch.empty(256, dtype=torch.uint8, device=device)
+        return ws
+    return _workspace(query(*args), device)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -47,7 +63,7 @@ def _stats_raw(feat: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tens
     mean = torch.empty(n * c, dtype=torch.float32, device=feat.device)
     std = torch.empty_like(mean)
     L = _lib.lib()
-    ws = _workspace(L.rpst_stats_workspace_bytes(n * c, hw), feat.device)
+    ws = _plane_workspace(L.rpst_stats_workspace_bytes, (n * c, hw), hw, feat.device)
     _lib.check(L.rpst_stats_nchw(feat.data_ptr(), n * c, hw, eps, mean.data_ptr(), std.data_ptr(),
                                  ws.data_ptr(), ws.numel(), _stream()))
     return mean, std
@@ -58,7 +74,7 @@ def _adain_raw(content, style, prev, out, out_batch_stride, eps, want_saved):
     hw = content[0, 0].numel() if content.numel() else 0
     saved = torch.empty(n * c, 4, dtype=torch.float32, device=content.device) if want_saved else None
     L = _lib.lib()
-    ws = _workspace(L.rpst_adain_workspace_bytes(n, c, hw), content.device)
+    ws = _plane_workspace(L.rpst_adain_workspace_bytes, (n, c, hw), hw, content.device)
     _lib.check(L.rpst_adain_fwd(content.data_ptr(), _ptr(style), _ptr(prev), out.data_ptr(), n, c, hw,
                                 out_batch_stride, eps, _ptr(saved), ws.data_ptr(), ws.numel(), _stream()))
     return saved
@@ -70,7 +86,7 @@ def _adain_bwd_raw(grad_out, content, style, saved, need_style):
     dc = torch.empty_like(content)
     ds = torch.empty_like(content) if need_style else None
     L = _lib.lib()
-    ws = _workspace(L.rpst_adain_bwd_workspace_bytes(n, c, hw), content.device)
+    ws = _plane_workspace(L.rpst_adain_bwd_workspace_bytes, (n, c, hw), hw, content.device)
     _lib.check(L.rpst_adain_bwd(grad_out.data_ptr(), content.data_ptr(), _ptr(style) if need_style else None,
                                 saved.data_ptr(), dc.data_ptr(), _ptr(ds), n, c, hw,
                                 ws.data_ptr(), ws.numel(), _stream()))
@@ -140,18 +156,36 @@ class _StatsFn(torch.autograd.Function):
         return out, None
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _adain_nograd(content, style, prev):
+    out = torch.empty_like(content)
+    c = content.shape[1]
+    hw = content[0, 0].numel() if content.numel() else 0
+    _adain_raw(content, style, prev, out, c * hw, EPS, False)
+    return out
+
+
 def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/base.py:410."""
     assert (content_feat.size() == style_feat.size())
     assert content_feat.dim() == 4
-    return _AdaINFn.apply(_prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"), None)
+    c, s = _prep(content_feat, "content_feat"), _prep(style_feat, "style_feat")
+    if not _needs_grad(c, s):
+        return _adain_nograd(c, s, None)
+    return _AdaINFn.apply(c, s, None)
 
 
 def adain_blend(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """`prev + AdaIN(content_feat, style_feat)` in one pass (network/adain_rp.py:300-301)."""
     assert (content_feat.size() == style_feat.size())
     assert (prev.size() == content_feat.size())
-    return _AdaINFn.apply(_prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"), _prep(prev, "prev"))
+    c, s, p = _prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"), _prep(prev, "prev")
+    if not _needs_grad(c, s, p):
+        return _adain_nograd(c, s, p)
+    return _AdaINFn.apply(c, s, p)
 
 
 def adain_concat(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
@@ -175,7 +209,10 @@ def adain_concat(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: tor
 def mean_variance_norm(feat: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/sanet.py:20."""
     assert feat.dim() == 4
-    return _AdaINFn.apply(_prep(feat, "feat"), None, None)
+    x = _prep(feat, "feat")
+    if not _needs_grad(x):
+        return _adain_nograd(x, None, None)
+    return _AdaINFn.apply(x, None, None)
 
 
 def plane_affine(x: torch.Tensor, scale: torch.Tensor, shift: Optional[torch.Tensor] = None) -> torch.Tensor:
