@@ -63,11 +63,15 @@ __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
 }
 
 // ------------------------------------------------------------------------------------------ gemm
-constexpr int kGemmStages = 4;
 constexpr int kGemmThreads = 192;
 constexpr int kGemmBN = 256;                         // output tile: 128 x 256
-constexpr int kGemmBTiles = kGemmBN / kTileRows;     // 16 KiB B tiles per stage
-constexpr uint32_t kGemmStageBytes = kTileBytes * (1 + kGemmBTiles);
+constexpr int kGemmBTiles = kGemmBN / kTileRows;     // 16 KiB B tiles per stage and precision part
+constexpr uint32_t kGemmPartBytes = kTileBytes * (1 + kGemmBTiles);   // A tile + B tiles of one part (48 KiB)
+// A stage holds one k-tile of both operands.  bf16: hi parts only, 4 stages.  bf16x3: hi AND lo parts
+// (96 KiB), 2 stages — every operand tile is fetched once per output tile and the three MMA groups
+// (hi.hi, hi.lo, lo.hi) are issued from the same stage instead of re-streaming tiles once per pass.
+constexpr int kGemmMaxStages = 4;
+constexpr size_t kGemmSmemBytes = (size_t)kGemmMaxStages * kGemmPartBytes + 1024;
 
 struct GemmParams {
     const __nv_bfloat16* a_hi;
@@ -89,6 +93,13 @@ struct GemmParams {
     const float* col_add;  // [n] or null
 };
 
+__device__ __forceinline__ void gemm_tile(int rem, int m_tiles, int n_tiles, int& mb, int& nb) {
+    // concurrently running CTAs (consecutive tile indices) should share the LARGER operand's tiles in L2:
+    // walk the short dimension fastest
+    if (m_tiles <= n_tiles) { nb = rem / m_tiles; mb = rem % m_tiles; }
+    else { mb = rem / n_tiles; nb = rem % n_tiles; }
+}
+
 // Persistent: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (A-tile-major order so that
 // concurrently running CTAs share operand tiles in L2).  Two 256-column TMEM accumulators: the epilogue
 // of tile i overlaps the MMAs of tile i+1.
@@ -96,7 +107,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles must start on a 1024-byte boundary of the shared address space
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t full[kGemmStages], empty[kGemmStages], acc_full[2], acc_empty[2];
+    __shared__ uint64_t full[kGemmMaxStages], empty[kGemmMaxStages], acc_full[2], acc_empty[2];
+    const int parts = p.passes == 3 ? 2 : 1;                  // hi only, or hi + lo
+    const int stages = kGemmMaxStages / parts;
+    const uint32_t stage_bytes = kGemmPartBytes * parts;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
     const int total_tiles = tiles_per_split * p.splits;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; ++s) {
+        for (int s = 0; s < kGemmMaxStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -126,25 +140,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             uint32_t it = 0;                             // running k-block counter across tiles
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int z = t / tiles_per_split, rem = t % tiles_per_split;
-                const int mb = rem / p.n_tiles, nb = rem % p.n_tiles;
+                int mb, nb;
+                gemm_tile(rem, p.m_tiles, p.n_tiles, mb, nb);
                 const int k_begin = z * p.k_per_split;
                 const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
                 const int nsub = min(kGemmBTiles, p.n_tiles128 - nb * kGemmBTiles);
-                for (int kb = 0; kb < k_count * p.passes; ++kb, ++it) {
-                    const int s = it % kGemmStages;
-                    mbar_wait(&empty[s], ((it / kGemmStages) & 1) ^ 1);
-                    const int pass = kb / k_count, kk = k_begin + kb % k_count;
-                    const __nv_bfloat16* a_src = pass == 2 ? p.a_lo : p.a_hi;
-                    const __nv_bfloat16* b_src = pass == 1 ? p.b_lo : p.b_hi;
-                    unsigned char* st = smem + (size_t)s * kGemmStageBytes;
-                    mbar_arrive_expect_tx(&full[s], kTileBytes * (1 + nsub));
-                    tma_load_1d(st, reinterpret_cast<const char*>(a_src) + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
-                                kTileBytes, &full[s], pol);
-                    for (int sub = 0; sub < nsub; ++sub)
-                        tma_load_1d(st + kTileBytes * (1 + sub),
-                                    reinterpret_cast<const char*>(b_src) +
-                                        (((int64_t)nb * kGemmBTiles + sub) * p.k_tiles + kk) * kTileBytes,
+                for (int kb = 0; kb < k_count; ++kb, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+                    const int kk = k_begin + kb;
+                    unsigned char* st = smem + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], kTileBytes * (1 + nsub) * parts);
+                    for (int part = 0; part < parts; ++part) {
+                        const __nv_bfloat16* a_src = part ? p.a_lo : p.a_hi;
+                        const __nv_bfloat16* b_src = part ? p.b_lo : p.b_hi;
+                        unsigned char* sp = st + (size_t)part * kGemmPartBytes;
+                        tma_load_1d(sp, reinterpret_cast<const char*>(a_src) + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
                                     kTileBytes, &full[s], pol);
+                        for (int sub = 0; sub < nsub; ++sub)
+                            tma_load_1d(sp + kTileBytes * (1 + sub),
+                                        reinterpret_cast<const char*>(b_src) +
+                                            (((int64_t)nb * kGemmBTiles + sub) * p.k_tiles + kk) * kTileBytes,
+                                        kTileBytes, &full[s], pol);
+                    }
                 }
             }
         }
@@ -154,7 +172,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             int ti = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
                 const int z = t / tiles_per_split, rem = t % tiles_per_split;
-                const int nb = rem % p.n_tiles;
+                int mb, nb;
+                gemm_tile(rem, p.m_tiles, p.n_tiles, mb, nb);
+                (void)mb;
                 const int k_begin = z * p.k_per_split;
                 const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
                 const int nsub = min(kGemmBTiles, p.n_tiles128 - nb * kGemmBTiles);
@@ -163,21 +183,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * kGemmBN);
                 mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);    // epilogue drained this accumulator
                 tcgen05_fence_after();
-                const int total_kb = k_count * p.passes;
-                for (int kb = 0; kb < total_kb; ++kb, ++it) {
-                    const int s = it % kGemmStages;
-                    mbar_wait(&full[s], (it / kGemmStages) & 1);
+                for (int kb = 0; kb < k_count; ++kb, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(&full[s], (it / stages) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * kGemmStageBytes);
-                    const uint32_t b_addr = a_addr + kTileBytes;
+                    const uint32_t hi_a = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t hi_b = hi_a + kTileBytes;
+                    const uint32_t lo_a = hi_a + kGemmPartBytes, lo_b = hi_b + kGemmPartBytes;
 #pragma unroll
                     for (int k = 0; k < kTileK / kUmmaK; ++k) {
                         // B rows 128..255 live in the next 16 KiB tile: the 1024-byte group stride still holds
-                        umma_bf16_ss(tmem_acc, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
-                                     umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, kb > 0 || k > 0);
+                        const uint32_t ko = k * kUmmaK * 2;
+                        umma_bf16_ss(tmem_acc, umma_desc_k_sw128(hi_a + ko), umma_desc_k_sw128(hi_b + ko), idesc,
+                                     kb > 0 || k > 0);
+                        if (parts == 2) {
+                            umma_bf16_ss(tmem_acc, umma_desc_k_sw128(hi_a + ko), umma_desc_k_sw128(lo_b + ko), idesc, true);
+                            umma_bf16_ss(tmem_acc, umma_desc_k_sw128(lo_a + ko), umma_desc_k_sw128(hi_b + ko), idesc, true);
+                        }
                     }
                     umma_commit(&empty[s]);                           // stage free once these MMAs have read it
-                    if (kb == total_kb - 1) umma_commit(&acc_full[buf]);  // accumulator complete
+                    if (kb == k_count - 1) umma_commit(&acc_full[buf]);   // accumulator complete
                 }
             }
         }
@@ -187,7 +212,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
         int ti = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
             const int z = t / tiles_per_split, rem = t % tiles_per_split;
-            const int mb = rem / p.n_tiles, nb = rem % p.n_tiles;
+            int mb, nb;
+            gemm_tile(rem, p.m_tiles, p.n_tiles, mb, nb);
             const int buf = ti & 1;
             float* const out = p.out + (int64_t)z * p.split_stride;
             mbar_wait(&acc_full[buf], (ti >> 1) & 1);
@@ -300,7 +326,7 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
     p.n_tiles = (int)((n + kGemmBN - 1) / kGemmBN);
     p.n_tiles128 = (int)((n + 127) / 128);
     p.passes = passes; p.alpha = alpha; p.row_add = row_add; p.col_add = col_add;
-    constexpr size_t smem = (size_t)kGemmStages * kGemmStageBytes + 1024;
+    constexpr size_t smem = kGemmSmemBytes;
     static bool configured = false;
     if (!configured) {
         RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
