@@ -80,6 +80,16 @@ RPST_API int rpst_adain_fwd(const float* content, const float* style, const floa
                    int64_t n, int64_t c, int64_t hw, int64_t out_batch_stride, float eps,
                    float* saved_stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* f3  channel shuffle / sort-by-SE-weight folded into the loads     network/adain_rp.py:230-249,304-311
+ * Same as rpst_adain_fwd, but output plane p = i*c + ch reads its content from plane content_map[p]
+ * and its style from plane style_map[p] of the SAME tensors (global plane indices in [0, n*c); either
+ * map may be NULL = identity), so `shuffle(feats)` / `sort_by_weights(feats)` never materialise a
+ * permuted copy.  prev and out are indexed by the output plane. */
+RPST_API int rpst_adain_fwd_mapped(const float* content, const float* style, const float* prev, float* out,
+                          int64_t n, int64_t c, int64_t hw, int64_t out_batch_stride, float eps,
+                          const int32_t* content_map, const int32_t* style_map, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Backward of rpst_adain_fwd w.r.t. content and style (autograd gives this to the reference for
  * free; gradients reach the shared RP encoder through both arguments, SURVEY.md §7 hard part 7).
  *   grad_out [n,c,hw]; saved_stats from the forward; grad_content / grad_style [n,c,hw]
@@ -95,6 +105,23 @@ RPST_API int rpst_adain_bwd(const float* grad_out, const float* content, const f
  * ------------------------------------------------------------------------------------------ */
 RPST_API int rpst_plane_affine(const float* x, const float* scale, const float* shift, float* out,
                       int64_t planes, int64_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f1  calc_style_loss(input, target)            network/adain_rp.py:84-88, network/sanet.py:232-236
+ *     calc_content_loss(input, target, norm=True)                    network/sanet.py:226-230
+ * One streaming pass over the pair (x, y) (2*E*4 bytes) yields per-plane statistics and both losses:
+ *   losses[0] = mse(mean_x, mean_y) + mse(std_x, std_y)              (mean over the N*C planes)
+ *   losses[1] = mse(mean_variance_norm(x), mean_variance_norm(y))    (mean over N*C*H*W elements)
+ *   x, y   [planes, hw];  losses [2] (device);
+ *   stats  [planes, 8] or NULL: (mu_x, sd_x, mu_y, sd_y, M2_x, M2_y, C_xy, 0) — what the backward
+ *          pass needs (M2 = sum of squared deviations, C_xy = sum of cross deviations).
+ * rpst_plane_affine2 is that backward pass: out[p,:] = ax[p]*x[p,:] + ay[p]*y[p,:] + b[p] (b may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_pair_stats_workspace_bytes(int64_t planes, int64_t hw);
+RPST_API int rpst_pair_stats(const float* x, const float* y, int64_t planes, int64_t hw, float eps, float* stats,
+                    float* losses, void* workspace, size_t workspace_bytes, void* stream);
+RPST_API int rpst_plane_affine2(const float* x, const float* y, const float* ax, const float* ay, const float* b,
+                       float* out, int64_t planes, int64_t hw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a4  adaptive_instance_normalization_with_segment(content_feat, style_feat, c_seg, s_seg)

@@ -146,6 +146,22 @@ def gen_se(net):
               w1=m.fc[0].weight, w2=m.fc[2].weight)
 
 
+def gen_losses(net):
+    """calc_style_loss / calc_content_loss(norm) are methods that only touch `self.mse_loss`."""
+    import types
+    stub = types.SimpleNamespace(mse_loss=torch.nn.MSELoss())
+    adain_rp, sanet = sys.modules["network.adain_rp"], sys.modules["network.sanet"]
+    x, y = synth_features((2, 6, 9, 11), cfg=8)
+    g = torch.Generator().manual_seed(88)
+    near = x + 0.05 * torch.randn(x.shape, generator=g)      # stylized ~ content: small normalised loss
+    _save("losses", x=x, y=y, near=near,
+          style=adain_rp.AdaINRPNet.calc_style_loss(stub, x, y),
+          style_sanet=sanet.SAModel.calc_style_loss(stub, x, y),
+          content_norm=sanet.SAModel.calc_content_loss(stub, x, y, norm=True),
+          content_norm_near=sanet.SAModel.calc_content_loss(stub, near, x, norm=True),
+          content_plain=sanet.SAModel.calc_content_loss(stub, x, y))
+
+
 def main():
     net = load_reference()
     with torch.no_grad():
@@ -155,6 +171,7 @@ def main():
         gen_sanet(net)
         gen_mrf(net)
         gen_se(net)
+        gen_losses(net)
 
 
 if __name__ == "__main__":

@@ -4,9 +4,11 @@
 Everything here calls hand-written sm_100a kernels through the C ABI in include/rpst.h."""
 from . import _lib
 from ._lib import RpstError, get_tuning, set_tuning
-from .functional import (adain_blend, adain_concat, adaptive_instance_normalization, calc_mean_std,
-                         mean_variance_norm, plane_affine)
+from .functional import (adain_blend, adain_concat, adain_mapped, adaptive_instance_normalization, calc_mean_std,
+                         compose_maps, mean_variance_norm, plane_affine, shuffle_map, sort_map)
 
+from . import losses
+from .losses import calc_content_loss, calc_style_loss
 from .modules import SELayer
 from .mrf import MRFLoss, cal_affinity_map, cal_dist, mrf_match, packed_gemm
 from .wct import matrix_inv_sqrt, matrix_sqrt, wct_fuse, whiten_and_color

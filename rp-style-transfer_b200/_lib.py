@@ -30,9 +30,13 @@ SIGNATURES = {
     "rpst_stats_nchw": (c_int, [P, c_int64, c_int64, c_float, P, P, P, c_size_t, P]),
     "rpst_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_adain_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
+    "rpst_adain_fwd_mapped": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, c_size_t, P]),
     "rpst_adain_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_adain_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "rpst_plane_affine": (c_int, [P, P, P, P, c_int64, c_int64, P]),
+    "rpst_pair_stats_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rpst_pair_stats": (c_int, [P, P, c_int64, c_int64, c_float, P, P, P, c_size_t, P]),
+    "rpst_plane_affine2": (c_int, [P, P, P, P, P, P, c_int64, c_int64, P]),
     "rpst_seg_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "rpst_pairwise_sqdist_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_pairwise_sqdist": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, c_size_t, P]),

@@ -57,7 +57,15 @@ struct AdainParams {
     unsigned* ticket;    // starts at 0xFFFFFFFF
     float4* coef;        // [planes] (mu_c hi, a, mu_s, mu_c lo); 0xFF-filled = not merged yet
     float4* part;        // [planes*ipp] (mean_c, m2_c, mean_s, m2_s); 0xFF-filled = not written yet
+    // channel shuffle / sort folded into the loads (network/adain_rp.py:230-249,304-311): output plane p
+    // takes its content from plane cmap[p] and its style from plane smap[p] (null = identity)
+    const int* cmap;
+    const int* smap;
 };
+
+__device__ __forceinline__ int64_t src_plane(const int* map, int64_t plane) {
+    return map ? (int64_t)__ldg(map + plane) : plane;
+}
 
 // ------------------------------------------------------------------------------------------
 // direct kernel: one CTA per plane, content stays in registers
@@ -71,13 +79,13 @@ __global__ void __launch_bounds__(THREADS) adain_direct_kernel(AdainParams p) {
     const float hwf = (float)p.hw;
 
     for (int64_t plane = blockIdx.x; plane < p.planes; plane += gridDim.x) {
-        const float* cbase = p.content + plane * p.hw;
+        const float* cbase = p.content + src_plane(p.cmap, plane) * p.hw;
         float c[kBatches][kBatch][VEC];
         Moments mc = {0.f, 0.f, 0.f}, ms = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int b = 0; b < kBatches; ++b) load_batch<VEC, THREADS>(c[b], cbase, b, nvec, pol_first, hint);
         if (p.style != nullptr) {
-            const float* sbase = p.style + plane * p.hw;
+            const float* sbase = p.style + src_plane(p.smap, plane) * p.hw;
 #pragma unroll
             for (int b = 0; b < kBatches; ++b) {
                 float s[kBatch][VEC];
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(kPipeThreads, MINB) adain_pipe_kernel(AdainPar
         const int64_t e0 = (int64_t)it.chunk * kItemElems;
         const int64_t rem = p.hw - e0;
         const int nvec = (int)((rem < kItemElems ? rem : kItemElems) / VEC);
-        const float* cbase = p.content + it.plane * p.hw + e0;
+        const float* cbase = p.content + src_plane(p.cmap, it.plane) * p.hw + e0;
 
         if (it.kind == 0) {
             // ---------------- statistics item
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(kPipeThreads, MINB) adain_pipe_kernel(AdainPar
 #pragma unroll
             for (int b = 0; b < NB; ++b) load_batch<VEC, T>(c[b], cbase, b, nvec, cpol, hint);
             if (has_style) {
-                const float* sbase = p.style + it.plane * p.hw + e0;
+                const float* sbase = p.style + src_plane(p.smap, it.plane) * p.hw + e0;
 #pragma unroll
                 for (int b = 0; b < NB; ++b) load_batch<VEC, T>(s[b], sbase, b, nvec, pol_first, hint);
             }
@@ -466,7 +474,7 @@ struct __align__(16) StageDesc {
 };
 
 struct DecodedItem {
-    int64_t plane;
+    int64_t plane, cplane, splane;   // output plane, source planes of content / style
     int kind, chunk;
 };
 
@@ -544,6 +552,8 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                 const unsigned t = base + (unsigned)lane;
                 if (t < p.total_items) decode_tma(t, p, kind, plane, chunk);
                 dec[lane].kind = kind; dec[lane].chunk = chunk; dec[lane].plane = plane;
+                dec[lane].cplane = (kind == 0 || kind == 1) ? src_plane(p.cmap, plane) : plane;
+                dec[lane].splane = kind == 0 ? src_plane(p.smap, plane) : plane;
             }
             __syncwarp();
             bool finished = false;
@@ -573,12 +583,12 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                     d->plane = plane; d->kind = kind; d->chunk = chunk; d->nvec = nvec;
                     float* buf_a = bufs + (size_t)(stage * 2 + 0) * kItemElems;
                     float* buf_b = bufs + (size_t)(stage * 2 + 1) * kItemElems;
-                    const float* csrc = p.content + plane * p.hw + e0;
+                    const float* csrc = p.content + dec[i].cplane * p.hw + e0;
                     if (kind == 0) {
                         const bool has_style = p.style != nullptr;
                         mbar_arrive_expect_tx(&full[stage], has_style ? 2u * bytes : bytes);
                         tma_load_1d(buf_a, csrc, bytes, &full[stage], p.stats_only ? pol_first : pol_last);
-                        if (has_style) tma_load_1d(buf_b, p.style + plane * p.hw + e0, bytes, &full[stage], pol_first);
+                        if (has_style) tma_load_1d(buf_b, p.style + dec[i].splane * p.hw + e0, bytes, &full[stage], pol_first);
                     } else if (kind == 1) {
                         const bool has_prev = p.prev != nullptr;
                         mbar_arrive_expect_tx(&full[stage], (has_prev ? 2u * bytes : bytes) + 16u);
@@ -968,7 +978,6 @@ __global__ void __launch_bounds__(256) plane_affine_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct PipeLayout {
     size_t coef_off, part_off, total;  // ticket, coef, partial slots; everything is memset to 0xFF
@@ -1198,9 +1207,32 @@ extern "C" size_t rpst_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw) {
     return pipe_layout(n * c, hw).total;
 }
 
+namespace {
+int adain_fwd_impl(const float* content, const float* style, const float* prev, float* out, int64_t n, int64_t c,
+                   int64_t hw, int64_t out_batch_stride, float eps, const int* content_map, const int* style_map,
+                   float* saved_stats, void* workspace, size_t workspace_bytes, void* stream);
+}
+
 extern "C" int rpst_adain_fwd(const float* content, const float* style, const float* prev, float* out,
                               int64_t n, int64_t c, int64_t hw, int64_t out_batch_stride, float eps,
                               float* saved_stats, void* workspace, size_t workspace_bytes, void* stream) {
+    return adain_fwd_impl(content, style, prev, out, n, c, hw, out_batch_stride, eps, nullptr, nullptr, saved_stats,
+                          workspace, workspace_bytes, stream);
+}
+
+extern "C" int rpst_adain_fwd_mapped(const float* content, const float* style, const float* prev, float* out,
+                                     int64_t n, int64_t c, int64_t hw, int64_t out_batch_stride, float eps,
+                                     const int32_t* content_map, const int32_t* style_map, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(n * c < (1ll << 31), "adain_mapped: plane index does not fit int32");
+    return adain_fwd_impl(content, style, prev, out, n, c, hw, out_batch_stride, eps, content_map, style_map, nullptr,
+                          workspace, workspace_bytes, stream);
+}
+
+namespace {
+int adain_fwd_impl(const float* content, const float* style, const float* prev, float* out, int64_t n, int64_t c,
+                   int64_t hw, int64_t out_batch_stride, float eps, const int* content_map, const int* style_map,
+                   float* saved_stats, void* workspace, size_t workspace_bytes, void* stream) {
     RPST_CHECK_ARG(n >= 0 && c >= 0 && hw >= 0, "adain: negative size");
     if (n == 0 || c == 0 || hw == 0) return RPST_OK;
     RPST_CHECK_ARG(content != nullptr && out != nullptr, "adain: null content/out");
@@ -1218,8 +1250,11 @@ extern "C" int rpst_adain_fwd(const float* content, const float* style, const fl
     p.channels = c;
     p.out_batch_stride = out_batch_stride;
     p.eps = eps;
+    p.cmap = content_map;
+    p.smap = style_map;
     return run_adain(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+}  // namespace
 
 extern "C" size_t rpst_adain_bwd_workspace_bytes(int64_t n, int64_t c, int64_t hw) {
     if (n <= 0 || c <= 0 || hw <= 0) return 256;

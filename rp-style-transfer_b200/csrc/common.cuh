@@ -31,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------- device: memory ops
 #ifdef __CUDACC__

@@ -8,6 +8,7 @@ Reference interfaces mirrored (paths relative to the reference root):
 plus the fused forms the reference spells as two ops:
   adain_blend(prev, c, s)              network/adain_rp.py:300-301  (`stylized + AdaIN(c, s)`)
   adain_concat(prev, c, s)             network/adain_rp.py:793      (`cat([stylized, AdaIN(c, s)], 1)`)
+  adain_mapped(c, s, cmap, smap, prev) network/adain_rp.py:230-249,304-311 (channel shuffle / sort folded into the loads)
 """
 from __future__ import annotations
 
@@ -203,6 +204,65 @@ def adain_concat(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: tor
     out = torch.empty((n, cp + cc) + tuple(c.shape[2:]), dtype=c.dtype, device=c.device)
     out[:, :cp].copy_(prev)
     _adain_raw(c, s, None, out[:, cp:], (cp + cc) * hw, EPS, False)
+    return out
+
+
+def shuffle_map(n: int, c: int, groups: int = 4, device=None) -> torch.Tensor:
+    """Plane map of `MultiScaleAdaINRPNet.shuffle` (network/adain_rp.py:304-311):
+    `feats.view(N, g, C//g, H, W).permute(0, 2, 1, 3, 4)` => output channel j reads channel
+    (j % g) * (C//g) + j // g.  Returns int32 [N*C] global plane indices."""
+    j = torch.arange(c, device=device)
+    src = (j % groups) * (c // groups) + j // groups
+    return (src[None, :] + torch.arange(n, device=device)[:, None] * c).reshape(-1).to(torch.int32)
+
+
+def sort_map(attention: torch.Tensor) -> torch.Tensor:
+    """Plane map of `sort_by_weights` (network/adain_rp.py:230-249): per sample, channels in descending
+    order of the SE attention weight [N,C,1,1].  Returns int32 [N*C] global plane indices."""
+    n, c = attention.shape[:2]
+    _, indexes = attention.sort(dim=1, descending=True)
+    indexes = indexes.view(n, c)
+    return (indexes + torch.arange(n, device=attention.device)[:, None] * c).reshape(-1).to(torch.int32)
+
+
+def compose_maps(first: Optional[torch.Tensor], then: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Map of `then(first(x))`: output plane p reads first[then[p]]."""
+    if first is None:
+        return then
+    if then is None:
+        return first
+    return first[then.long()].contiguous()
+
+
+def adain_mapped(content_feat: torch.Tensor, style_feat: torch.Tensor, content_map: Optional[torch.Tensor] = None,
+                 style_map: Optional[torch.Tensor] = None, prev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`[prev +] AdaIN(content_feat.flatten(0,1)[content_map], style_feat.flatten(0,1)[style_map])` without
+    materialising the permuted tensors.  Maps are int32 [N*C] plane indices."""
+    assert (content_feat.size() == style_feat.size())
+    assert content_feat.dim() == 4
+    c, s = _prep(content_feat, "content_feat"), _prep(style_feat, "style_feat")
+    p = None if prev is None else _prep(prev, "prev")
+    n, ch = c.shape[:2]
+    hw = c[0, 0].numel() if c.numel() else 0
+
+    def chk(m, name):
+        if m is None:
+            return None
+        if not m.is_cuda or m.dtype != torch.int32 or m.numel() != n * ch:
+            raise TypeError(f"rpst: `{name}` must be a CUDA int32 tensor with N*C = {n * ch} entries")
+        return m.contiguous()
+
+    cm, sm = chk(content_map, "content_map"), chk(style_map, "style_map")
+    if _needs_grad(c, s, p):
+        # training: gather through autograd, then the differentiable kernel path
+        cg = c if cm is None else c.flatten(0, 1)[cm.long()].view_as(c)
+        sg = s if sm is None else s.flatten(0, 1)[sm.long()].view_as(s)
+        return _AdaINFn.apply(cg.contiguous(), sg.contiguous(), p)
+    out = torch.empty_like(c)
+    L = _lib.lib()
+    ws = _plane_workspace(L.rpst_adain_workspace_bytes, (n, ch, hw), hw, c.device)
+    _lib.check(L.rpst_adain_fwd_mapped(c.data_ptr(), s.data_ptr(), _ptr(p), out.data_ptr(), n, ch, hw, ch * hw, EPS,
+                                       _ptr(cm), _ptr(sm), ws.data_ptr(), ws.numel(), _stream()))
     return out
 
 

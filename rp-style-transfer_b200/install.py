@@ -11,12 +11,13 @@ import sys
 from typing import Dict, List, Tuple
 
 from . import functional as F
+from . import losses as LOSS
 from . import modules as M
 from . import mrf as MRF
 from . import sanet as SA
 from . import segment as SEG
 from . import wct as WCT
-from .decode import PATCHED_DECODES
+from .decode import PATCHED_DECODES, PATCHED_TESTS
 
 # reference name -> replacement (applied wherever the name exists in a network.* namespace)
 NAME_MAP = {
@@ -79,6 +80,17 @@ def install(package: str = "network") -> Dict[str, int]:
             if cname in PATCHED_DECODES and "decode" in vars(cls):
                 _patch(cls, "decode", PATCHED_DECODES[cname])
                 counts[cname + ".decode"] = 1
+            if cname in PATCHED_TESTS and "test" in vars(cls):
+                _patch(cls, "test", PATCHED_TESTS[cname])
+                counts[cname + ".test"] = 1
+            # loss statistics: methods that only use self.mse_loss
+            if "calc_style_loss" in vars(cls):
+                _patch(cls, "calc_style_loss", lambda self, input, target: LOSS.calc_style_loss(input, target))
+                counts["calc_style_loss"] = counts.get("calc_style_loss", 0) + 1
+            if "calc_content_loss" in vars(cls):
+                _patch(cls, "calc_content_loss",
+                       lambda self, input, target, norm=False: LOSS.calc_content_loss(input, target, norm))
+                counts["calc_content_loss"] = counts.get("calc_content_loss", 0) + 1
             if "do_mask_stylized" in vars(cls):
                 _patch(cls, "do_mask_stylized", lambda self, cf, sf, cm, sm: SEG.do_mask_stylized(cf, sf, cm, sm))
                 counts["do_mask_stylized"] = counts.get("do_mask_stylized", 0) + 1

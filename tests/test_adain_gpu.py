@@ -181,3 +181,49 @@ def test_tuning_variants_agree(rpst):
     finally:
         for k, v in old.items():
             rpst.set_tuning(k, v)
+
+
+# channel shuffle / sort folded into the loads: direct, scalar-pipelined and TMA paths
+@pytest.mark.parametrize("shape", [(2, 8, 16, 16), (2, 8, 150, 151), (2, 16, 256, 256), (1, 8, 512, 512)])
+@pytest.mark.parametrize("blend", [False, True])
+def test_mapped_matches_materialised_permutation(rpst, shape, blend):
+    n, ch = shape[:2]
+    c, s = R.synth_features(shape, cfg=50)
+    prev = torch.randn(shape, generator=torch.Generator().manual_seed(9)) if blend else None
+    g = torch.Generator().manual_seed(51)
+    att_c, att_s = torch.rand(n, ch, 1, 1, generator=g), torch.rand(n, ch, 1, 1, generator=g)
+    shuf = rpst.shuffle_map(n, ch, 4, "cuda")
+    cm = rpst.compose_maps(shuf, rpst.sort_map(att_c.cuda()))
+    sm = rpst.sort_map(att_s.cuda())
+    # reference spelling: shuffle (network/adain_rp.py:304-311), then sort_by_weights (:230-249), then AdaIN
+    def shuffle(f):
+        N, C, H, W = f.size()
+        return f.view(N, 4, C // 4, H, W).permute(0, 2, 1, 3, 4).contiguous().view(N, C, H, W)
+    def sort(f, att):
+        _, idx = att.sort(dim=1, descending=True)
+        return torch.cat([torch.index_select(f[b].unsqueeze(0), 1, idx[b].view(-1)) for b in range(f.shape[0])], 0)
+    want = R.adain(sort(shuffle(c), att_c), sort(s, att_s), dtype=torch.float64)
+    if blend:
+        want = want + prev.double()
+    got = rpst.adain_mapped(c.cuda(), s.cuda(), cm, sm, prev=None if prev is None else prev.cuda())
+    assert R.rel_l2(got, want) < TIGHT
+    # identity maps reproduce the unmapped call bit for bit
+    ident = torch.arange(n * ch, dtype=torch.int32, device="cuda")
+    a = rpst.adain_mapped(c.cuda(), s.cuda(), ident, ident)
+    b = rpst.adaptive_instance_normalization(c.cuda(), s.cuda())
+    assert torch.equal(a, b)
+
+
+def test_mapped_autograd_matches_gather(rpst):
+    c, s = R.synth_features((2, 8, 20, 20), cfg=52, signed=True)
+    m = rpst.shuffle_map(2, 8, 4, "cuda")
+    cg, sg = c.cuda().requires_grad_(), s.cuda().requires_grad_()
+    out = rpst.adain_mapped(cg, sg, m, m)
+    out.square().sum().backward()
+    cd, sd = c.double().requires_grad_(), s.double().requires_grad_()
+    ml = m.long().cpu()
+    cp, sp = cd.flatten(0, 1)[ml].view_as(cd), sd.flatten(0, 1)[ml].view_as(sd)
+    mu_c, sd_c = cp.mean((2, 3), keepdim=True), (cp.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    mu_s, sd_s = sp.mean((2, 3), keepdim=True), (sp.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    ((cp - mu_c) / sd_c * sd_s + mu_s).square().sum().backward()
+    assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4

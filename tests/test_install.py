@@ -35,6 +35,11 @@ def test_install_rebinds_every_namespace_and_restores():
         assert adain_rp.MultiScaleAdaINRPNet.decode is not orig_decode
         assert adain_rp.LDMSAdaINRPNet2.decode is adain_rp.LDMSAdaINRPNet.decode     # inherited patch
         assert net.SELayer is rpst.SELayer or sys.modules["network.attention"].SELayer is rpst.SELayer
+        # loss-statistics methods on every class that defines them
+        assert counts["calc_style_loss"] >= 3 and counts["calc_content_loss"] >= 3
+        assert adain_rp.AdaINRPNet.calc_style_loss is not None
+        import inspect
+        assert "norm" in inspect.signature(sanet.SAModel.calc_content_loss).parameters
         assert rpst.install() == {}                                                # idempotent
     finally:
         rpst.uninstall()

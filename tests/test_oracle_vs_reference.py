@@ -15,7 +15,7 @@ pytestmark = [pytest.mark.reference,
 @pytest.fixture(scope="module")
 def ref():
     load_reference()
-    return {n: sys.modules[f"network.{n}"] for n in ("base", "wct_rp", "sanet", "mrf_rp", "attention")}
+    return {n: sys.modules[f"network.{n}"] for n in ("base", "wct_rp", "sanet", "mrf_rp", "attention", "adain_rp")}
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 5, 7), (2, 8, 16, 12), (1, 4, 33, 31)])
@@ -67,3 +67,13 @@ def test_sanet_random(ref):
     with torch.no_grad():
         want = m(c, s)
     assert R.rel_l2(R.sanet_forward(c, s, dict(m.state_dict())), want) <= 1e-5
+
+
+def test_losses_random(ref):
+    import types
+    stub = types.SimpleNamespace(mse_loss=torch.nn.MSELoss())
+    x, y = R.synth_features((2, 5, 17, 13), cfg=33)
+    sanet, adain_rp = ref["sanet"], ref["adain_rp"]
+    assert R.rel_l2(R.style_loss(x, y), adain_rp.AdaINRPNet.calc_style_loss(stub, x, y)) <= 1e-6
+    assert R.rel_l2(R.content_loss(x, y, norm=True), sanet.SAModel.calc_content_loss(stub, x, y, norm=True)) <= 1e-6
+    assert R.rel_l2(R.content_loss(x, y), adain_rp.AdaINRPNet.calc_content_loss(stub, x, y)) <= 1e-6
