@@ -122,6 +122,10 @@ RPST_API int rpst_pair_stats(const float* x, const float* y, int64_t planes, int
                     float* losses, void* workspace, size_t workspace_bytes, void* stream);
 RPST_API int rpst_plane_affine2(const float* x, const float* y, const float* ax, const float* ay, const float* b,
                        float* out, int64_t planes, int64_t hw, void* stream);
+/* Gradient of losses[which] (0 style, 1 normalised content) w.r.t. x (wrt_second = 0) or y (1), scaled by
+ * the upstream gradient *grad (device scalar); per-plane coefficients come from `stats` inside the kernel. */
+RPST_API int rpst_pair_loss_bwd(const float* x, const float* y, const float* stats, const float* grad, int which,
+                       int wrt_second, float* out, int64_t planes, int64_t hw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a4  adaptive_instance_normalization_with_segment(content_feat, style_feat, c_seg, s_seg)
@@ -213,6 +217,14 @@ RPST_API size_t rpst_sanet_attn_workspace_bytes(int64_t c, int64_t lc, int64_t l
 RPST_API int rpst_sanet_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t c,
                         int64_t lc, int64_t ls, int passes, float* attn_out, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* f2  backward of rpst_sanet_attn_fwd (autograd gives it to the reference for free; needed to train
+ *     SAModel, network/sanet.py:253-276).  grad_out [b,c,lc] -> grad_f [b,c,lc], grad_g / grad_h [b,c,ls].
+ *     The attention matrix is recomputed, not saved. */
+RPST_API size_t rpst_sanet_attn_bwd_workspace_bytes(int64_t c, int64_t lc, int64_t ls);
+RPST_API int rpst_sanet_attn_bwd(const float* f, const float* g, const float* h, const float* grad_out,
+                        float* grad_f, float* grad_g, float* grad_h, int64_t b, int64_t c, int64_t lc,
+                        int64_t ls, int passes, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a11 cal_affinity_matrix(content_feat, style_feat)                   network/sanet.py:12-18

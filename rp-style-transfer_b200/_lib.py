@@ -37,6 +37,7 @@ SIGNATURES = {
     "rpst_pair_stats_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "rpst_pair_stats": (c_int, [P, P, c_int64, c_int64, c_float, P, P, P, c_size_t, P]),
     "rpst_plane_affine2": (c_int, [P, P, P, P, P, P, c_int64, c_int64, P]),
+    "rpst_pair_loss_bwd": (c_int, [P, P, P, P, c_int, c_int, P, c_int64, c_int64, P]),
     "rpst_seg_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "rpst_pairwise_sqdist_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_pairwise_sqdist": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, c_size_t, P]),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "rpst_wct_fuse": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_size_t, P]),
     "rpst_sanet_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_sanet_attn_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, P, c_size_t, P]),
+    "rpst_sanet_attn_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_sanet_attn_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
     "rpst_cosine_affinity_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_cosine_affinity": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "rpst_sanet_adaptive_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),

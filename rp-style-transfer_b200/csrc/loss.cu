@@ -276,6 +276,65 @@ __global__ void __launch_bounds__(256) plane_affine2_kernel(const float* __restr
     }
 }
 
+// Backward of the two losses w.r.t. one tensor of the pair, coefficients derived per plane from the
+// saved statistics (no host-side tensor algebra):  out = ax*u + ay*v + b, u = the tensor being
+// differentiated, v = the other one, g = upstream gradient (device scalar), P planes, n = HW.
+//   style  : d/du_i = 2g/P [ (mu_u-mu_v)/n + (sd_u-sd_v)(u_i-mu_u)/((n-1) sd_u) ]            (ay = 0, v not read)
+//   content: d/du_i = 2g/(P n sd_u) [ u^_i - v^_i - u^_i K ],  K = (M2_u/sd_u^2 - C/(sd_u sd_v))/(n-1)
+template <int VEC>
+__global__ void __launch_bounds__(256) pair_loss_bwd_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                                            const float* __restrict__ stats, const float* __restrict__ grad,
+                                                            int which, int wrt_second, float* __restrict__ out,
+                                                            int64_t planes, int64_t hw, int cpp) {
+    constexpr int CHUNK = 256 * kPerThread * VEC;
+    const uint64_t pol = policy_evict_first();
+    const int64_t items = planes * cpp;
+    const float g = __ldg(grad);
+    const float n = (float)hw, P = (float)planes;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t plane = item / cpp;
+        const int64_t e0 = (item % cpp) * (int64_t)CHUNK;
+        const int64_t rem = hw - e0;
+        const int nvec = (int)((rem < CHUNK ? rem : CHUNK) / VEC);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(stats + plane * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(stats + plane * 8) + 1);
+        // (mu, sd, M2) of u and of v
+        const float mu_u = wrt_second ? s0.z : s0.x, sd_u = wrt_second ? s0.w : s0.y, m2_u = wrt_second ? s1.y : s1.x;
+        const float mu_v = wrt_second ? s0.x : s0.z, sd_v = wrt_second ? s0.y : s0.w;
+        float ax, ay, b;
+        if (which == 0) {
+            ax = 2.f * g * (sd_u - sd_v) / (P * (n - 1.f) * sd_u);
+            ay = 0.f;
+            b = 2.f * g * (mu_u - mu_v) / (P * n) - ax * mu_u;
+        } else {
+            const float sc = 2.f * g / (P * n);
+            const float k = (m2_u / (sd_u * sd_u) - s1.z / (sd_u * sd_v)) / (n - 1.f);
+            ax = sc * (1.f - k) / (sd_u * sd_u);
+            ay = -sc / (sd_u * sd_v);
+            b = -ax * mu_u - ay * mu_v;
+        }
+        const float* ub = u + plane * hw + e0;
+        const float* vb = v + plane * hw + e0;
+        float* ob = out + plane * hw + e0;
+#pragma unroll
+        for (int bt = 0; bt < kBatches; ++bt) {
+            float uv[kBatch][VEC], vv[kBatch][VEC];
+            load_batch<VEC, 256>(uv, ub, bt, nvec, pol, true);
+            if (which != 0) load_batch<VEC, 256>(vv, vb, bt, nvec, pol, true);
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const int idx = (bt * kBatch + j) * 256 + threadIdx.x;
+                if (idx < nvec) {
+                    float o[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) o[e] = which != 0 ? fmaf(ax, uv[j][e], fmaf(ay, vv[j][e], b)) : fmaf(ax, uv[j][e], b);
+                    store_vec<VEC>(ob + (int64_t)idx * VEC, o, pol, true);
+                }
+            }
+        }
+    }
+}
+
 struct PairLayout {
     size_t part_off, block_off, total;
     int cpp;
@@ -324,7 +383,15 @@ extern "C" int rpst_pair_stats(const float* x, const float* y, int64_t planes, i
     p.ticket = reinterpret_cast<unsigned*>(base);
     RPST_CHECK_ARG(l.fin_blocks < (1ll << 31), "pair_stats: too many planes");
     RPST_CUDA(cudaMemsetAsync(base, 0, 256, st));
-    int64_t grid = (int64_t)sm_count() * 4;   // 4 x 64 KiB of loads in flight per SM
+    // persistent grid = exactly the co-resident CTAs (64 KiB of loads in flight each)
+    static int per_sm[2] = {0, 0};
+    if (per_sm[vec] == 0) {
+        int nb = 0;
+        if (vec) RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<4>, kLossThreads, 0));
+        else RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<1>, kLossThreads, 0));
+        per_sm[vec] = nb > 0 ? nb : 1;
+    }
+    int64_t grid = (int64_t)sm_count() * per_sm[vec];
     if (grid > p.items) grid = p.items;
     if (vec) pair_moments_kernel<4><<<(int)grid, kLossThreads, 0, st>>>(p);
     else pair_moments_kernel<1><<<(int)grid, kLossThreads, 0, st>>>(p);
@@ -348,6 +415,28 @@ extern "C" int rpst_plane_affine2(const float* x, const float* y, const float* a
     if (grid > items) grid = items;
     if (vec) plane_affine2_kernel<4><<<(int)grid, 256, 0, st>>>(x, y, ax, ay, b, out, planes, hw, cpp);
     else plane_affine2_kernel<1><<<(int)grid, 256, 0, st>>>(x, y, ax, ay, b, out, planes, hw, cpp);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
+extern "C" int rpst_pair_loss_bwd(const float* x, const float* y, const float* stats, const float* grad, int which,
+                                  int wrt_second, float* out, int64_t planes, int64_t hw, void* stream) {
+    RPST_CHECK_ARG(planes >= 0 && hw >= 0, "pair_loss_bwd: negative size");
+    if (planes == 0 || hw == 0) return RPST_OK;
+    RPST_CHECK_ARG(x && y && stats && grad && out, "pair_loss_bwd: null pointer");
+    RPST_CHECK_ARG(which == 0 || which == 1, "pair_loss_bwd: which must be 0 (style) or 1 (normalised content)");
+    RPST_CHECK_ARG(aligned16(stats), "pair_loss_bwd: stats must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* u = wrt_second ? y : x;
+    const float* v = wrt_second ? x : y;
+    const bool vec = hw % 4 == 0 && aligned16(u) && aligned16(v) && aligned16(out);
+    const int64_t chunk = 256ll * kPerThread * (vec ? 4 : 1);
+    const int cpp = (int)((hw + chunk - 1) / chunk);
+    int64_t items = planes * cpp;
+    int64_t grid = (int64_t)sm_count() * 8;
+    if (grid > items) grid = items;
+    if (vec) pair_loss_bwd_kernel<4><<<(int)grid, 256, 0, st>>>(u, v, stats, grad, which, wrt_second ? 1 : 0, out, planes, hw, cpp);
+    else pair_loss_bwd_kernel<1><<<(int)grid, 256, 0, st>>>(u, v, stats, grad, which, wrt_second ? 1 : 0, out, planes, hw, cpp);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }

@@ -152,6 +152,59 @@ AttnLayout attn_layout(int64_t c, int64_t lc, int64_t ls) {
     return l;
 }
 
+// Backward of the row softmax: dS = P o (dP - sum_j dP o P).  One CTA per row; P and dP rows are read
+// twice (second time from L1/L2); dS overwrites dP in fp32 and is emitted as packed operand tiles.
+__global__ void __launch_bounds__(kRowThreads) attn_bwd_rows_kernel(const float* __restrict__ prob, float* dp,
+                                                                     __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                                                     int64_t cols, int k_tiles) {
+    __shared__ float red[kRowThreads / 32];
+    const int64_t row = blockIdx.x;
+    const float* pr = prob + row * cols;
+    float* dr = dp + row * cols;
+    float acc = 0.f;
+    for (int64_t j = threadIdx.x; j < cols; j += kRowThreads) acc = fmaf(pr[j], dr[j], acc);
+    const float delta = block_sum(acc, red);
+    const int64_t chunks = (cols + 7) / 8;
+    const int64_t rb = row / kTileRows;
+    const int r = (int)(row % kTileRows);
+    for (int64_t q = threadIdx.x; q < chunks; q += kRowThreads) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t j = q * 8 + e;
+            y[e] = j < cols ? pr[j] * (dr[j] - delta) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (q * 8 + e < cols) dr[q * 8 + e] = y[e];
+        __align__(16) __nv_bfloat16 h[8];
+        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(y[e], h[e], l[e]);
+        const int64_t tile = rb * k_tiles + (q >> 3);
+        const size_t off = (size_t)tile * kTileBytes + tile_chunk_offset(r, (int)(q & 7));
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(hi) + off) = *reinterpret_cast<const uint4*>(h);
+        if (lo) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(lo) + off) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
+// workspace of the backward pass: the forward's buffers (Q/K/V tiles, S) plus dP and two L x L tile sets
+struct AttnBwdLayout {
+    AttnLayout a;            // q: [lc x c] tiles, k: [ls x c], v: [c x ls], s: P (fp32), p: [lc x ls] tiles (dS)
+    size_t dp, t_hi, t_lo, w_hi, w_lo, total;   // dP/dS fp32; [ls x lc] tiles (P^T, dS^T); [c x lc] tiles (dO, F)
+};
+AttnBwdLayout attn_bwd_layout(int64_t c, int64_t lc, int64_t ls) {
+    AttnBwdLayout l;
+    l.a = attn_layout(c, lc, ls);
+    size_t o = l.a.total;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    l.dp = take((size_t)lc * ls * sizeof(float));
+    l.t_hi = take(packed_operand_bytes(ls, lc)); l.t_lo = take(packed_operand_bytes(ls, lc));
+    l.w_hi = take(packed_operand_bytes(c, lc)); l.w_lo = take(packed_operand_bytes(c, lc));
+    l.total = o;
+    return l;
+}
+
 struct AdaLayout {
     AttnLayout a;
     size_t aff, w_hi, w_lo, hidden, clamp, vec[6], total;
@@ -240,6 +293,77 @@ extern "C" int rpst_sanet_attn_fwd(const float* f, const float* g, const float* 
         if (rc) return rc;
         rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l, out + i * c * lc, st);
         if (rc) return rc;
+    }
+    return RPST_OK;
+}
+
+extern "C" size_t rpst_sanet_attn_bwd_workspace_bytes(int64_t c, int64_t lc, int64_t ls) {
+    if (c <= 0 || lc <= 0 || ls <= 0) return 256;
+    return attn_bwd_layout(c, lc, ls).total;
+}
+
+// Backward of rpst_sanet_attn_fwd.  With S = F^T G, P = softmax_j(S), O = H P^T:
+//   dH = dO P          [C,Ls]      dP = dO^T H   [Lc,Ls]      dS = P o (dP - rowsum(dP o P))
+//   dF = G dS^T        [C,Lc]      dG = F dS     [C,Ls]
+// P is recomputed (one extra GEMM) instead of being kept from the forward: at L = 16384 it is 1 GiB per
+// sample.  Five tcgen05 GEMMs + two row kernels per sample, all on the caller's stream.
+extern "C" int rpst_sanet_attn_bwd(const float* f, const float* g, const float* h, const float* grad_out,
+                                   float* grad_f, float* grad_g, float* grad_h, int64_t b, int64_t c, int64_t lc,
+                                   int64_t ls, int passes, void* workspace, size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(b >= 0 && c >= 0 && lc >= 0 && ls >= 0, "sanet_bwd: negative size");
+    if (b == 0 || c == 0 || lc == 0) return RPST_OK;
+    RPST_CHECK_ARG(ls > 0, "sanet_bwd: empty style map");
+    RPST_CHECK_ARG(f && g && h && grad_out && grad_f && grad_g && grad_h, "sanet_bwd: null pointer");
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet_bwd: passes must be 1 (bf16) or 3 (bf16x3, fp32-grade)");
+    const AttnBwdLayout l = attn_bwd_layout(c, lc, ls);
+    if (!workspace || workspace_bytes < l.total) {
+        set_error("sanet_bwd: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet_bwd: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    const bool x3 = passes == 3;
+    float* prob = reinterpret_cast<float*>(w + l.a.s);
+    float* dp = reinterpret_cast<float*>(w + l.dp);
+    auto lo = [&](size_t off) -> void* { return x3 ? w + off : nullptr; };
+    int rc;
+    for (int64_t i = 0; i < b; ++i) {
+        const float* fi = f + i * c * lc;
+        const float* gi = g + i * c * ls;
+        const float* hi_ = h + i * c * ls;
+        const float* doi = grad_out + i * c * lc;
+        // 1. P = softmax(F^T G), kept in fp32
+        if ((rc = scores(fi, gi, c, lc, ls, passes, w, l.a, prob, st))) return rc;
+        if ((rc = launch_rows(prob, prob, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;
+        // 2. dH[c,j] = sum_i dO[c,i] P[i,j]:  A = dO (rows c, K = i), B = P^T (rows j, K = i)
+        if ((rc = pack_operand_shift(doi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), st))) return rc;
+        if ((rc = pack_operand_shift(prob, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_h + i * c * ls, c, ls, lc, ls,
+                                     passes, 1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        // 3. dP[i,j] = sum_c dO[c,i] H[c,j]:  A = dO^T (rows i, K = c), B = H^T (rows j, K = c)
+        if ((rc = pack_operand_shift(doi, lc, c, 1, lc, nullptr, nullptr, w + l.a.q_hi, lo(l.a.q_lo), st))) return rc;
+        if ((rc = pack_operand_shift(hi_, ls, c, 1, ls, nullptr, nullptr, w + l.a.k_hi, lo(l.a.k_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.a.q_hi, w + l.a.q_lo, w + l.a.k_hi, w + l.a.k_lo, dp, lc, ls, c, ls, passes, 1.f,
+                                     nullptr, nullptr, 1, 0, st))) return rc;
+        // 4. dS = P o (dP - rowsum(dP o P)): fp32 in place of dP + operand tiles (rows i, K = j)
+        if (lc % kTileRows != 0 || ls % kTileK != 0) {
+            RPST_CUDA(cudaMemsetAsync(w + l.a.p_hi, 0, packed_operand_bytes(lc, ls), st));
+            if (x3) RPST_CUDA(cudaMemsetAsync(w + l.a.p_lo, 0, packed_operand_bytes(lc, ls), st));
+        }
+        attn_bwd_rows_kernel<<<(unsigned)lc, kRowThreads, 0, st>>>(prob, dp, reinterpret_cast<__nv_bfloat16*>(w + l.a.p_hi),
+                                                                   x3 ? reinterpret_cast<__nv_bfloat16*>(w + l.a.p_lo) : nullptr,
+                                                                   ls, (int)((ls + kTileK - 1) / kTileK));
+        RPST_CUDA(cudaGetLastError());
+        // 5. dF[c,i] = sum_j G[c,j] dS[i,j]:  A = G (rows c, K = j), B = dS (rows i, K = j)
+        if ((rc = pack_operand_shift(gi, c, ls, ls, 1, nullptr, nullptr, w + l.a.v_hi, lo(l.a.v_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.a.v_hi, w + l.a.v_lo, w + l.a.p_hi, w + l.a.p_lo, grad_f + i * c * lc, c, lc, ls, lc,
+                                     passes, 1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        // 6. dG[c,j] = sum_i F[c,i] dS[i,j]:  A = F (rows c, K = i), B = dS^T (rows j, K = i)
+        if ((rc = pack_operand_shift(fi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), st))) return rc;
+        if ((rc = pack_operand_shift(dp, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_g + i * c * ls, c, ls, lc, ls,
+                                     passes, 1.f, nullptr, nullptr, 1, 0, st))) return rc;
     }
     return RPST_OK;
 }

@@ -29,20 +29,6 @@ def _pair_stats_raw(x: torch.Tensor, y: torch.Tensor, eps: float, want_stats: bo
     return losses, stats
 
 
-def _affine(x, scale, shift):
-    out = torch.empty_like(x)
-    _lib.check(_lib.lib().rpst_plane_affine(x.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
-                                            x.shape[0] * x.shape[1], x[0, 0].numel(), _stream()))
-    return out
-
-
-def _affine2(x, y, ax, ay, b):
-    out = torch.empty_like(x)
-    _lib.check(_lib.lib().rpst_plane_affine2(x.data_ptr(), y.data_ptr(), ax.data_ptr(), ay.data_ptr(), b.data_ptr(),
-                                             out.data_ptr(), x.shape[0] * x.shape[1], x[0, 0].numel(), _stream()))
-    return out
-
-
 class _PairLossFn(torch.autograd.Function):
     """which = 0: style loss, 1: normalised content loss.  Returns a 0-dim tensor."""
 
@@ -59,35 +45,16 @@ class _PairLossFn(torch.autograd.Function):
     def backward(ctx, g):
         x, y, st = ctx.saved_tensors
         planes, hw = st.shape[0], x[0, 0].numel()
-        mx, sx, my, sy, m2x, m2y, cxy = (st[:, i] for i in range(7))
-        g = g.to(torch.float32)
-        gx = gy = None
-        if ctx.which == 0:
-            # d/dx_i [ (mx-my)^2 + (sx-sy)^2 ] / P  with  d mx/dx_i = 1/HW,  d sx/dx_i = (x_i-mx)/((HW-1) sx)
-            dm = 2.0 * g * (mx - my) / (planes * hw)
-            dsd = 2.0 * g * (sx - sy) / (planes * (hw - 1))
-            if ctx.needs_input_grad[0]:
-                scale = (dsd / sx).contiguous()
-                gx = _affine(x, scale, (dm - scale * mx).contiguous())
-            if ctx.needs_input_grad[1]:
-                scale = (-dsd / sy).contiguous()
-                gy = _affine(y, scale, (-dm - scale * my).contiguous())
-        else:
-            # L = sum (x^ - y^)^2 / (P HW);  dL/dx_i = s/sd_x (x^_i - y^_i - x^_i K_x),
-            # K_x = (M2_x/sd_x^2 - C_xy/(sd_x sd_y)) / (HW-1)   (sum of x^ and of y^ are both zero)
-            s = 2.0 * g / (planes * hw)
-            cross = cxy / (sx * sy)
-            if ctx.needs_input_grad[0]:
-                kx = (m2x / (sx * sx) - cross) / (hw - 1)
-                ax = s * (1.0 - kx) / (sx * sx)
-                ay = -s / (sx * sy)
-                gx = _affine2(x, y, ax.contiguous(), ay.contiguous(), (-ax * mx - ay * my).contiguous())
-            if ctx.needs_input_grad[1]:
-                ky = (m2y / (sy * sy) - cross) / (hw - 1)
-                ay = s * (1.0 - ky) / (sy * sy)
-                ax = -s / (sx * sy)
-                gy = _affine2(y, x, ay.contiguous(), ax.contiguous(), (-ay * my - ax * mx).contiguous())
-        return gx, gy, None
+        g = g.to(torch.float32).reshape(1).contiguous()
+        L = _lib.lib()
+        grads = [None, None]
+        for wrt, t in enumerate((x, y)):
+            if ctx.needs_input_grad[wrt]:
+                out = torch.empty_like(t)
+                _lib.check(L.rpst_pair_loss_bwd(x.data_ptr(), y.data_ptr(), st.data_ptr(), g.data_ptr(), ctx.which, wrt,
+                                                out.data_ptr(), planes, hw, _stream()))
+                grads[wrt] = out
+        return grads[0], grads[1], None
 
 
 def _pair(input: torch.Tensor, target: torch.Tensor, which: int) -> torch.Tensor:

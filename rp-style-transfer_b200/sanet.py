@@ -21,8 +21,8 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 def _no_grad_guard(*tensors):
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
         raise NotImplementedError(
-            "rpst: the attention core is forward-only in this round (attention backward is SURVEY.md §8f rank 2); "
-            "call it under torch.no_grad() (as `SAModel.test` does) or detach the inputs")
+            "rpst: the ADAPTIVE attention (AEA clamps) is forward-only; the static SANet core is differentiable "
+            "(rpst_sanet_attn_bwd).  Call this under torch.no_grad() (as `AdaptiveSAModel.test` does) or detach the inputs")
 
 
 def cal_affinity_matrix(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
@@ -38,20 +38,57 @@ def cal_affinity_matrix(content_feat: torch.Tensor, style_feat: torch.Tensor) ->
     return out
 
 
-def attention_core(F: torch.Tensor, G: torch.Tensor, H: torch.Tensor, precision: str = "fp32", return_attn: bool = False):
-    """softmax(F^T G) applied to H: F [b,c,hc,wc], G/H [b,c,hs,ws] -> [b,c,hc,wc] (network/sanet.py:85-94)."""
-    _no_grad_guard(F, G, H)
-    F, G, H = _prep(F.detach(), "F"), _prep(G.detach(), "G"), _prep(H.detach(), "H")
+def _attn_fwd_raw(F, G, H, precision, return_attn):
     b, c, hc, wc = F.shape
     ls = G.shape[2] * G.shape[3]
     lc = hc * wc
-    assert G.shape[:2] == (b, c) and H.shape == G.shape
     out = torch.empty(b, c, hc, wc, dtype=torch.float32, device=F.device)
     attn = torch.empty(b, lc, ls, dtype=torch.float32, device=F.device) if return_attn else None
     L = _lib.lib()
     ws = _ws(L.rpst_sanet_attn_workspace_bytes(c, lc, ls), F.device)
     _lib.check(L.rpst_sanet_attn_fwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), out.data_ptr(), b, c, lc, ls,
                                      PRECISION[precision], _ptr(attn), ws.data_ptr(), ws.numel(), _stream()))
+    return out, attn
+
+
+class _AttnFn(torch.autograd.Function):
+    """Differentiable attention core: the backward pass recomputes the attention matrix
+    (rpst_sanet_attn_bwd) instead of keeping L x L state alive."""
+
+    @staticmethod
+    def forward(ctx, F, G, H, precision):
+        out, _ = _attn_fwd_raw(F, G, H, precision, False)
+        ctx.save_for_backward(F, G, H)
+        ctx.precision = precision
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        F, G, H = ctx.saved_tensors
+        b, c, hc, wc = F.shape
+        lc, ls = hc * wc, G.shape[2] * G.shape[3]
+        go = _prep(grad_out, "grad_out")
+        dF, dG, dH = torch.empty_like(F), torch.empty_like(G), torch.empty_like(H)
+        L = _lib.lib()
+        ws = _ws(L.rpst_sanet_attn_bwd_workspace_bytes(c, lc, ls), F.device)
+        _lib.check(L.rpst_sanet_attn_bwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), go.data_ptr(), dF.data_ptr(),
+                                         dG.data_ptr(), dH.data_ptr(), b, c, lc, ls, PRECISION[ctx.precision],
+                                         ws.data_ptr(), ws.numel(), _stream()))
+        return dF, dG, dH, None
+
+
+def attention_core(F: torch.Tensor, G: torch.Tensor, H: torch.Tensor, precision: str = "fp32", return_attn: bool = False):
+    """softmax(F^T G) applied to H: F [b,c,hc,wc], G/H [b,c,hs,ws] -> [b,c,hc,wc] (network/sanet.py:85-94).
+    Differentiable w.r.t. F, G and H (the attention matrix itself is returned detached)."""
+    F, G, H = _prep(F, "F"), _prep(G, "G"), _prep(H, "H")
+    assert G.shape[:2] == F.shape[:2] and H.shape == G.shape
+    if torch.is_grad_enabled() and (F.requires_grad or G.requires_grad or H.requires_grad):
+        out = _AttnFn.apply(F, G, H, precision)
+        if not return_attn:
+            return out
+        with torch.no_grad():
+            return out, _attn_fwd_raw(F, G, H, precision, True)[1]
+    out, attn = _attn_fwd_raw(F, G, H, precision, return_attn)
     return (out, attn) if return_attn else out
 
 

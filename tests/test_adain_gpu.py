@@ -218,12 +218,13 @@ def test_mapped_autograd_matches_gather(rpst):
     c, s = R.synth_features((2, 8, 20, 20), cfg=52, signed=True)
     m = rpst.shuffle_map(2, 8, 4, "cuda")
     cg, sg = c.cuda().requires_grad_(), s.cuda().requires_grad_()
+    w = torch.randn(c.shape, generator=torch.Generator().manual_seed(53))   # sum(out^2) alone is ~constant in c
     out = rpst.adain_mapped(cg, sg, m, m)
-    out.square().sum().backward()
+    (out * w.cuda()).sum().backward()
     cd, sd = c.double().requires_grad_(), s.double().requires_grad_()
     ml = m.long().cpu()
     cp, sp = cd.flatten(0, 1)[ml].view_as(cd), sd.flatten(0, 1)[ml].view_as(sd)
     mu_c, sd_c = cp.mean((2, 3), keepdim=True), (cp.var((2, 3), keepdim=True) + 1e-5).sqrt()
     mu_s, sd_s = sp.mean((2, 3), keepdim=True), (sp.var((2, 3), keepdim=True) + 1e-5).sqrt()
-    ((cp - mu_c) / sd_c * sd_s + mu_s).square().sum().backward()
+    (((cp - mu_c) / sd_c * sd_s + mu_s) * w.double()).sum().backward()
     assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4

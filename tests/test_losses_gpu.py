@@ -17,7 +17,7 @@ def rpst():
 
 
 def rel(a, b):
-    a, b = float(a), float(b)
+    a, b = float(a.detach()) if torch.is_tensor(a) else float(a), float(b.detach()) if torch.is_tensor(b) else float(b)
     return abs(a - b) / max(abs(b), 1e-30)
 
 

@@ -89,8 +89,67 @@ def test_sanet_relu4_1_size_vs_fp64(rpst):
     assert R.rel_l2(got, want) < TOL32
 
 
-def test_requires_grad_is_refused_loudly(rpst):
-    m = rpst.SANet(8).cuda()
+@pytest.mark.parametrize("b,c,hc,wc,hs,ws", [(2, 32, 12, 12, 12, 12), (1, 64, 20, 24, 16, 18), (1, 24, 7, 9, 11, 5),
+                                             (1, 512, 32, 32, 32, 32)])
+def test_attention_core_backward_vs_fp64_autograd(rpst, b, c, hc, wc, hs, ws):
+    """dF, dG, dH of softmax(F^T G) applied to H against fp64 autograd of the
+    reference formula (network/sanet.py:85-94); ragged tiles, lc != ls, and the relu5_1 training size."""
+    g = torch.Generator().manual_seed(100 + c)
+    f = torch.randn(b, c, hc, wc, generator=g) * 0.5
+    k = torch.randn(b, c, hs, ws, generator=g) * 0.5
+    v = torch.randn(b, c, hs, ws, generator=g)
+    w = torch.randn(b, c, hc, wc, generator=g)
+    fd, kd, vd = (t.double().requires_grad_() for t in (f, k, v))
+    S = torch.softmax(torch.bmm(fd.reshape(b, c, -1).transpose(1, 2), kd.reshape(b, c, -1)), dim=-1)
+    O = torch.bmm(vd.reshape(b, c, -1), S.transpose(1, 2)).reshape(b, c, hc, wc)
+    (O * w.double()).sum().backward()
+    fg, kg, vg = (t.cuda().requires_grad_() for t in (f, k, v))
+    out = rpst.attention_core(fg, kg, vg)
+    assert R.rel_l2(out, O) < TOL32
+    (out * w.cuda()).sum().backward()
+    assert R.rel_l2(vg.grad, vd.grad) < TOL32, R.rel_l2(vg.grad, vd.grad)
+    assert R.rel_l2(fg.grad, fd.grad) < TOL32, R.rel_l2(fg.grad, fd.grad)
+    assert R.rel_l2(kg.grad, kd.grad) < TOL32, R.rel_l2(kg.grad, kd.grad)
+    # bf16 operands: contract 1e-2 on the output; gradients pass through two more bf16 products
+    fb, kb, vb = (t.cuda().requires_grad_() for t in (f, k, v))
+    (rpst.attention_core(fb, kb, vb, precision="bf16") * w.cuda()).sum().backward()
+    assert R.rel_l2(vb.grad, vd.grad) < 5e-2 and R.rel_l2(fb.grad, fd.grad) < 5e-2 and R.rel_l2(kb.grad, kd.grad) < 5e-2
+
+
+def test_sanet_module_training_step_matches_fp64(rpst):
+    """Whole SANet module (mvn -> 1x1 convs -> attention -> out_conv + residual) forward+backward:
+    parameter and input gradients against the same module evaluated with fp64 torch ops."""
+    torch.manual_seed(3)
+    m = rpst.SANet(32).cuda()
+    c, s = R.synth_features((2, 32, 16, 16), cfg=9, device="cuda", signed=True)
+    w = torch.randn(2, 32, 16, 16, device="cuda")
+    cg, sg = c.clone().requires_grad_(), s.clone().requires_grad_()
+    (m(cg, sg) * w).sum().backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters()}
+
+    m64 = rpst.SANet(32).cuda().double()
+    m64.load_state_dict({k_: v_.double() for k_, v_ in m.state_dict().items()})
+    cd, sd = c.double().requires_grad_(), s.double().requires_grad_()
+
+    def mvn(x):
+        mu = x.mean((2, 3), keepdim=True)
+        return (x - mu) / (x.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    F, G, H = m64.f(mvn(cd)), m64.g(mvn(sd)), m64.h(sd)
+    bsz, ch, hh, ww = F.shape
+    S = torch.softmax(torch.bmm(F.view(bsz, ch, -1).permute(0, 2, 1), G.view(bsz, ch, -1)), dim=-1)
+    O = torch.bmm(H.view(bsz, ch, -1), S.permute(0, 2, 1)).view(bsz, ch, hh, ww)
+    O = m64.out_conv(O) + cd
+    (O * w.double()).sum().backward()
+    for n, p in m64.named_parameters():
+        if n == "g.bias":   # softmax is invariant to a per-row shift of S: the true gradient is exactly zero
+            assert float(got[n].abs().max()) < 1e-3 * float(m64.g.weight.grad.abs().max())
+            continue
+        assert R.rel_l2(got[n], p.grad) < TOL32, (n, R.rel_l2(got[n], p.grad))
+    assert R.rel_l2(cg.grad, cd.grad) < TOL32 and R.rel_l2(sg.grad, sd.grad) < TOL32
+
+
+def test_adaptive_requires_grad_is_refused_loudly(rpst):
+    m = rpst.AdaptiveSANet(8, 16).cuda()
     x = torch.randn(1, 8, 4, 4, device="cuda")
     with pytest.raises(NotImplementedError):
         m(x, x)

@@ -127,6 +127,32 @@ def bench_sanet():
              speedup_fp32grade=te / t3, speedup_bf16=te / t1)
 
 
+def bench_sanet_bwd():
+    """attention core forward+backward at the SAModel training sizes (network/sanet.py:253-276 at 512^2
+    crops: relu4_1 L=4096, relu5_1 L=1024) vs eager autograd on the same GPU."""
+    for (b, l_side) in ((4, 64), (4, 32)):
+        ch = 512
+        g = torch.Generator(device=dev).manual_seed(4)
+        f, k, v = (torch.randn(b, ch, l_side, l_side, device=dev, generator=g) * sc for sc in (0.3, 0.3, 1.0))
+        w = torch.randn(b, ch, l_side, l_side, device=dev, generator=g)
+        L = l_side * l_side
+        for t in (f, k, v):
+            t.requires_grad_()
+
+        def ours(prec):
+            out = rpst.attention_core(f, k, v, precision=prec)
+            return torch.autograd.grad(out, (f, k, v), w)
+
+        def eager():
+            F = f.reshape(b, ch, -1); G = k.reshape(b, ch, -1); H = v.reshape(b, ch, -1)
+            S = torch.softmax(torch.bmm(F.transpose(1, 2), G), -1)
+            return torch.autograd.grad(torch.bmm(H, S.transpose(1, 2)).reshape(w.shape), (f, k, v), w)
+        t3, t1, te = timeit(lambda: ours("fp32"), 3, 1), timeit(lambda: ours("bf16"), 3, 1), timeit(eager, 3, 1)
+        flops = (2 + 6) * 2 * L * L * ch * b     # forward 2 GEMMs, backward recompute + 5 GEMMs (one shared): 8 in total
+        emit(op=f"sanet attention fwd+bwd b={b} L={L} C=512", fp32grade_ms=t3, bf16_ms=t1, eager_gpu_fp32_ms=te,
+             TFLOPs_fp32grade=flops / t3 / 1e9, TFLOPs_bf16=flops / t1 / 1e9, speedup_fp32grade=te / t3, speedup_bf16=te / t1)
+
+
 def bench_mrf():
     ch, side, k = 512, 64, 5
     c, s = R.synth_features((1, ch, side, side), cfg=6, device=dev)
@@ -144,7 +170,31 @@ def bench_mrf():
     emit(op="mrf match+loss C=512 L=4096 k=5", rpst_ms=t, eager_gpu_ms=te, speedup=te / t)
 
 
-ALL = {"adain1": bench_adain1, "bwd": bench_bwd, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "mrf": bench_mrf}
+def bench_losses():
+    """calc_style_loss / calc_content_loss(norm) on the training step's VGG shapes (batch 8 @ 512^2 crops
+    -> relu1_1 64x512^2) and on an RP-level tensor; eager = the reference's op sequence on the same GPU."""
+    for shape in ((8, 64, 512, 512), (8, 512, 64, 64)):
+        x, y = R.synth_features(shape, cfg=8, device=dev)
+        E = x.numel() * 4
+        t = timeit(lambda: rpst.calc_style_loss(x, y), 10)
+
+        def eager_style():
+            mi, si = eager_stats(x); mt, st = eager_stats(y)
+            return torch.nn.functional.mse_loss(mi, mt) + torch.nn.functional.mse_loss(si, st)
+
+        def eager_content():
+            mi, si = eager_stats(x); mt, st = eager_stats(y)
+            return torch.nn.functional.mse_loss((x - mi) / si, (y - mt) / st)
+        te, tc = timeit(eager_style, 5), timeit(eager_content, 5)
+        xg = x.clone().requires_grad_()
+        loss = rpst.calc_content_loss(xg, y, norm=True)
+        tb = timeit(lambda: torch.autograd.grad(loss, xg, retain_graph=True), 5)
+        emit(op=f"loss statistics {shape}", one_pass_ms=t, GBs=2 * E / t / 1e6, frac_of_peak=2 * E / t / 1e6 / PEAK_GBS,
+             eager_style_ms=te, eager_content_norm_ms=tc, speedup_style=te / t, speedup_content_norm=tc / t,
+             content_norm_bwd_ms=tb, bwd_GBs=3 * E / tb / 1e6)
+
+
+ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "mrf": bench_mrf}
 for name in (sys.argv[1:] or list(ALL)):
     try:
         ALL[name]()
