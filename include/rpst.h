@@ -213,6 +213,8 @@ RPST_API int rpst_wct_fuse(const float* content, const float* style, float* out,
  *   attn_out [b,lc,ls] or NULL receives S.  passes: 3 = bf16x3 (fp32-grade, rel-L2 <= 1e-3 contract),
  *   1 = bf16 (<= 1e-2 contract).
  * ------------------------------------------------------------------------------------------ */
+ /* The workspace query returns the PER-SAMPLE minimum; a workspace of k times that size makes the call
+  * run k samples per kernel launch (batched tcgen05 GEMMs) — worth it when L is small and launches dominate. */
 RPST_API size_t rpst_sanet_attn_workspace_bytes(int64_t c, int64_t lc, int64_t ls);
 RPST_API int rpst_sanet_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t c,
                         int64_t lc, int64_t ls, int passes, float* attn_out, void* workspace,

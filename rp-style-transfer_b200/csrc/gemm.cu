@@ -31,6 +31,8 @@ struct PackParams {
     __nv_bfloat16* hi;
     __nv_bfloat16* lo;          // may be null
     int64_t row_tiles, k_tiles;
+    // batch (blockIdx.y): element stride of x, byte stride of the tile buffers, element stride of scale/shift
+    int64_t x_batch, tile_batch_bytes, vec_batch;
 };
 
 // One thread produces one 16-byte chunk (8 consecutive k of one row).  Threads of a warp walk the
@@ -38,8 +40,12 @@ struct PackParams {
 __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
     const int64_t tile = blockIdx.x;               // (row tile, k tile)
     const int64_t rb = tile / p.k_tiles, kb = tile % p.k_tiles;
-    char* hi_tile = reinterpret_cast<char*>(p.hi) + tile * kTileBytes;
-    char* lo_tile = p.lo ? reinterpret_cast<char*>(p.lo) + tile * kTileBytes : nullptr;
+    const int64_t bi = blockIdx.y;
+    p.x += bi * p.x_batch;
+    if (p.row_scale) p.row_scale += bi * p.vec_batch;
+    if (p.row_shift) p.row_shift += bi * p.vec_batch;
+    char* hi_tile = reinterpret_cast<char*>(p.hi) + bi * p.tile_batch_bytes + tile * kTileBytes;
+    char* lo_tile = p.lo ? reinterpret_cast<char*>(p.lo) + bi * p.tile_batch_bytes + tile * kTileBytes : nullptr;
     for (int item = threadIdx.x; item < kTileRows * 8; item += blockDim.x) {
         int r, c;
         if (p.stride_r == 1) { r = item % kTileRows; c = item / kTileRows; }   // MN-major source
@@ -91,6 +97,10 @@ struct GemmParams {
     float alpha;
     const float* row_add;  // [m] or null
     const float* col_add;  // [n] or null
+    // batch of independent products sharing one launch (tile index space = batch x splits x tiles)
+    int batch;
+    int64_t a_batch_bytes, b_batch_bytes;   // byte strides of the packed operands (0 = shared by the batch)
+    int64_t out_batch;                      // element stride of the output
 };
 
 __device__ __forceinline__ void gemm_tile(int rem, int m_tiles, int n_tiles, int& mb, int& nb) {
@@ -115,7 +125,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_split = p.m_tiles * p.n_tiles;
-    const int total_tiles = tiles_per_split * p.splits;
+    const int tiles_per_batch = tiles_per_split * p.splits;
+    const int total_tiles = tiles_per_batch * p.batch;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmMaxStages; ++s) {
@@ -139,12 +150,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             const uint64_t pol = policy_evict_last();   // operands are re-read by other CTAs: keep in L2
             uint32_t it = 0;                             // running k-block counter across tiles
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int z = t / tiles_per_split, rem = t % tiles_per_split;
+                const int bi = t / tiles_per_batch, tb = t % tiles_per_batch;
+                const int z = tb / tiles_per_split, rem = tb % tiles_per_split;
                 int mb, nb;
                 gemm_tile(rem, p.m_tiles, p.n_tiles, mb, nb);
                 const int k_begin = z * p.k_per_split;
                 const int k_count = min(p.k_per_split, p.k_tiles - k_begin);
                 const int nsub = min(kGemmBTiles, p.n_tiles128 - nb * kGemmBTiles);
+                const int64_t a_off = (int64_t)bi * p.a_batch_bytes, b_off = (int64_t)bi * p.b_batch_bytes;
                 for (int kb = 0; kb < k_count; ++kb, ++it) {
                     const int s = it % stages;
                     mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
@@ -155,11 +168,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
                         const __nv_bfloat16* a_src = part ? p.a_lo : p.a_hi;
                         const __nv_bfloat16* b_src = part ? p.b_lo : p.b_hi;
                         unsigned char* sp = st + (size_t)part * kGemmPartBytes;
-                        tma_load_1d(sp, reinterpret_cast<const char*>(a_src) + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
+                        tma_load_1d(sp, reinterpret_cast<const char*>(a_src) + a_off + ((int64_t)mb * p.k_tiles + kk) * kTileBytes,
                                     kTileBytes, &full[s], pol);
                         for (int sub = 0; sub < nsub; ++sub)
                             tma_load_1d(sp + kTileBytes * (1 + sub),
-                                        reinterpret_cast<const char*>(b_src) +
+                                        reinterpret_cast<const char*>(b_src) + b_off +
                                             (((int64_t)nb * kGemmBTiles + sub) * p.k_tiles + kk) * kTileBytes,
                                         kTileBytes, &full[s], pol);
                     }
@@ -171,7 +184,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             uint32_t it = 0;
             int ti = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-                const int z = t / tiles_per_split, rem = t % tiles_per_split;
+                const int tb = t % tiles_per_batch;
+                const int z = tb / tiles_per_split, rem = tb % tiles_per_split;
                 int mb, nb;
                 gemm_tile(rem, p.m_tiles, p.n_tiles, mb, nb);
                 (void)mb;
@@ -211,11 +225,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
         const int q = warp & 3;
         int ti = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-            const int z = t / tiles_per_split, rem = t % tiles_per_split;
+            const int bi = t / tiles_per_batch, tb = t % tiles_per_batch;
+            const int z = tb / tiles_per_split, rem = tb % tiles_per_split;
             int mb, nb;
             gemm_tile(rem, p.m_tiles, p.n_tiles, mb, nb);
             const int buf = ti & 1;
-            float* const out = p.out + (int64_t)z * p.split_stride;
+            float* const out = p.out + (int64_t)z * p.split_stride + (int64_t)bi * p.out_batch;
             mbar_wait(&acc_full[buf], (ti >> 1) & 1);
             tcgen05_fence_after();
             const int64_t row = (int64_t)mb * 128 + q * 32 + lane;
@@ -268,9 +283,22 @@ size_t packed_operand_bytes(int64_t rows, int64_t k) {
     return (size_t)rt * kt * kTileBytes;
 }
 
+int pack_operand_batched(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                         const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
+                         int64_t tile_batch_bytes, int64_t vec_batch, cudaStream_t stream);
+
 int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
                        const float* row_scale, const float* row_shift, void* hi, void* lo, cudaStream_t stream) {
+    return pack_operand_batched(x, rows, k, stride_r, stride_k, row_scale, row_shift, hi, lo, 1, 0, 0, 0, stream);
+}
+
+// `batch` independent operands in one launch: sample i reads x + i*x_batch (elements), scale/shift + i*vec_batch,
+// and writes its tiles at hi/lo + i*tile_batch_bytes.
+int pack_operand_batched(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                         const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
+                         int64_t tile_batch_bytes, int64_t vec_batch, cudaStream_t stream) {
     PackParams p{};
+    p.x_batch = x_batch; p.tile_batch_bytes = tile_batch_bytes; p.vec_batch = vec_batch;
     p.x = x; p.rows = rows; p.k = k; p.stride_r = stride_r; p.stride_k = stride_k; p.row_scale = row_scale;
     p.row_shift = row_shift;
     p.hi = static_cast<__nv_bfloat16*>(hi);
@@ -280,7 +308,8 @@ int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r
     const int64_t tiles = p.row_tiles * p.k_tiles;
     if (tiles == 0) return RPST_OK;
     RPST_CHECK_ARG(tiles < (1ll << 31), "pack_operand: too many tiles");
-    pack_operand_kernel<<<(unsigned)tiles, 256, 0, stream>>>(p);
+    RPST_CHECK_ARG(batch >= 1 && batch < 65536, "pack_operand: bad batch");
+    pack_operand_kernel<<<dim3((unsigned)tiles, (unsigned)batch), 256, 0, stream>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
@@ -294,6 +323,11 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                        const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
 
+int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                        const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
+                        int64_t b_batch_bytes, int64_t out_batch, cudaStream_t stream);
+
 int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                 int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                 const float* col_add, cudaStream_t stream) {
@@ -305,7 +339,18 @@ int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void
 int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                        const float* col_add, int splits, int64_t split_stride, cudaStream_t stream) {
+    return gemm_packed_batched(a_hi, a_lo, b_hi, b_lo, out, m, n, k, ldo, passes, alpha, row_add, col_add, splits,
+                               split_stride, 1, 0, 0, 0, stream);
+}
+
+// `batch` independent products in ONE persistent launch (sample i: operands + i*{a,b}_batch_bytes, output +
+// i*out_batch elements); a stride of 0 shares that operand across the batch.
+int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                        const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
+                        int64_t b_batch_bytes, int64_t out_batch, cudaStream_t stream) {
     RPST_CHECK_ARG(passes == 1 || passes == 3, "gemm_packed: passes must be 1 or 3");
+    RPST_CHECK_ARG(batch >= 1, "gemm_packed: bad batch");
     RPST_CHECK_ARG(passes == 1 || (a_lo && b_lo), "gemm_packed: bf16x3 needs the lo operands");
     if (m == 0 || n == 0) return RPST_OK;
     RPST_CHECK_ARG(k > 0, "gemm_packed: K must be positive");
@@ -332,7 +377,8 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
         RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * splits;
+    p.batch = batch; p.a_batch_bytes = a_batch_bytes; p.b_batch_bytes = b_batch_bytes; p.out_batch = out_batch;
+    const int64_t total_tiles = (int64_t)p.m_tiles * p.n_tiles * splits * batch;
     RPST_CHECK_ARG(total_tiles < (1ll << 30), "gemm_packed: too many output tiles");
     int64_t grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;

@@ -20,6 +20,13 @@ int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r
 int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                        const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
+int pack_operand_batched(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                         const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
+                         int64_t tile_batch_bytes, int64_t vec_batch, cudaStream_t stream);
+int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                        const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
+                        int64_t b_batch_bytes, int64_t out_batch, cudaStream_t stream);
 int channel_norms(const float* x, int64_t c, int64_t l, float* sq, float* nrm, float* inv, cudaStream_t st);
 
 namespace {
@@ -58,14 +65,20 @@ struct RowParams {
     int k_tiles;          // ceil(cols / 64)
     int mode;             // 0 softmax(x); 1 sigmoid(scale*(x-clamp)); 2 softmax(relu(x-clamp))
     float scale;
+    // blockIdx.y = sample of a group: element strides of in/out32 and clamp, byte stride of the tile buffers
+    int64_t in_batch, out_batch, clamp_batch, tile_batch_bytes;
 };
 
 // One CTA per row; the row (<= 64 KiB) is re-read from L1/L2 between the passes.
 __global__ void __launch_bounds__(kRowThreads) attn_rows_kernel(RowParams p) {
     __shared__ float red[kRowThreads / 32];
     const int64_t row = blockIdx.x;
-    const float* x = p.in + row * p.cols;
-    const float cl = p.clamp ? __ldg(p.clamp + row) : 0.f;
+    const int64_t bi = blockIdx.y;
+    const float* x = p.in + bi * p.in_batch + row * p.cols;
+    if (p.out32) p.out32 += bi * p.out_batch;
+    if (p.hi) p.hi = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(p.hi) + bi * p.tile_batch_bytes);
+    if (p.lo) p.lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(p.lo) + bi * p.tile_batch_bytes);
+    const float cl = p.clamp ? __ldg(p.clamp + bi * p.clamp_batch + row) : 0.f;
     float mx = 0.f, inv_sum = 1.f;
     if (p.mode != 1) {
         float m = -INFINITY;
@@ -136,18 +149,27 @@ __global__ void __launch_bounds__(256) psi_head_kernel(const float* __restrict__
         clamp[row] = mode == 1 ? (1.f / (1.f + expf(-acc))) * value_interval + from_value : (tanhf(acc) + 1.f) * 0.5f;
 }
 
+// Workspace of one GROUP of `kb` samples processed by the same launches: every buffer holds kb
+// consecutive per-sample slices (byte strides *_b), so total(kb) = kb * total(1) and a caller that passes
+// a multiple of the per-sample size gets that many samples per launch.
 struct AttnLayout {
     size_t q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, s, p_hi, p_lo, total;
+    size_t q_b, k_b, v_b, s_b, p_b;
 };
-AttnLayout attn_layout(int64_t c, int64_t lc, int64_t ls) {
+AttnLayout attn_layout(int64_t c, int64_t lc, int64_t ls, int64_t kb = 1) {
     AttnLayout l;
     size_t o = 0;
-    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
-    l.q_hi = take(packed_operand_bytes(lc, c)); l.q_lo = take(packed_operand_bytes(lc, c));
-    l.k_hi = take(packed_operand_bytes(ls, c)); l.k_lo = take(packed_operand_bytes(ls, c));
-    l.v_hi = take(packed_operand_bytes(c, ls)); l.v_lo = take(packed_operand_bytes(c, ls));
-    l.s = take((size_t)lc * ls * sizeof(float));
-    l.p_hi = take(packed_operand_bytes(lc, ls)); l.p_lo = take(packed_operand_bytes(lc, ls));
+    auto take = [&](size_t stride) { size_t at = o; o += stride * (size_t)kb; return at; };
+    l.q_b = align_up(packed_operand_bytes(lc, c), 256);
+    l.k_b = align_up(packed_operand_bytes(ls, c), 256);
+    l.v_b = align_up(packed_operand_bytes(c, ls), 256);
+    l.s_b = align_up((size_t)lc * ls * sizeof(float), 256);
+    l.p_b = align_up(packed_operand_bytes(lc, ls), 256);
+    l.q_hi = take(l.q_b); l.q_lo = take(l.q_b);
+    l.k_hi = take(l.k_b); l.k_lo = take(l.k_b);
+    l.v_hi = take(l.v_b); l.v_lo = take(l.v_b);
+    l.s = take(l.s_b);
+    l.p_hi = take(l.p_b); l.p_lo = take(l.p_b);
     l.total = o;
     return l;
 }
@@ -156,11 +178,15 @@ AttnLayout attn_layout(int64_t c, int64_t lc, int64_t ls) {
 // twice (second time from L1/L2); dS overwrites dP in fp32 and is emitted as packed operand tiles.
 __global__ void __launch_bounds__(kRowThreads) attn_bwd_rows_kernel(const float* __restrict__ prob, float* dp,
                                                                      __nv_bfloat16* hi, __nv_bfloat16* lo,
-                                                                     int64_t cols, int k_tiles) {
+                                                                     int64_t cols, int k_tiles, int64_t mat_batch,
+                                                                     int64_t tile_batch_bytes) {
     __shared__ float red[kRowThreads / 32];
     const int64_t row = blockIdx.x;
-    const float* pr = prob + row * cols;
-    float* dr = dp + row * cols;
+    const int64_t bi = blockIdx.y;
+    hi = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(hi) + bi * tile_batch_bytes);
+    if (lo) lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(lo) + bi * tile_batch_bytes);
+    const float* pr = prob + bi * mat_batch + row * cols;
+    float* dr = dp + bi * mat_batch + row * cols;
     float acc = 0.f;
     for (int64_t j = threadIdx.x; j < cols; j += kRowThreads) acc = fmaf(pr[j], dr[j], acc);
     const float delta = block_sum(acc, red);
@@ -192,15 +218,18 @@ __global__ void __launch_bounds__(kRowThreads) attn_bwd_rows_kernel(const float*
 struct AttnBwdLayout {
     AttnLayout a;            // q: [lc x c] tiles, k: [ls x c], v: [c x ls], s: P (fp32), p: [lc x ls] tiles (dS)
     size_t dp, t_hi, t_lo, w_hi, w_lo, total;   // dP/dS fp32; [ls x lc] tiles (P^T, dS^T); [c x lc] tiles (dO, F)
+    size_t t_b, w_b;
 };
-AttnBwdLayout attn_bwd_layout(int64_t c, int64_t lc, int64_t ls) {
+AttnBwdLayout attn_bwd_layout(int64_t c, int64_t lc, int64_t ls, int64_t kb = 1) {
     AttnBwdLayout l;
-    l.a = attn_layout(c, lc, ls);
+    l.a = attn_layout(c, lc, ls, kb);
     size_t o = l.a.total;
-    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
-    l.dp = take((size_t)lc * ls * sizeof(float));
-    l.t_hi = take(packed_operand_bytes(ls, lc)); l.t_lo = take(packed_operand_bytes(ls, lc));
-    l.w_hi = take(packed_operand_bytes(c, lc)); l.w_lo = take(packed_operand_bytes(c, lc));
+    auto take = [&](size_t stride) { size_t at = o; o += stride * (size_t)kb; return at; };
+    l.t_b = align_up(packed_operand_bytes(ls, lc), 256);
+    l.w_b = align_up(packed_operand_bytes(c, lc), 256);
+    l.dp = take(l.a.s_b);
+    l.t_hi = take(l.t_b); l.t_lo = take(l.t_b);
+    l.w_hi = take(l.w_b); l.w_lo = take(l.w_b);
     l.total = o;
     return l;
 }
@@ -224,38 +253,52 @@ AdaLayout ada_layout(int64_t c, int64_t lc, int64_t ls, int64_t lh) {
 }
 
 int launch_rows(const float* in, float* out32, void* hi, void* lo, const float* clamp, int64_t rows, int64_t cols,
-                int mode, float scale, cudaStream_t st) {
+                int mode, float scale, cudaStream_t st, int kb = 1, int64_t in_batch = 0, int64_t out_batch = 0,
+                int64_t tile_batch_bytes = 0, int64_t clamp_batch = 0) {
     RowParams p{};
     p.in = in; p.out32 = out32; p.hi = static_cast<__nv_bfloat16*>(hi); p.lo = static_cast<__nv_bfloat16*>(lo);
     p.clamp = clamp; p.rows = rows; p.cols = cols; p.k_tiles = (int)((cols + kTileK - 1) / kTileK);
     p.mode = mode; p.scale = scale;
+    p.in_batch = in_batch; p.out_batch = out_batch; p.tile_batch_bytes = tile_batch_bytes; p.clamp_batch = clamp_batch;
     if (hi && (rows % kTileRows != 0 || cols % kTileK != 0)) {   // zero padding of the partial tiles
-        RPST_CUDA(cudaMemsetAsync(hi, 0, packed_operand_bytes(rows, cols), st));
-        if (lo) RPST_CUDA(cudaMemsetAsync(lo, 0, packed_operand_bytes(rows, cols), st));
+        const size_t span = kb > 1 ? (size_t)tile_batch_bytes * kb : packed_operand_bytes(rows, cols);
+        RPST_CUDA(cudaMemsetAsync(hi, 0, span, st));
+        if (lo) RPST_CUDA(cudaMemsetAsync(lo, 0, span, st));
     }
-    attn_rows_kernel<<<(unsigned)rows, kRowThreads, 0, st>>>(p);
+    attn_rows_kernel<<<dim3((unsigned)rows, (unsigned)kb), kRowThreads, 0, st>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
 
-// S = F^T G for one sample into `s`
+// S = F^T G for a group of kb samples into `s` (sample stride s_batch elements)
 int scores(const float* f, const float* g, int64_t c, int64_t lc, int64_t ls, int passes, char* w, const AttnLayout& l,
-           float* s, cudaStream_t st) {
-    int rc = pack_operand_shift(f, lc, c, 1, lc, nullptr, nullptr, w + l.q_hi, passes == 3 ? w + l.q_lo : nullptr, st);
+           float* s, cudaStream_t st, int kb = 1, int64_t s_batch = 0) {
+    int rc = pack_operand_batched(f, lc, c, 1, lc, nullptr, nullptr, w + l.q_hi, passes == 3 ? w + l.q_lo : nullptr, kb,
+                                  c * lc, (int64_t)l.q_b, 0, st);
     if (rc) return rc;
-    rc = pack_operand_shift(g, ls, c, 1, ls, nullptr, nullptr, w + l.k_hi, passes == 3 ? w + l.k_lo : nullptr, st);
+    rc = pack_operand_batched(g, ls, c, 1, ls, nullptr, nullptr, w + l.k_hi, passes == 3 ? w + l.k_lo : nullptr, kb,
+                              c * ls, (int64_t)l.k_b, 0, st);
     if (rc) return rc;
-    return gemm_packed_splitk(w + l.q_hi, w + l.q_lo, w + l.k_hi, w + l.k_lo, s, lc, ls, c, ls, passes, 1.f, nullptr,
-                              nullptr, 1, 0, st);
+    return gemm_packed_batched(w + l.q_hi, w + l.q_lo, w + l.k_hi, w + l.k_lo, s, lc, ls, c, ls, passes, 1.f, nullptr,
+                               nullptr, 1, 0, kb, (int64_t)l.q_b, (int64_t)l.k_b, s_batch, st);
 }
 
-// O = H P^T for one sample (P already packed in the workspace)
+// O = H P^T for a group of kb samples (P already packed in the workspace)
 int weighted_values(const float* h, int64_t c, int64_t lc, int64_t ls, int passes, char* w, const AttnLayout& l,
-                    float* out, cudaStream_t st) {
-    int rc = pack_operand_shift(h, c, ls, ls, 1, nullptr, nullptr, w + l.v_hi, passes == 3 ? w + l.v_lo : nullptr, st);
+                    float* out, cudaStream_t st, int kb = 1) {
+    int rc = pack_operand_batched(h, c, ls, ls, 1, nullptr, nullptr, w + l.v_hi, passes == 3 ? w + l.v_lo : nullptr, kb,
+                                  c * ls, (int64_t)l.v_b, 0, st);
     if (rc) return rc;
-    return gemm_packed_splitk(w + l.v_hi, w + l.v_lo, w + l.p_hi, w + l.p_lo, out, c, lc, ls, lc, passes, 1.f, nullptr,
-                              nullptr, 1, 0, st);
+    return gemm_packed_batched(w + l.v_hi, w + l.v_lo, w + l.p_hi, w + l.p_lo, out, c, lc, ls, lc, passes, 1.f, nullptr,
+                               nullptr, 1, 0, kb, (int64_t)l.v_b, (int64_t)l.p_b, c * lc, st);
+}
+
+// samples per launch that fit the caller's workspace (a multiple of the per-sample size buys batching)
+int64_t group_size(int64_t b, size_t workspace_bytes, size_t per_sample) {
+    int64_t kb = (int64_t)(workspace_bytes / per_sample);
+    if (kb > b) kb = b;
+    if (kb > 4096) kb = 4096;
+    return kb < 1 ? 1 : kb;
 }
 
 }  // namespace
@@ -276,22 +319,26 @@ extern "C" int rpst_sanet_attn_fwd(const float* f, const float* g, const float* 
     RPST_CHECK_ARG(ls > 0, "sanet: empty style map");
     RPST_CHECK_ARG(f && g && h && out, "sanet: null pointer");
     RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet: passes must be 1 (bf16) or 3 (bf16x3, fp32-grade)");
-    const AttnLayout l = attn_layout(c, lc, ls);
-    if (!workspace || workspace_bytes < l.total) {
-        set_error("sanet: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+    const size_t per_sample = attn_layout(c, lc, ls).total;
+    if (!workspace || workspace_bytes < per_sample) {
+        set_error("sanet: workspace too small (%zu < %zu bytes)", workspace_bytes, per_sample);
         return RPST_ERR_WORKSPACE;
     }
     RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* w = static_cast<char*>(workspace);
-    for (int64_t i = 0; i < b; ++i) {
+    const int64_t kb_max = group_size(b, workspace_bytes, per_sample);
+    for (int64_t i = 0; i < b; i += kb_max) {
+        const int kb = (int)(b - i < kb_max ? b - i : kb_max);
+        const AttnLayout l = attn_layout(c, lc, ls, kb);
         float* s = attn_out ? attn_out + i * lc * ls : reinterpret_cast<float*>(w + l.s);
-        int rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l, s, st);
+        const int64_t s_batch = attn_out ? lc * ls : (int64_t)(l.s_b / sizeof(float));
+        int rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l, s, st, kb, s_batch);
         if (rc) return rc;
         rc = launch_rows(s, attn_out ? s : nullptr, w + l.p_hi, passes == 3 ? w + l.p_lo : nullptr, nullptr, lc, ls, 0,
-                         0.f, st);
+                         0.f, st, kb, s_batch, s_batch, (int64_t)l.p_b, 0);
         if (rc) return rc;
-        rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l, out + i * c * lc, st);
+        rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l, out + i * c * lc, st, kb);
         if (rc) return rc;
     }
     return RPST_OK;
@@ -315,55 +362,60 @@ extern "C" int rpst_sanet_attn_bwd(const float* f, const float* g, const float* 
     RPST_CHECK_ARG(ls > 0, "sanet_bwd: empty style map");
     RPST_CHECK_ARG(f && g && h && grad_out && grad_f && grad_g && grad_h, "sanet_bwd: null pointer");
     RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet_bwd: passes must be 1 (bf16) or 3 (bf16x3, fp32-grade)");
-    const AttnBwdLayout l = attn_bwd_layout(c, lc, ls);
-    if (!workspace || workspace_bytes < l.total) {
-        set_error("sanet_bwd: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+    const size_t per_sample = attn_bwd_layout(c, lc, ls).total;
+    if (!workspace || workspace_bytes < per_sample) {
+        set_error("sanet_bwd: workspace too small (%zu < %zu bytes)", workspace_bytes, per_sample);
         return RPST_ERR_WORKSPACE;
     }
     RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet_bwd: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* w = static_cast<char*>(workspace);
     const bool x3 = passes == 3;
-    float* prob = reinterpret_cast<float*>(w + l.a.s);
-    float* dp = reinterpret_cast<float*>(w + l.dp);
     auto lo = [&](size_t off) -> void* { return x3 ? w + off : nullptr; };
+    const int64_t kb_max = group_size(b, workspace_bytes, per_sample);
     int rc;
-    for (int64_t i = 0; i < b; ++i) {
+    for (int64_t i = 0; i < b; i += kb_max) {
+        const int kb = (int)(b - i < kb_max ? b - i : kb_max);
+        const AttnBwdLayout l = attn_bwd_layout(c, lc, ls, kb);
+        const AttnLayout& a = l.a;
+        float* prob = reinterpret_cast<float*>(w + a.s);
+        float* dp = reinterpret_cast<float*>(w + l.dp);
+        const int64_t mat = (int64_t)(a.s_b / sizeof(float));    // element stride of the per-sample L x L matrices
         const float* fi = f + i * c * lc;
         const float* gi = g + i * c * ls;
         const float* hi_ = h + i * c * ls;
         const float* doi = grad_out + i * c * lc;
         // 1. P = softmax(F^T G), kept in fp32
-        if ((rc = scores(fi, gi, c, lc, ls, passes, w, l.a, prob, st))) return rc;
-        if ((rc = launch_rows(prob, prob, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;
+        if ((rc = scores(fi, gi, c, lc, ls, passes, w, a, prob, st, kb, mat))) return rc;
+        if ((rc = launch_rows(prob, prob, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st, kb, mat, mat, 0, 0))) return rc;
         // 2. dH[c,j] = sum_i dO[c,i] P[i,j]:  A = dO (rows c, K = i), B = P^T (rows j, K = i)
-        if ((rc = pack_operand_shift(doi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), st))) return rc;
-        if ((rc = pack_operand_shift(prob, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), st))) return rc;
-        if ((rc = gemm_packed_splitk(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_h + i * c * ls, c, ls, lc, ls,
-                                     passes, 1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        if ((rc = pack_operand_batched(doi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), kb, c * lc, (int64_t)l.w_b, 0, st))) return rc;
+        if ((rc = pack_operand_batched(prob, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), kb, mat, (int64_t)l.t_b, 0, st))) return rc;
+        if ((rc = gemm_packed_batched(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_h + i * c * ls, c, ls, lc, ls,
+                                      passes, 1.f, nullptr, nullptr, 1, 0, kb, (int64_t)l.w_b, (int64_t)l.t_b, c * ls, st))) return rc;
         // 3. dP[i,j] = sum_c dO[c,i] H[c,j]:  A = dO^T (rows i, K = c), B = H^T (rows j, K = c)
-        if ((rc = pack_operand_shift(doi, lc, c, 1, lc, nullptr, nullptr, w + l.a.q_hi, lo(l.a.q_lo), st))) return rc;
-        if ((rc = pack_operand_shift(hi_, ls, c, 1, ls, nullptr, nullptr, w + l.a.k_hi, lo(l.a.k_lo), st))) return rc;
-        if ((rc = gemm_packed_splitk(w + l.a.q_hi, w + l.a.q_lo, w + l.a.k_hi, w + l.a.k_lo, dp, lc, ls, c, ls, passes, 1.f,
-                                     nullptr, nullptr, 1, 0, st))) return rc;
+        if ((rc = pack_operand_batched(doi, lc, c, 1, lc, nullptr, nullptr, w + a.q_hi, lo(a.q_lo), kb, c * lc, (int64_t)a.q_b, 0, st))) return rc;
+        if ((rc = pack_operand_batched(hi_, ls, c, 1, ls, nullptr, nullptr, w + a.k_hi, lo(a.k_lo), kb, c * ls, (int64_t)a.k_b, 0, st))) return rc;
+        if ((rc = gemm_packed_batched(w + a.q_hi, w + a.q_lo, w + a.k_hi, w + a.k_lo, dp, lc, ls, c, ls, passes, 1.f,
+                                      nullptr, nullptr, 1, 0, kb, (int64_t)a.q_b, (int64_t)a.k_b, mat, st))) return rc;
         // 4. dS = P o (dP - rowsum(dP o P)): fp32 in place of dP + operand tiles (rows i, K = j)
         if (lc % kTileRows != 0 || ls % kTileK != 0) {
-            RPST_CUDA(cudaMemsetAsync(w + l.a.p_hi, 0, packed_operand_bytes(lc, ls), st));
-            if (x3) RPST_CUDA(cudaMemsetAsync(w + l.a.p_lo, 0, packed_operand_bytes(lc, ls), st));
+            RPST_CUDA(cudaMemsetAsync(w + a.p_hi, 0, a.p_b * kb, st));
+            if (x3) RPST_CUDA(cudaMemsetAsync(w + a.p_lo, 0, a.p_b * kb, st));
         }
-        attn_bwd_rows_kernel<<<(unsigned)lc, kRowThreads, 0, st>>>(prob, dp, reinterpret_cast<__nv_bfloat16*>(w + l.a.p_hi),
-                                                                   x3 ? reinterpret_cast<__nv_bfloat16*>(w + l.a.p_lo) : nullptr,
-                                                                   ls, (int)((ls + kTileK - 1) / kTileK));
+        attn_bwd_rows_kernel<<<dim3((unsigned)lc, (unsigned)kb), kRowThreads, 0, st>>>(
+            prob, dp, reinterpret_cast<__nv_bfloat16*>(w + a.p_hi), x3 ? reinterpret_cast<__nv_bfloat16*>(w + a.p_lo) : nullptr,
+            ls, (int)((ls + kTileK - 1) / kTileK), mat, (int64_t)a.p_b);
         RPST_CUDA(cudaGetLastError());
         // 5. dF[c,i] = sum_j G[c,j] dS[i,j]:  A = G (rows c, K = j), B = dS (rows i, K = j)
-        if ((rc = pack_operand_shift(gi, c, ls, ls, 1, nullptr, nullptr, w + l.a.v_hi, lo(l.a.v_lo), st))) return rc;
-        if ((rc = gemm_packed_splitk(w + l.a.v_hi, w + l.a.v_lo, w + l.a.p_hi, w + l.a.p_lo, grad_f + i * c * lc, c, lc, ls, lc,
-                                     passes, 1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        if ((rc = pack_operand_batched(gi, c, ls, ls, 1, nullptr, nullptr, w + a.v_hi, lo(a.v_lo), kb, c * ls, (int64_t)a.v_b, 0, st))) return rc;
+        if ((rc = gemm_packed_batched(w + a.v_hi, w + a.v_lo, w + a.p_hi, w + a.p_lo, grad_f + i * c * lc, c, lc, ls, lc,
+                                      passes, 1.f, nullptr, nullptr, 1, 0, kb, (int64_t)a.v_b, (int64_t)a.p_b, c * lc, st))) return rc;
         // 6. dG[c,j] = sum_i F[c,i] dS[i,j]:  A = F (rows c, K = i), B = dS^T (rows j, K = i)
-        if ((rc = pack_operand_shift(fi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), st))) return rc;
-        if ((rc = pack_operand_shift(dp, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), st))) return rc;
-        if ((rc = gemm_packed_splitk(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_g + i * c * ls, c, ls, lc, ls,
-                                     passes, 1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        if ((rc = pack_operand_batched(fi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), kb, c * lc, (int64_t)l.w_b, 0, st))) return rc;
+        if ((rc = pack_operand_batched(dp, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), kb, mat, (int64_t)l.t_b, 0, st))) return rc;
+        if ((rc = gemm_packed_batched(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_g + i * c * ls, c, ls, lc, ls,
+                                      passes, 1.f, nullptr, nullptr, 1, 0, kb, (int64_t)l.w_b, (int64_t)l.t_b, c * ls, st))) return rc;
     }
     return RPST_OK;
 }

@@ -18,6 +18,15 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+_GROUP_BYTES = 4 << 30   # workspace budget that buys multi-sample launches (see include/rpst.h)
+
+
+def _group_ws(per_sample: int, b: int, device) -> torch.Tensor:
+    """The attention entry points take `k * per_sample` bytes and then run k samples per launch."""
+    k = max(1, min(b, _GROUP_BYTES // max(int(per_sample), 1)))
+    return _ws(k * int(per_sample), device)
+
+
 def _no_grad_guard(*tensors):
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
         raise NotImplementedError(
@@ -45,7 +54,7 @@ def _attn_fwd_raw(F, G, H, precision, return_attn):
     out = torch.empty(b, c, hc, wc, dtype=torch.float32, device=F.device)
     attn = torch.empty(b, lc, ls, dtype=torch.float32, device=F.device) if return_attn else None
     L = _lib.lib()
-    ws = _ws(L.rpst_sanet_attn_workspace_bytes(c, lc, ls), F.device)
+    ws = _group_ws(L.rpst_sanet_attn_workspace_bytes(c, lc, ls), b, F.device)
     _lib.check(L.rpst_sanet_attn_fwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), out.data_ptr(), b, c, lc, ls,
                                      PRECISION[precision], _ptr(attn), ws.data_ptr(), ws.numel(), _stream()))
     return out, attn
@@ -70,7 +79,7 @@ class _AttnFn(torch.autograd.Function):
         go = _prep(grad_out, "grad_out")
         dF, dG, dH = torch.empty_like(F), torch.empty_like(G), torch.empty_like(H)
         L = _lib.lib()
-        ws = _ws(L.rpst_sanet_attn_bwd_workspace_bytes(c, lc, ls), F.device)
+        ws = _group_ws(L.rpst_sanet_attn_bwd_workspace_bytes(c, lc, ls), b, F.device)
         _lib.check(L.rpst_sanet_attn_bwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), go.data_ptr(), dF.data_ptr(),
                                          dG.data_ptr(), dH.data_ptr(), b, c, lc, ls, PRECISION[ctx.precision],
                                          ws.data_ptr(), ws.numel(), _stream()))

@@ -153,3 +153,24 @@ def test_adaptive_requires_grad_is_refused_loudly(rpst):
     x = torch.randn(1, 8, 4, 4, device="cuda")
     with pytest.raises(NotImplementedError):
         m(x, x)
+
+
+def test_sample_groups_match_per_sample_launches(rpst, monkeypatch):
+    """k samples per launch (workspace = k x per-sample size) must give the per-sample results bit for bit:
+    group sizes 1, 2+1 and 3 on a ragged shape, forward and backward."""
+    b, c, hc, wc, hs, ws = 3, 40, 9, 11, 10, 7
+    g = torch.Generator().manual_seed(7)
+    f, k, v, w = (torch.randn(b, c, *hw, generator=g).cuda() for hw in ((hc, wc), (hs, ws), (hs, ws), (hc, wc)))
+    L = rpst._lib.lib()
+    per_f = L.rpst_sanet_attn_workspace_bytes(c, hc * wc, hs * ws)
+    per_b = L.rpst_sanet_attn_bwd_workspace_bytes(c, hc * wc, hs * ws)
+    results = []
+    for k_group in (1, 2, 3):
+        monkeypatch.setattr(rpst.sanet, "_GROUP_BYTES", k_group * max(per_f, per_b))
+        fg, kg, vg = (t.clone().requires_grad_() for t in (f, k, v))
+        out, attn = rpst.attention_core(fg, kg, vg, return_attn=True)
+        (out * w).sum().backward()
+        results.append((out.detach(), attn, fg.grad, kg.grad, vg.grad))
+    for other in results[1:]:
+        for a, b_ in zip(results[0], other):
+            assert torch.equal(a, b_)
