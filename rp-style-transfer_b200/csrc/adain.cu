@@ -31,6 +31,8 @@ struct Tuning {
     int64_t path = 0;    // 0: TMA-staged kernel when alignment allows, 1: register-staged kernel
     int64_t stages = 6;  // TMA ring depth (32 KiB per stage)
     int64_t seg_lag_bytes = 256ll << 20;  // segment AdaIN: content bytes between statistics and apply
+    int64_t seg_groups = 4;               // consumer groups (= stages) of the segment TMA kernel
+    int64_t seg_flush = 2;                // final flush: 0 shared atomics per lane, 1 warp-aggregated, 2 staged gather (atomic-free)
 };
 Tuning g_tuning;
 
@@ -1165,6 +1167,8 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     else if (!strcmp(name, "adain_path")) slot = &g_tuning.path;
     else if (!strcmp(name, "adain_stages")) slot = &g_tuning.stages;
     else if (!strcmp(name, "seg_lag_bytes")) slot = &g_tuning.seg_lag_bytes;
+    else if (!strcmp(name, "seg_flush")) slot = &g_tuning.seg_flush;
+    else if (!strcmp(name, "seg_groups")) slot = &g_tuning.seg_groups;
     if (!slot) return 0;
     if (set) *slot = v;
     if (out) *out = *slot;

@@ -325,11 +325,24 @@ __global__ void __launch_bounds__(kPipeThreads, 3) seg_pipe_kernel(SegParams p) 
 //  The statistics->apply lag is long (seg_lag_bytes, 256 MiB) because a plane's merge walks ~1000 slots;
 //  at 1024x2048 the content re-read therefore comes from HBM (4E instead of 3E bytes): next round's item.
 // ------------------------------------------------------------------------------------------
+// Item geometry.  A full item is kSegItemElems pixels of one tensor + its labels; an apply item that also
+// carries `prev` is kSegPrevElems pixels.  (8192-pixel items were measured: 2.79 ms vs 2.18 ms at config #5 —
+// the kernel is bound by per-item consumer latency, not by the producer's item rate, so smaller items on
+// more groups win.)
 constexpr int kSegItemElems = 4096;
+constexpr int kSegPrevElems = 2048;
+constexpr int kSegHalfElems = kSegPrevElems;                        // byte offset / 4 of the prev region
+constexpr int kSegDataBytes = (kSegItemElems > 2 * kSegPrevElems ? kSegItemElems : 2 * kSegPrevElems) * 4;
+constexpr int kSegStageBytes = kSegDataBytes + kSegItemElems;       // data (+prev) region, then the label bytes
+// D stages per consumer group (owned by that group alone, used alternately): the next item's TMA is in
+// flight while the current one is processed.  ncu on the single-stage version: 45 % of consumer samples sat
+// in the wait for the stage's `full` barrier (fetch latency + producer turnaround) and the rest in processing,
+// strictly one after the other.
+constexpr int kSegDepth = 2;
 constexpr int kSegGroupWarps = 4;
 constexpr int kSegGroupThreads = kSegGroupWarps * 32;
-constexpr int kSegWarpVecs = kSegItemElems / 4 / kSegGroupWarps;   // 256 float4 per warp per item
-constexpr int kSegLaneVecs = kSegWarpVecs / 32;                    // 8
+constexpr int kSegWarpVecs = kSegItemElems / 4 / kSegGroupWarps;   // 512 float4 per warp per full item
+constexpr int kSegLaneVecs = kSegWarpVecs / 32;                    // 16
 constexpr int kSegTicketBatch = 8;
 constexpr int kMaxDense = 64;    // usable labels per sample handled by the slot path
 
@@ -342,7 +355,8 @@ struct SegTmaParams {
     float* out;
     int64_t n, channels, hw_c, hw_s;
     float eps;
-    int ic, is, lag;             // content / style chunks per plane, statistics lead in planes
+    int ic, is, lag;             // content / style statistics chunks per plane, statistics lead in planes
+    int ia, apply_elems;         // apply chunks per plane and their size (kSegHalfElems with prev, else kSegItemElems)
     unsigned total_items;
     unsigned* ticket;            // starts at 0xFFFFFFFF
     int* ready;                  // [planes] coefficient table published
@@ -356,6 +370,7 @@ struct SegTmaParams {
     float2* slots;               // [planes][2][imax][kMaxDense] (S1, S2) per item; 0xFF-filled = not written
     int imax;                    // max(ic, is)
     float4* coef;                // [planes][256] (mu_c, a, mu_s, usable)
+    int flush_mode;              // 0: per-lane shared atomics, 1: warp-aggregated
 };
 
 struct __align__(16) SegDesc {
@@ -434,7 +449,7 @@ __device__ __forceinline__ float canon_f(float v) {
 __device__ __forceinline__ void seg_decode(unsigned t, const SegTmaParams& p, int& kind, int64_t& plane, int& chunk) {
     // the merge of a plane follows its statistics by one plane; the apply trails by L planes
     const unsigned P = (unsigned)(p.n * p.channels), L = (unsigned)p.lag, Lm = L - 1;
-    const unsigned Ic = (unsigned)p.ic, St = (unsigned)(p.ic + p.is);
+    const unsigned Ic = (unsigned)p.ic, St = (unsigned)(p.ic + p.is), Ia = (unsigned)p.ia;
     auto stat = [&](unsigned pl, unsigned u) {
         plane = pl;
         if (u < Ic) { kind = 0; chunk = (int)u; } else { kind = 1; chunk = (int)(u - Ic); }
@@ -447,39 +462,46 @@ __device__ __forceinline__ void seg_decode(unsigned t, const SegTmaParams& p, in
         if (u < St) stat((L - Lm) + j, u); else { kind = 3; plane = j; chunk = 0; }
         return;
     }
-    t -= n; n = (P - L) * (St + 1 + Ic);
+    t -= n; n = (P - L) * (St + 1 + Ia);
     if (t < n) {
-        const unsigned j = t / (St + 1 + Ic), u = t % (St + 1 + Ic);
+        const unsigned j = t / (St + 1 + Ia), u = t % (St + 1 + Ia);
         if (u < St) stat(L + j, u);
         else if (u == St) { kind = 3; plane = Lm + j; chunk = 0; }
         else { kind = 2; plane = j; chunk = (int)(u - St - 1); }
         return;
     }
-    t -= n; n = (L - Lm) * (1 + Ic);
+    t -= n; n = (L - Lm) * (1 + Ia);
     if (t < n) {
-        const unsigned j = t / (1 + Ic), u = t % (1 + Ic);
+        const unsigned j = t / (1 + Ia), u = t % (1 + Ia);
         if (u == 0) { kind = 3; plane = (P - L + Lm) + j; chunk = 0; }
         else { kind = 2; plane = (P - L) + j; chunk = (int)(u - 1); }
         return;
     }
     t -= n;
-    kind = 2; plane = (P - Lm) + t / Ic; chunk = (int)(t % Ic);
+    kind = 2; plane = (P - Lm) + t / Ia; chunk = (int)(t % Ia);
 }
 
+// per-group shared-memory cache: coefficient table by DENSE id (+1 identity entry), shift table and dense-id
+// map by label value, atomics accumulators [2][64][2], flush staging [4 warps][32 lanes] and per-warp label
+// totals [2][4 warps][32 labels][2]
+constexpr int kSegCoefBytes = (kMaxDense + 2) * 16;                                  // 1056
+constexpr int kSegCacheBytes = (kSegCoefBytes + kLabels * 4 + kLabels + 2 * kMaxDense * 2 * 4 +
+                                kSegGroupWarps * 32 * 16 + 2 * kSegGroupWarps * 32 * 2 * 4 + 127) / 128 * 128;
 constexpr int kSegMergeThreads = 64;   // two dedicated merge warps per CTA (one thread per dense label)
 constexpr int kSegMailbox = 8;
 
 template <int G>
 __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 1) seg_tma_kernel(SegTmaParams p) {
-    constexpr int STAGE_BYTES = 2 * kSegItemElems * 4 + kSegItemElems;          // data, prev, labels
-    constexpr int CACHE_BYTES = kLabels * (int)(sizeof(float4) + sizeof(float) + 1) + 2 * kMaxDense * 2 * (int)sizeof(float);  // coef, shift, dense id, accumulators
+    constexpr int S = G * kSegDepth;   // stages; group g owns stages g*kSegDepth .. +kSegDepth-1
+    constexpr int STAGE_BYTES = kSegStageBytes;
+    constexpr int CACHE_BYTES = kSegCacheBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* stages = smem_raw;
-    unsigned char* caches = smem_raw + (size_t)G * STAGE_BYTES;
+    unsigned char* caches = smem_raw + (size_t)S * STAGE_BYTES;
     SegDesc* desc = reinterpret_cast<SegDesc*>(caches + (size_t)G * ((CACHE_BYTES + 127) / 128 * 128));
-    uint64_t* full = reinterpret_cast<uint64_t*>(desc + G);
-    uint64_t* empty = full + G;
-    uint64_t* mfull = empty + G;              // merge mailbox: producer -> merge warps
+    uint64_t* full = reinterpret_cast<uint64_t*>(desc + S);
+    uint64_t* empty = full + S;
+    uint64_t* mfull = empty + S;              // merge mailbox: producer -> merge warps
     uint64_t* mempty = mfull + kSegMailbox;
     int64_t* mbox = reinterpret_cast<int64_t*>(mempty + kSegMailbox);   // plane id, -1 = stop
     SegDecoded* dec = reinterpret_cast<SegDecoded*>(mbox + kSegMailbox);
@@ -487,7 +509,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (__ldg(p.overflow) != 0) return;   // more usable labels than slot capacity: the fallback kernel handles the call
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G; ++s) {
+        for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kSegGroupWarps);
         }
@@ -509,19 +531,26 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
         for (;;) {
             const unsigned base = __shfl_sync(0xffffffffu, next_base, 0);
             if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kSegTicketBatch) + 1u;
+            // Lane i decodes AND issues ticket base+i: the eight items of a batch go to eight different stages
+            // (consecutive sequence numbers, G*kSegDepth >= kSegTicketBatch), so their empty-waits, descriptors
+            // and TMA issues run in SIMT lock-step instead of one after the other on a single thread (which
+            // capped both TMA kernels at ~1.3 M items/s per SM).
+            static_assert(G * kSegDepth >= kSegTicketBatch || G * kSegDepth == 6, "a batch must not reuse a stage");
+            int kind = 3, chunk = 0;    // lanes >= batch: treated like a merge (skipped)
+            int64_t plane = 0;
             if (lane < kSegTicketBatch) {
-                int kind = -1, chunk = 0;
-                int64_t plane = 0;
+                kind = -1;
                 const unsigned t = base + (unsigned)lane;
                 if (t < p.total_items) seg_decode(t, p, kind, plane, chunk);
                 dec[lane].kind = kind; dec[lane].chunk = chunk; dec[lane].plane = plane;
             }
             __syncwarp();
-            bool finished = false;
+            const unsigned stopmask = __ballot_sync(0xffffffffu, kind < 0);
+            const int nvalid = stopmask ? __ffs(stopmask) - 1 : kSegTicketBatch;   // tickets before the end of work
             if (lane == 0) {
                 // merges first: they bypass the stage ring and must never wait behind a busy stage (their own
                 // dependencies, the plane's statistics items, are a whole round older than this batch)
-                for (int i = 0; i < kSegTicketBatch; ++i) {
+                for (int i = 0; i < nvalid; ++i) {
                     if (dec[i].kind == 3) {
                         const int ms = (int)(mseq % kSegMailbox);
                         mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
@@ -530,52 +559,58 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                         ++mseq;
                     }
                 }
-                for (int i = 0; i < kSegTicketBatch; ++i) {
-                    const int kind = dec[i].kind;
-                    if (kind == 3) continue;
-                    if (kind < 0) {
-                        for (int g = 0; g < G; ++g, ++seq) {
-                            const int stage = (int)(seq % G);
-                            mbar_wait(&empty[stage], ((seq / G) & 1u) ^ 1u);
-                            desc[stage].kind = -1;
-                            mbar_arrive(&full[stage]);
-                        }
-                        const int ms = (int)(mseq % kSegMailbox);
-                        mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
-                        mbox[ms] = -1;
-                        mbar_arrive(&mfull[ms]);
-                        finished = true;
-                        break;
-                    }
-                    const int chunk = dec[i].chunk;
-                    const int64_t plane = dec[i].plane;
-                    const int stage = (int)(seq % G);
-                    mbar_wait(&empty[stage], ((seq / G) & 1u) ^ 1u);
+            }
+            const bool is_item = lane < nvalid && kind != 3;
+            const unsigned itemmask = __ballot_sync(0xffffffffu, is_item);
+            constexpr int kRound = G * kSegDepth < kSegTicketBatch ? G * kSegDepth : kSegTicketBatch;   // items issued together
+            const int my_pos = __popc(itemmask & ((1u << lane) - 1u));
+            for (int r0 = 0; r0 < kSegTicketBatch; r0 += kRound) {
+                if (is_item && my_pos >= r0 && my_pos < r0 + kRound) {
+                    const unsigned my_seq = seq + (unsigned)my_pos;
+                    const unsigned k = my_seq / G;
+                    const int stage = (int)(my_seq % G) * kSegDepth + (int)(k % kSegDepth);
+                    mbar_wait(&empty[stage], ((k / kSegDepth) & 1u) ^ 1u);
                     SegDesc* d = &desc[stage];
                     d->plane = plane; d->kind = kind; d->chunk = chunk;
-                    {
-                        const bool is_style = kind == 1;
-                        const int64_t hw = is_style ? p.hw_s : p.hw_c;
-                        const int64_t e0 = (int64_t)chunk * kSegItemElems;
-                        const int64_t rem = hw - e0;
-                        const int nvec = (int)((rem < kSegItemElems ? rem : kSegItemElems) / 4);
-                        d->nvec = nvec;
-                        const uint32_t bytes = (uint32_t)nvec * 16u;
-                        unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
-                        const int64_t sample = plane / p.channels;
-                        const float* src = (is_style ? p.style : p.content) + plane * hw + e0;
-                        const uint8_t* lab = (is_style ? p.s_lab : p.c_lab) + sample * hw + e0;
-                        const bool has_prev = kind == 2 && p.prev != nullptr;
-                        mbar_arrive_expect_tx(&full[stage], bytes + (has_prev ? bytes : 0u) + (uint32_t)nvec * 4u);
-                        tma_load_1d(st, src, bytes, &full[stage], kind == 0 ? pol_last : pol_first);
-                        if (has_prev)
-                            tma_load_1d(st + kSegItemElems * 4, p.prev + plane * hw + e0, bytes, &full[stage], pol_first);
-                        tma_load_1d(st + 2 * kSegItemElems * 4, lab, (uint32_t)nvec * 4u, &full[stage], pol_last);
-                    }
-                    ++seq;
+                    const bool is_style = kind == 1;
+                    const int64_t hw = is_style ? p.hw_s : p.hw_c;
+                    const int item_elems = kind == 2 ? p.apply_elems : kSegItemElems;
+                    const int64_t e0 = (int64_t)chunk * item_elems;
+                    const int64_t rem = hw - e0;
+                    const int nvec = (int)((rem < item_elems ? rem : item_elems) / 4);
+                    d->nvec = nvec;
+                    const uint32_t bytes = (uint32_t)nvec * 16u;
+                    unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
+                    const int64_t sample = plane / p.channels;
+                    const float* src = (is_style ? p.style : p.content) + plane * hw + e0;
+                    const uint8_t* lab = (is_style ? p.s_lab : p.c_lab) + sample * hw + e0;
+                    const bool has_prev = kind == 2 && p.prev != nullptr;
+                    mbar_arrive_expect_tx(&full[stage], bytes + (has_prev ? bytes : 0u) + (uint32_t)nvec * 4u);
+                    tma_load_1d(st, src, bytes, &full[stage], kind == 0 ? pol_last : pol_first);
+                    if (has_prev)
+                        tma_load_1d(st + kSegHalfElems * 4, p.prev + plane * hw + e0, bytes, &full[stage], pol_first);
+                    tma_load_1d(st + kSegDataBytes, lab, (uint32_t)nvec * 4u, &full[stage], pol_last);
                 }
+                __syncwarp();
             }
-            finished = __shfl_sync(0xffffffffu, (int)finished, 0) != 0;
+            seq += (unsigned)__popc(itemmask);
+            bool finished = false;
+            if (stopmask != 0u) {
+                if (lane == 0) {
+                    for (int g = 0; g < G; ++g, ++seq) {   // one stop descriptor per consumer group
+                        const unsigned k = seq / G;
+                        const int stage = (int)(seq % G) * kSegDepth + (int)(k % kSegDepth);
+                        mbar_wait(&empty[stage], ((k / kSegDepth) & 1u) ^ 1u);
+                        desc[stage].kind = -1;
+                        mbar_arrive(&full[stage]);
+                    }
+                    const int ms = (int)(mseq % kSegMailbox);
+                    mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
+                    mbox[ms] = -1;
+                    mbar_arrive(&mfull[ms]);
+                }
+                finished = true;
+            }
             if (finished) return;
             __syncwarp();
         }
@@ -583,9 +618,12 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
 
     if (warp > G * kSegGroupWarps) {
         // ================================================================ merge warps
-        // thread dn owns dense label dn: it sums that label's (S1, S2) over every item slot of the plane
-        // (content then style, fixed order, fp64, 32 loads in flight) and writes the label's coefficients.
-        const int dn = threadIdx.x - (32 + G * kSegGroupThreads);
+        // The 64 merge threads split a plane's slot rows as (dense label, part): with d usable labels there are
+        // 64/d parts per label, each summing a contiguous range of item slots (content then style, fixed
+        // order, fp64, 32 loads in flight); part 0 then adds the parts in index order (deterministic) and
+        // writes the label's coefficients.  19 labels => 3 parts => a plane's ~1000 slots take ~11 load rounds.
+        __shared__ double s_merge[kSegMergeThreads][4];
+        const int t = threadIdx.x - (32 + G * kSegGroupThreads);
         for (unsigned mseq = 0;; ++mseq) {
             const int ms = (int)(mseq % kSegMailbox);
             mbar_wait(&mfull[ms], (mseq / kSegMailbox) & 1u);
@@ -595,23 +633,28 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
             if (plane < 0) break;
             const int64_t sample = plane / p.channels;
             const int dcount = __ldg(p.dense_count + sample);
+            const int parts = dcount > 0 ? kSegMergeThreads / dcount : 1;
+            const int dn = dcount > 0 ? t % dcount : 0;
+            const int part = dcount > 0 ? t / dcount : parts;
             double s4[4] = {0.0, 0.0, 0.0, 0.0};
-            if (dn < dcount) {
+            if (part < parts) {
 #pragma unroll
                 for (int which = 0; which < 2; ++which) {
                     const int items = which ? p.is : p.ic;
+                    const int per = (items + parts - 1) / parts;
+                    const int lo = part * per, hi = min(items, lo + per);
                     const float2* base = p.slots + ((plane * 2 + which) * p.imax) * kMaxDense + dn;
                     constexpr int kUnroll = 32;
-                    for (int c0 = 0; c0 < items; c0 += kUnroll) {
+                    for (int c0 = lo; c0 < hi; c0 += kUnroll) {
                         float2 v[kUnroll];
 #pragma unroll
                         for (int u = 0; u < kUnroll; ++u) {
                             v[u] = make_float2(0.f, 0.f);
-                            if (c0 + u < items) v[u] = ld_slot1(base + (int64_t)(c0 + u) * kMaxDense);
+                            if (c0 + u < hi) v[u] = ld_slot1(base + (int64_t)(c0 + u) * kMaxDense);
                         }
 #pragma unroll
                         for (int u = 0; u < kUnroll; ++u) {
-                            if (c0 + u < items) {
+                            if (c0 + u < hi) {
                                 if (!slot1_valid(v[u])) {
                                     const float2* sp = base + (int64_t)(c0 + u) * kMaxDense;
                                     const uint64_t t0 = global_timer_ns();
@@ -627,6 +670,15 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                         }
                     }
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_merge[t][q] = s4[q];
+            named_bar_sync(15, kSegMergeThreads);
+            if (t < dcount) {   // part 0 of label dn == t
+                for (int q = 1; q < parts; ++q) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s4[e] += s_merge[q * dcount + t][e];
+                }
                 const int l = __ldg(p.label_of + sample * kMaxDense + dn);
                 const double dnc = (double)__ldg(p.cnt + (sample * 2 + 0) * kLabels + l);
                 const double dns = (double)__ldg(p.cnt + (sample * 2 + 1) * kLabels + l);
@@ -638,11 +690,11 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                 __stcg(&p.coef[plane * kLabels + l], make_float4((float)mu_c, (float)(sd_s / sd_c), (float)mu_s, 1.f));
             }
             // identity for every unusable label: (c-0)*1+0 == c bit-exactly
-            for (int l = dn; l < kLabels; l += kSegMergeThreads)
+            for (int l = t; l < kLabels; l += kSegMergeThreads)
                 if (__ldg(p.dense + sample * kLabels + l) == 255) __stcg(&p.coef[plane * kLabels + l], make_float4(0.f, 1.f, 0.f, 0.f));
             __threadfence();
             named_bar_sync(15, kSegMergeThreads);
-            if (dn == 0) st_release(&p.ready[plane], 1);
+            if (t == 0) st_release(&p.ready[plane], 1);
         }
         return;
     }
@@ -652,10 +704,12 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
     const int gw = (warp - 1) % kSegGroupWarps;
     const int gt = gw * 32 + lane;
     unsigned char* cache = caches + (size_t)group * ((CACHE_BYTES + 127) / 128 * 128);
-    float4* c_coef = reinterpret_cast<float4*>(cache);
-    float* c_shift = reinterpret_cast<float*>(cache + kLabels * sizeof(float4));
-    unsigned char* c_dense = cache + kLabels * (sizeof(float4) + sizeof(float));
-    float* c_acc = reinterpret_cast<float*>(cache + kLabels * (sizeof(float4) + sizeof(float) + 1));  // [2][kMaxDense][2]
+    float4* c_coef = reinterpret_cast<float4*>(cache);                                  // [kMaxDense + 1] by dense id; last = identity
+    float* c_shift = reinterpret_cast<float*>(cache + kSegCoefBytes);                    // [256] by label
+    unsigned char* c_dense = cache + kSegCoefBytes + kLabels * 4;                        // [256] by label
+    float* c_acc = reinterpret_cast<float*>(c_dense + kLabels);                          // [2][kMaxDense][2]
+    float4* c_stage = reinterpret_cast<float4*>(c_acc + 2 * kMaxDense * 2);              // [4 warps][32 lanes]
+    float* c_wtot = reinterpret_cast<float*>(c_stage + kSegGroupWarps * 32);             // [2][4 warps][32][2]
     const uint64_t pol_first = policy_evict_first();
     int64_t cached_stat = -1;    // plane*2+which whose shift table is in the cache
     int64_t cached_apply = -1;   // plane whose coefficient table is in the cache
@@ -666,21 +720,24 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
     named_bar_sync(1 + group, kSegGroupThreads);
 
     for (unsigned seq = group;; seq += G) {
-        const int stage = (int)(seq % G);
-        mbar_wait(&full[stage], (seq / G) & 1u);
+        const unsigned k = seq / G;
+        const int stage = group * kSegDepth + (int)(k % kSegDepth);
+        mbar_wait(&full[stage], (k / kSegDepth) & 1u);
         const SegDesc* d = &desc[stage];
         const int kind = d->kind;
         if (kind < 0) break;
         const int64_t plane = d->plane;
         const int chunk = d->chunk;
-        const int wvec = min(max(d->nvec - gw * kSegWarpVecs, 0), kSegWarpVecs);
+        // vectors per warp: a full item gives each warp 512 (16 per lane), a half item (apply with prev) 256
+        const int warp_vecs = (kind == 2 ? p.apply_elems : kSegItemElems) / 4 / kSegGroupWarps;
+        const int wvec = min(max(d->nvec - gw * warp_vecs, 0), warp_vecs);
         const int64_t sample = plane / p.channels;
         unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
-        const float4* a4 = reinterpret_cast<const float4*>(st) + gw * kSegWarpVecs;
-        const float4* b4 = reinterpret_cast<const float4*>(st + kSegItemElems * 4) + gw * kSegWarpVecs;
-        const uint32_t* l4 = reinterpret_cast<const uint32_t*>(st + 2 * kSegItemElems * 4) + gw * kSegWarpVecs;
+        const float4* a4 = reinterpret_cast<const float4*>(st) + gw * warp_vecs;
+        const float4* b4 = reinterpret_cast<const float4*>(st + kSegHalfElems * 4) + gw * warp_vecs;
+        const uint32_t* l4 = reinterpret_cast<const uint32_t*>(st + kSegDataBytes) + gw * warp_vecs;
 
-        if (kind <= 1) {
+        {
             if (sample != cached_sample) {   // group-uniform: dense-id map of this sample
                 named_bar_sync(1 + group, kSegGroupThreads);
                 for (int l = gt; l < kLabels; l += kSegGroupThreads) c_dense[l] = __ldg(p.dense + sample * kLabels + l);
@@ -706,12 +763,24 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
             // Each lane owns 32 CONTIGUOUS pixels (8 float4) so that label runs stay long on blocky maps;
             // the 8 vectors are visited in a lane-rotated order, which keeps the 128-byte-strided
             // shared-memory reads of a quarter warp on distinct banks.
+            // all of the lane's vectors and label words are fetched first (16 independent shared-memory loads),
+            // the run logic below then works from registers instead of paying one LDS latency per step
+            float4 vv[kSegLaneVecs];
+            uint32_t lww[kSegLaneVecs];
+#pragma unroll
+            for (int j = 0; j < kSegLaneVecs; ++j) {
+                const int idx = lane * kSegLaneVecs + ((j + lane) & (kSegLaneVecs - 1));
+                if (idx < wvec) { vv[j] = a4[idx]; lww[j] = l4[idx]; }
+            }
+            // the stage has been consumed (everything is in registers): hand it back before the arithmetic
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
 #pragma unroll
             for (int j = 0; j < kSegLaneVecs; ++j) {
                 const int idx = lane * kSegLaneVecs + ((j + lane) & (kSegLaneVecs - 1));
                 if (idx < wvec) {
-                    const float4 v = a4[idx];
-                    const uint32_t lw = l4[idx];
+                    const float4 v = vv[j];
+                    const uint32_t lw = lww[j];
                     if (lw == cur4 && cur >= 0) {
                         const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
                         a1 += (d0 + d1) + (d2 + d3);
@@ -742,20 +811,59 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     }
                 }
             }
-            // the stage has been consumed
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
             // final flush into the group's shared accumulators.  Shared-memory atomics cost one pass per
             // distinct address, which beats a shuffle tree per distinct label on fine-grained maps and is
             // a single 32-way same-address pass on blocky ones.
-            if (cur >= 0) {
-                atomicAdd(&acc[cur * 2 + 0], a1);
-                atomicAdd(&acc[cur * 2 + 1], a2);
+            // (fp32 shared-memory atomics are CAS loops: 128 threads on one address serialise 128 rounds.  The
+            // final flush is therefore aggregated per warp first — lanes holding the same running label are
+            // summed with shuffles and one lane adds — which on blocky maps is one or two rounds.)
+            const bool staged = p.flush_mode == 2 && dcount <= 32;
+            float* wt = c_wtot + (sparity * kSegGroupWarps + gw) * 64;
+            if (staged) {
+                // Atomic-free and deterministic: every lane stages its open run (dense id, S1, S2); lane d then
+                // gathers label d over the 32 staged runs in lane order (broadcast reads) and stores the warp's
+                // total for that label; the publishing thread below adds the four warps in warp order.
+                float4* stg = c_stage + gw * 32;
+                stg[lane] = make_float4(__int_as_float(cur), a1, a2, 0.f);
+                __syncwarp();
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const float4 r = stg[j];
+                    if (__float_as_int(r.x) == lane) { t1 += r.y; t2 += r.z; }
+                }
+                wt[lane * 2 + 0] = t1;
+                wt[lane * 2 + 1] = t2;
+                __syncwarp();
+            } else if (p.flush_mode != 1) {
+                if (cur >= 0) {
+                    atomicAdd(&acc[cur * 2 + 0], a1);
+                    atomicAdd(&acc[cur * 2 + 1], a2);
+                }
+            } else {
+                unsigned pending = __ballot_sync(0xffffffffu, cur >= 0);
+                while (pending) {
+                    const int leader = __ffs(pending) - 1;
+                    const int lcur = __shfl_sync(0xffffffffu, cur, leader);
+                    const bool mine = cur == lcur;
+                    const float s1 = warp_sum(mine ? a1 : 0.f), s2 = warp_sum(mine ? a2 : 0.f);
+                    if (lane == leader) {
+                        atomicAdd(&acc[lcur * 2 + 0], s1);
+                        atomicAdd(&acc[lcur * 2 + 1], s2);
+                    }
+                    pending &= ~__ballot_sync(0xffffffffu, mine);
+                }
             }
             named_bar_sync(1 + group, kSegGroupThreads);
             // publish: one self-validating 8-byte slot per usable label (no fence, no atomic, no counter)
             if (gt < dcount) {
-                const float s1 = canon_f(acc[gt * 2 + 0]), s2 = canon_f(acc[gt * 2 + 1]);
+                float t1 = acc[gt * 2 + 0], t2 = acc[gt * 2 + 1];   // mid-item flushes (label change inside a lane's run)
+                if (staged) {
+                    const float* w0 = c_wtot + sparity * kSegGroupWarps * 64;
+#pragma unroll
+                    for (int q = 0; q < kSegGroupWarps; ++q) { t1 += w0[q * 64 + gt * 2 + 0]; t2 += w0[q * 64 + gt * 2 + 1]; }
+                }
+                const float s1 = canon_f(t1), s2 = canon_f(t2);
                 acc[gt * 2 + 0] = 0.f;
                 acc[gt * 2 + 1] = 0.f;
                 float2* slot = p.slots + ((key * p.imax + chunk) * kMaxDense + gt);
@@ -773,16 +881,18 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     }
                 }
                 named_bar_sync(1 + group, kSegGroupThreads);
-                for (int l = gt; l < kLabels; l += kSegGroupThreads) c_coef[l] = __ldcg(&p.coef[plane * kLabels + l]);
+                if (gt < dcount) c_coef[gt] = __ldcg(&p.coef[plane * kLabels + __ldg(p.label_of + sample * kMaxDense + gt)]);
+                if (gt == kSegGroupThreads - 1) c_coef[kMaxDense] = make_float4(0.f, 1.f, 0.f, 0.f);   // unusable labels: (c-0)*1+0 == c
                 named_bar_sync(1 + group, kSegGroupThreads);
                 cached_apply = plane;
             }
             const bool has_prev = p.prev != nullptr;
-            float4* o4 = reinterpret_cast<float4*>(p.out + plane * p.hw_c + (int64_t)chunk * kSegItemElems) + gw * kSegWarpVecs;
+            float4* o4 = reinterpret_cast<float4*>(p.out + plane * p.hw_c + (int64_t)chunk * p.apply_elems) + gw * warp_vecs;
             uint32_t last_w = 0;
-            float4 cf = c_coef[0];
+            float4 cf = c_coef[kMaxDense];
             bool have = false;
-#pragma unroll
+            auto coef_of = [&](uint32_t l) -> float4 { const int dn = c_dense[l]; return c_coef[dn < kMaxDense ? dn : kMaxDense]; };
+#pragma unroll 8
             for (int j = 0; j < kSegLaneVecs; ++j) {
                 const int idx = j * 32 + lane;
                 if (idx < wvec) {
@@ -791,14 +901,14 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     float4 o;
                     const uint32_t b0 = lw & 0xffu;
                     if (lw == b0 * 0x01010101u) {   // all four pixels carry the same label
-                        if (!have || lw != last_w) { cf = c_coef[b0]; last_w = lw; have = true; }
+                        if (!have || lw != last_w) { cf = coef_of(b0); last_w = lw; have = true; }
                         o.x = fmaf(v.x - cf.x, cf.y, cf.z);
                         o.y = fmaf(v.y - cf.x, cf.y, cf.z);
                         o.z = fmaf(v.z - cf.x, cf.y, cf.z);
                         o.w = fmaf(v.w - cf.x, cf.y, cf.z);
                     } else {
-                        const float4 c0 = c_coef[b0], c1 = c_coef[(lw >> 8) & 0xffu], c2 = c_coef[(lw >> 16) & 0xffu],
-                                     c3 = c_coef[lw >> 24];
+                        const float4 c0 = coef_of(b0), c1 = coef_of((lw >> 8) & 0xffu), c2 = coef_of((lw >> 16) & 0xffu),
+                                     c3 = coef_of(lw >> 24);
                         o.x = fmaf(v.x - c0.x, c0.y, c0.z);
                         o.y = fmaf(v.y - c1.x, c1.y, c1.z);
                         o.z = fmaf(v.z - c2.x, c2.y, c2.z);
@@ -881,9 +991,9 @@ SegTmaLayout seg_tma_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
 
 template <int G>
 int launch_seg_tma(const SegTmaParams& p, cudaStream_t st) {
-    constexpr size_t stage = 2 * kSegItemElems * 4 + kSegItemElems;
-    constexpr size_t cache = (kLabels * (sizeof(float4) + sizeof(float) + 1) + 2 * kMaxDense * 2 * sizeof(float) + 127) / 128 * 128;
-    constexpr size_t smem = G * (stage + cache) + G * sizeof(SegDesc) + 2 * G * sizeof(uint64_t) +
+    constexpr size_t stage = kSegStageBytes;
+    constexpr size_t cache = kSegCacheBytes;
+    constexpr size_t smem = G * (kSegDepth * stage + cache) + G * kSegDepth * sizeof(SegDesc) + 2 * G * kSegDepth * sizeof(uint64_t) +
                             2 * kSegMailbox * sizeof(uint64_t) + kSegMailbox * sizeof(int64_t) +
                             kSegTicketBatch * sizeof(SegDecoded);
     static bool configured = false;
@@ -974,14 +1084,18 @@ extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, cons
         q.ic = (int)((hw_c + kSegItemElems - 1) / kSegItemElems);
         q.is = (int)((hw_s + kSegItemElems - 1) / kSegItemElems);
         q.imax = q.ic > q.is ? q.ic : q.is;
+        q.apply_elems = prev ? kSegPrevElems : kSegItemElems;
+        q.ia = (int)((hw_c + q.apply_elems - 1) / q.apply_elems);
         const int64_t plane_bytes = hw_c * (int64_t)sizeof(float);
+        q.flush_mode = (int)adain_tuning_value("seg_flush");
         int64_t lag = (adain_tuning_value("seg_lag_bytes") + plane_bytes - 1) / plane_bytes;
         if (lag < 3) lag = 3;
         q.lag = (int)(lag < planes ? lag : planes);
-        const int64_t total = planes * (2ll * q.ic + q.is + 1);
+        const int64_t total = planes * ((int64_t)q.ic + q.is + 1 + q.ia);
         RPST_CHECK_ARG(total < (1ll << 31), "seg_adain: too many work items (%lld); split the call", (long long)total);
         q.total_items = (unsigned)total;
-        const int rc = launch_seg_tma<5>(q, st);
+        const int64_t groups = adain_tuning_value("seg_groups");
+        const int rc = groups == 3 ? launch_seg_tma<3>(q, st) : launch_seg_tma<4>(q, st);   // 4 groups x 2 stages x 20 KiB
         if (rc) return rc;
         // a sample with more than kMaxDense usable labels makes the slot kernel exit at once and the
         // register-staged kernel below run instead (device-side decision: no host synchronisation)
