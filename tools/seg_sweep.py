@@ -3,14 +3,13 @@ import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rpst
 from oracle import restate as R
-n, ch, h, w = 1, 256, 1024, 2048
+n, ch, h, w = (int(a) for a in os.environ.get("SEG_SHAPE", "1,256,1024,2048").split(","))
 c, s = R.synth_features((n, ch, h, w), cfg=5, device="cuda")
 cl = R.synth_labels(n, h, w, seed=4000, device="cuda"); sl = R.synth_labels(n, h, w, seed=5000, device="cuda")
 E = c.numel() * 4
 alg = 3 * E + 2 * h * w
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
 for flush in (4,):
-  rpst.set_tuning("seg_groups", flush)
   for lag_mib in [int(a) for a in sys.argv[1:]] or [24, 32, 48, 64, 96, 128, 256]:
     rpst.set_tuning("seg_lag_bytes", lag_mib << 20)
     for _ in range(2):
