@@ -78,7 +78,7 @@ def bench_seg():
 
 
 def bench_wct():
-    n, ch, h, w = 4, 256, 512, 512
+    n, ch, h, w = 16, 256, 512, 512      # BASELINE configs[2] at its full batch
     c, s = R.synth_features((n, ch, h, w), cfg=3, device=dev)
     t = timeit(lambda: rpst.wct_fuse(c, s), 3, 1)
     t16 = timeit(lambda: rpst.wct_fuse(c, s, precision="bf16"), 3, 1)
@@ -100,7 +100,7 @@ def bench_wct():
         return (t_ @ xc + sm).float()
     te = timeit(eager_one, 1, 1)
     flops = 3 * 2 * ch * ch * h * w * n
-    emit(op="wct config#3 (4 of 16 samples) 256x512x512", ms_per_sample=t / n, bf16_ms_per_sample=t16 / n,
+    emit(op="wct config#3 batch 16 x 256x512x512", ms_per_sample=t / n, bf16_ms_per_sample=t16 / n,
          eager_gpu_fp64_ms_per_sample=te, speedup_vs_eager=te / (t / n), algorithmic_TFLOPs=flops / t / 1e9,
          algorithmic_GBs=4 * c.numel() * 4 / t / 1e6)
 
