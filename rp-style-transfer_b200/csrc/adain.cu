@@ -31,6 +31,7 @@ struct Tuning {
     int64_t path = 0;    // 0: TMA-staged kernel when alignment allows, 1: register-staged kernel
     int64_t stages = 6;  // TMA ring depth (32 KiB per stage)
     int64_t seg_lag_bytes = 256ll << 20;  // segment AdaIN: content bytes between statistics and apply
+    int64_t twin_apply = 1;               // TMA kernel, no prev: apply items carry two content chunks (32 KiB per stage)
     int64_t seg_groups = 4;               // consumer groups (= stages) of the segment TMA kernel
     int64_t seg_flush = 2;                // final flush: 0 shared atomics per lane, 1 warp-aggregated, 2 staged gather (atomic-free)
 };
@@ -52,6 +53,8 @@ struct AdainParams {
     int hints;
     // pipelined kernel only
     int ipp;             // items (chunks) per plane
+    int ipa;             // TMA kernel: apply items per plane (ipp with prev; ceil(ipp/2) without: an apply item
+                         // then carries two content chunks, so every stage moves 32 KiB whatever the item kind)
     int spp;             // statistics slots per plane
     int slot_elems;      // elements summarised by one slot (last slot of a plane may be short)
     int lag;             // planes between statistics and apply
@@ -471,8 +474,9 @@ struct __align__(16) StageDesc {
     int64_t plane;
     int kind;       // 0 statistics, 1 apply, 2 merge, -1 stop
     int chunk;
-    int nvec;
-    int pad[3];
+    int nvec;       // valid float4 in buffer a
+    int nvec2;      // apply items without prev: valid float4 of the SECOND content chunk in buffer b
+    int pad[2];
 };
 
 struct DecodedItem {
@@ -483,7 +487,7 @@ struct DecodedItem {
 __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int& kind, int64_t& plane, int& chunk) {
     const unsigned I = (unsigned)p.ipp;
     if (p.stats_only) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
-    const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = L / 2;
+    const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = L / 2, A = (unsigned)p.ipa;
     // rounds: [S only] x (L-Lm), [S,M] x Lm, [S,M,A] x (P-L), [M,A] x (L-Lm), [A] x Lm
     unsigned n = (L - Lm) * I;
     if (t < n) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
@@ -494,23 +498,23 @@ __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int
         else { kind = 2; plane = j; chunk = 0; }
         return;
     }
-    t -= n; n = (P - L) * (2 * I + 1);
+    t -= n; n = (P - L) * (I + 1 + A);
     if (t < n) {
-        const unsigned j = t / (2 * I + 1), u = t % (2 * I + 1);
+        const unsigned j = t / (I + 1 + A), u = t % (I + 1 + A);
         if (u < I) { kind = 0; plane = L + j; chunk = (int)u; }
         else if (u == I) { kind = 2; plane = Lm + j; chunk = 0; }
         else { kind = 1; plane = j; chunk = (int)(u - I - 1); }
         return;
     }
-    t -= n; n = (L - Lm) * (I + 1);
+    t -= n; n = (L - Lm) * (A + 1);
     if (t < n) {
-        const unsigned j = t / (I + 1), u = t % (I + 1);
+        const unsigned j = t / (A + 1), u = t % (A + 1);
         if (u == 0) { kind = 2; plane = (P - L + Lm) + j; chunk = 0; }
         else { kind = 1; plane = (P - L) + j; chunk = (int)(u - 1); }
         return;
     }
     t -= n;
-    kind = 1; plane = (P - Lm) + t / I; chunk = (int)(t % I);
+    kind = 1; plane = (P - Lm) + t / A; chunk = (int)(t % A);
 }
 
 // STAGES == number of consumer groups: group g owns stage g for the whole kernel, so the uses of a
@@ -578,11 +582,14 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                     const int stage = (int)(seq % STAGES);
                     mbar_wait(&empty[stage], ((seq / STAGES) & 1u) ^ 1u);
                     StageDesc* d = &desc[stage];
-                    const int64_t e0 = (int64_t)chunk * kItemElems;
+                    const bool twin = kind == 1 && p.ipa != p.ipp;    // apply item carrying two content chunks
+                    const int64_t e0 = (int64_t)chunk * (twin ? 2 * kItemElems : kItemElems);
                     const int64_t rem = p.hw - e0;
                     const int nvec = (int)((rem < kItemElems ? rem : kItemElems) / 4);
+                    const int64_t rem2 = rem - kItemElems;
+                    const int nvec2 = twin && rem2 > 0 ? (int)((rem2 < kItemElems ? rem2 : kItemElems) / 4) : 0;
                     const uint32_t bytes = (uint32_t)nvec * 16u;
-                    d->plane = plane; d->kind = kind; d->chunk = chunk; d->nvec = nvec;
+                    d->plane = plane; d->kind = kind; d->chunk = chunk; d->nvec = nvec; d->nvec2 = nvec2;
                     float* buf_a = bufs + (size_t)(stage * 2 + 0) * kItemElems;
                     float* buf_b = bufs + (size_t)(stage * 2 + 1) * kItemElems;
                     const float* csrc = p.content + dec[i].cplane * p.hw + e0;
@@ -593,9 +600,10 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                         if (has_style) tma_load_1d(buf_b, p.style + dec[i].splane * p.hw + e0, bytes, &full[stage], pol_first);
                     } else if (kind == 1) {
                         const bool has_prev = p.prev != nullptr;
-                        mbar_arrive_expect_tx(&full[stage], (has_prev ? 2u * bytes : bytes) + 16u);
+                        mbar_arrive_expect_tx(&full[stage], (has_prev ? 2u * bytes : bytes) + (uint32_t)nvec2 * 16u + 16u);
                         tma_load_1d(buf_a, csrc, bytes, &full[stage], pol_first);
                         if (has_prev) tma_load_1d(buf_b, p.prev + plane * p.hw + e0, bytes, &full[stage], pol_first);
+                        if (nvec2 > 0) tma_load_1d(buf_b, csrc + kItemElems, (uint32_t)nvec2 * 16u, &full[stage], pol_first);
                         tma_load_1d(&d->coef, &p.coef[plane], 16u, &full[stage], pol_last);
                     } else {
                         mbar_arrive(&full[stage]);
@@ -673,8 +681,9 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
             }
             const float mu_hi = cf.x, a = cf.y, mu_s = cf.z, mu_lo = cf.w;
             const int64_t n_idx = plane / p.channels, ch = plane % p.channels;
+            const bool twin = p.ipa != p.ipp;   // no prev: the item carries two content chunks (buffers a and b)
             float4* o4 = reinterpret_cast<float4*>(p.out + n_idx * p.out_batch_stride + ch * p.hw +
-                                                   (int64_t)chunk * kItemElems) + gw * (kTmaSlotElems / 4);
+                                                   (int64_t)chunk * (twin ? 2 * kItemElems : kItemElems)) + gw * (kTmaSlotElems / 4);
 #pragma unroll
             for (int j = 0; j < kTmaVecs; ++j) {
                 if (j < my_vecs) {
@@ -689,6 +698,23 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                         o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
                     }
                     stg_f4_hint(reinterpret_cast<float*>(o4 + j * 32 + lane), o, pol_first);
+                }
+            }
+            if (twin) {
+                const int wvec2 = min(max(d->nvec2 - gw * (kTmaSlotElems / 4), 0), kTmaSlotElems / 4);
+                const int my_vecs2 = wvec2 > lane ? min((wvec2 - lane + 31) / 32, kTmaVecs) : 0;
+                float4* o4b = o4 + kItemElems / 4;
+#pragma unroll
+                for (int j = 0; j < kTmaVecs; ++j) {
+                    if (j < my_vecs2) {
+                        const float4 c = b4[j * 32 + lane];
+                        float4 o;
+                        o.x = fmaf((c.x - mu_hi) - mu_lo, a, mu_s);
+                        o.y = fmaf((c.y - mu_hi) - mu_lo, a, mu_s);
+                        o.z = fmaf((c.z - mu_hi) - mu_lo, a, mu_s);
+                        o.w = fmaf((c.w - mu_hi) - mu_lo, a, mu_s);
+                        stg_f4_hint(reinterpret_cast<float*>(o4b + j * 32 + lane), o, pol_first);
+                    }
                 }
             }
             __syncwarp();
@@ -1056,7 +1082,8 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const bool use_tma = VEC == 4 && g_tuning.path == 0;
     p.slot_elems = use_tma ? kTmaSlotElems : kItemElems;
     p.spp = (int)((p.hw + p.slot_elems - 1) / p.slot_elems);
-    const int64_t total = p.stats_only ? p.planes * p.ipp : p.planes * (2ll * p.ipp + (use_tma ? 1 : 0));
+    p.ipa = (use_tma && !p.stats_only && p.prev == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
+    const int64_t total = p.stats_only ? p.planes * p.ipp : p.planes * ((int64_t)p.ipp + p.ipa + (use_tma ? 1 : 0));
     RPST_CHECK_ARG(total < (1ll << 31), "adain: too many work items (%lld); split the call", (long long)total);
     p.total_items = (unsigned)total;
     p.ticket = reinterpret_cast<unsigned*>(base);
@@ -1169,6 +1196,7 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     else if (!strcmp(name, "seg_lag_bytes")) slot = &g_tuning.seg_lag_bytes;
     else if (!strcmp(name, "seg_flush")) slot = &g_tuning.seg_flush;
     else if (!strcmp(name, "seg_groups")) slot = &g_tuning.seg_groups;
+    else if (!strcmp(name, "adain_twin_apply")) slot = &g_tuning.twin_apply;
     if (!slot) return 0;
     if (set) *slot = v;
     if (out) *out = *slot;
