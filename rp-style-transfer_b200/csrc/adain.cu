@@ -26,11 +26,13 @@ namespace {
 
 struct Tuning {
     int64_t lag_bytes = 32ll << 20;
+    int64_t big_lag_bytes = 128ll << 20;  // planes >= 4 MiB
     int64_t hints = 1;
     int64_t ctas_per_sm = 4;
     int64_t path = 0;    // 0: TMA-staged kernel when alignment allows, 1: register-staged kernel
     int64_t stages = 6;  // TMA ring depth (32 KiB per stage)
     int64_t seg_lag_bytes = 256ll << 20;  // segment AdaIN: content bytes between statistics and apply
+    int64_t group_merge_min_spp = 512;    // see merge_plane_coef_group
     int64_t twin_apply = 1;               // TMA kernel, no prev: apply items carry two content chunks (32 KiB per stage)
     int64_t seg_groups = 4;               // consumer groups (= stages) of the segment TMA kernel
     int64_t seg_flush = 2;                // final flush: 0 shared atomics per lane, 1 warp-aggregated, 2 staged gather (atomic-free)
@@ -66,6 +68,7 @@ struct AdainParams {
     // takes its content from plane cmap[p] and its style from plane smap[p] (null = identity)
     const int* cmap;
     const int* smap;
+    int group_merge_min_spp;   // TMA kernel: planes with at least this many statistics slots are merged by the whole group
 };
 
 __device__ __forceinline__ int64_t src_plane(const int* map, int64_t plane) {
@@ -517,10 +520,102 @@ __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int
     kind = 1; plane = (P - Lm) + t / A; chunk = (int)(t % A);
 }
 
+// Plane merge by a whole consumer group (128 threads), used by the TMA kernel's MERGE items.  A plane of
+// 1024x2048 has 2048 statistics slots; folded by one warp in two dependent passes that was ~64 serialized
+// round trips per pass (2.25 TB/s forward at that plane size).  Here thread t takes slots t, t+128, ... with
+// all of its loads in flight at once, folds them with Chan's update in fp64 (no common shift needed, so a
+// single pass), and the 128 partials are merged by a fixed shuffle tree + a fixed 4-warp order: one memory
+// round trip per plane, bit-reproducible.
+struct MomD {
+    double n, mc, m2c, ms, m2s;
+};
+__device__ __forceinline__ MomD momd_merge(const MomD& a, const MomD& b) {
+    MomD r;
+    r.n = a.n + b.n;
+    if (r.n == 0.0) { r.mc = r.m2c = r.ms = r.m2s = 0.0; return r; }
+    const double w = b.n / r.n, k = a.n * w;
+    const double dc = b.mc - a.mc, ds = b.ms - a.ms;
+    r.mc = a.mc + dc * w;
+    r.ms = a.ms + ds * w;
+    r.m2c = a.m2c + b.m2c + dc * dc * k;
+    r.m2s = a.m2s + b.m2s + ds * ds * k;
+    return r;
+}
+constexpr int kMergeSlotsPerThread = 8;    // loads in flight per thread (128 threads x 8 = 1024 slots per round)
+__device__ __noinline__ void merge_plane_coef_group(const AdainParams& p, int64_t plane, int gt, int barrier_id,
+                                                       double (*scratch)[5]) {
+    const float4* slots = p.part + plane * p.spp;
+    MomD acc = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k0 = gt; k0 < p.spp; k0 += kTmaGroupThreads * kMergeSlotsPerThread) {
+        float4 v[kMergeSlotsPerThread];
+#pragma unroll
+        for (int u = 0; u < kMergeSlotsPerThread; ++u) {
+            const int k = k0 + u * kTmaGroupThreads;
+            if (k < p.spp) v[u] = ld_slot(slots + k);
+        }
+#pragma unroll
+        for (int u = 0; u < kMergeSlotsPerThread; ++u) {
+            const int k = k0 + u * kTmaGroupThreads;
+            if (k < p.spp) {
+                if (!slot_valid(v[u])) {   // straggling statistics item: wait for it
+                    const uint64_t t0 = global_timer_ns();
+                    do {
+                        __nanosleep(40);
+                        v[u] = ld_slot(slots + k);
+                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                    } while (!slot_valid(v[u]));
+                }
+                const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+                const MomD b = {(double)(rem < p.slot_elems ? rem : p.slot_elems), (double)v[u].x, (double)v[u].y,
+                                (double)v[u].z, (double)v[u].w};
+                acc = momd_merge(acc, b);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        MomD other;
+        other.n = __shfl_xor_sync(0xffffffffu, acc.n, o);
+        other.mc = __shfl_xor_sync(0xffffffffu, acc.mc, o);
+        other.m2c = __shfl_xor_sync(0xffffffffu, acc.m2c, o);
+        other.ms = __shfl_xor_sync(0xffffffffu, acc.ms, o);
+        other.m2s = __shfl_xor_sync(0xffffffffu, acc.m2s, o);
+        // the lower lane of a pair is always the left operand: both lanes compute the same value
+        acc = ((gt & 31) & o) ? momd_merge(other, acc) : momd_merge(acc, other);
+    }
+    const int gw = gt >> 5;
+    if ((gt & 31) == 0) {
+        scratch[gw][0] = acc.n; scratch[gw][1] = acc.mc; scratch[gw][2] = acc.m2c; scratch[gw][3] = acc.ms; scratch[gw][4] = acc.m2s;
+    }
+    named_bar_sync((uint32_t)barrier_id, kTmaGroupThreads);
+    if (gt == 0) {
+        MomD t = {scratch[0][0], scratch[0][1], scratch[0][2], scratch[0][3], scratch[0][4]};
+#pragma unroll
+        for (int w = 1; w < kTmaGroupWarps; ++w) {
+            const MomD b = {scratch[w][0], scratch[w][1], scratch[w][2], scratch[w][3], scratch[w][4]};
+            t = momd_merge(t, b);
+        }
+        const double denom = (double)p.hw - 1.0;
+        const float mu_hi = (float)t.mc;
+        const float mu_lo = (float)(t.mc - (double)mu_hi);
+        const float sd_c = (float)sqrt(t.m2c / denom + (double)p.eps);
+        float mu_s = 0.f, sd_s = 1.f;
+        if (p.style != nullptr) {
+            mu_s = (float)t.ms;
+            sd_s = (float)sqrt(t.m2s / denom + (double)p.eps);
+        }
+        st_slot(&p.coef[plane], make_float4(mu_hi, sd_s / sd_c, mu_s, mu_lo));
+        if (p.saved) reinterpret_cast<float4*>(p.saved)[plane] = make_float4(mu_hi, sd_c, mu_s, sd_s);
+    }
+    named_bar_sync((uint32_t)barrier_id, kTmaGroupThreads);   // scratch is reused by the group's next merge item
+}
+
 // STAGES == number of consumer groups: group g owns stage g for the whole kernel, so the uses of a
 // stage are consumed in order by one group and the single-bit mbarrier parity can never alias (a group
 // that ran two phases ahead of a shared stage would pass the parity wait on stale data).
-template <int STAGES>
+// GROUP_MERGE is a separate instantiation so that the small-plane kernel (the benchmark's) carries neither the
+// call nor its register/barrier footprint: with a run-time switch the 512x512 path lost 10 % (5.66 vs 6.3 TB/s).
+template <int STAGES, bool GROUP_MERGE>
 __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_kernel(AdainParams p) {
     constexpr int kTmaGroups = STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -529,6 +624,7 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
     uint64_t* full = reinterpret_cast<uint64_t*>(desc + STAGES);
     uint64_t* empty = full + STAGES;
     DecodedItem* dec = reinterpret_cast<DecodedItem*>(empty + STAGES);
+    __shared__ double merge_scratch[GROUP_MERGE ? STAGES : 1][kTmaGroupWarps][5];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -723,7 +819,10 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
             // ---------------- merge: statistics slots of one plane -> coefficient slot
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
-            if (gw == 0) merge_plane_coef(p, plane, lane);
+            // few slots (512x512 planes: 256): one warp folds them while the other three go on to the next item;
+            // many slots (1024x2048: 2048): the whole group takes one round trip instead of 2 x 64 serialized ones
+            if constexpr (GROUP_MERGE) merge_plane_coef_group(p, plane, gw * 32 + lane, 1 + group, merge_scratch[group]);
+            else if (gw == 0) merge_plane_coef(p, plane, lane);
         }
     }
 }
@@ -1049,18 +1148,27 @@ int launch_pipe_variant(const AdainParams& p, cudaStream_t stream) {
     return RPST_OK;
 }
 
+template <int STAGES, bool GROUP_MERGE>
+int launch_tma_variant2(const AdainParams& p, cudaStream_t stream);
+
 template <int STAGES>
 int launch_tma_variant(const AdainParams& p, cudaStream_t stream) {
+    return (!p.stats_only && p.spp >= p.group_merge_min_spp) ? launch_tma_variant2<STAGES, true>(p, stream)
+                                                             : launch_tma_variant2<STAGES, false>(p, stream);
+}
+
+template <int STAGES, bool GROUP_MERGE>
+int launch_tma_variant2(const AdainParams& p, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * 2 * kItemElems * sizeof(float) + STAGES * sizeof(StageDesc) +
                             2 * STAGES * sizeof(uint64_t) + kTicketBatch * sizeof(DecodedItem);
     static bool configured = false;
     if (!configured) {
-        RPST_CUDA(cudaFuncSetAttribute(adain_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(adain_tma_kernel<STAGES, GROUP_MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int64_t grid = sm_count();
     if (grid > (int64_t)p.total_items) grid = p.total_items;
-    adain_tma_kernel<STAGES><<<(int)grid, 32 + STAGES * kTmaGroupThreads, smem, stream>>>(p);
+    adain_tma_kernel<STAGES, GROUP_MERGE><<<(int)grid, 32 + STAGES * kTmaGroupThreads, smem, stream>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
@@ -1076,7 +1184,11 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     char* base = static_cast<char*>(ws);
     p.ipp = (int)((p.hw + kItemElems - 1) / kItemElems);
     const int64_t plane_bytes = p.hw * (int64_t)sizeof(float);
-    int64_t lag = (g_tuning.lag_bytes + plane_bytes - 1) / plane_bytes;
+    // planes of >= 4 MiB: the statistics -> merge -> apply chain (>= 3 dependent global round trips of ~4.5 us
+    // each under load) no longer fits the ~32 MiB L2 window, and a short lag stalls the apply items instead;
+    // measured at 1x256x1024x2048: 32 MiB 3.03 TB/s, 64 MiB 4.92, 128 MiB 5.22 (tools/big_plane_sweep.py)
+    const int64_t lag_bytes = plane_bytes >= (4ll << 20) ? g_tuning.big_lag_bytes : g_tuning.lag_bytes;
+    int64_t lag = (lag_bytes + plane_bytes - 1) / plane_bytes;
     if (lag < 3) lag = 3;
     p.lag = (int)(lag < p.planes ? lag : p.planes);
     const bool use_tma = VEC == 4 && g_tuning.path == 0;
@@ -1174,6 +1286,7 @@ int launch_bwd(BwdParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
 int run_adain(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (p.planes == 0 || p.hw == 0) return RPST_OK;
     p.hints = (int)g_tuning.hints;
+    p.group_merge_min_spp = (int)g_tuning.group_merge_min_spp;
     bool vec = (p.hw % 4 == 0) && aligned16(p.content) && (!p.style || aligned16(p.style)) &&
                (!p.prev || aligned16(p.prev)) && (!p.out || (aligned16(p.out) && p.out_batch_stride % 4 == 0));
     if (vec) {
@@ -1189,6 +1302,7 @@ int run_adain(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
 int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     int64_t* slot = nullptr;
     if (!strcmp(name, "adain_lag_bytes")) slot = &g_tuning.lag_bytes;
+    else if (!strcmp(name, "adain_big_lag_bytes")) slot = &g_tuning.big_lag_bytes;
     else if (!strcmp(name, "adain_hints")) slot = &g_tuning.hints;
     else if (!strcmp(name, "adain_ctas_per_sm")) slot = &g_tuning.ctas_per_sm;
     else if (!strcmp(name, "adain_path")) slot = &g_tuning.path;
@@ -1197,6 +1311,7 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     else if (!strcmp(name, "seg_flush")) slot = &g_tuning.seg_flush;
     else if (!strcmp(name, "seg_groups")) slot = &g_tuning.seg_groups;
     else if (!strcmp(name, "adain_twin_apply")) slot = &g_tuning.twin_apply;
+    else if (!strcmp(name, "adain_group_merge_min_spp")) slot = &g_tuning.group_merge_min_spp;
     if (!slot) return 0;
     if (set) *slot = v;
     if (out) *out = *slot;

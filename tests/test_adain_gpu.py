@@ -228,3 +228,42 @@ def test_mapped_autograd_matches_gather(rpst):
     mu_s, sd_s = sp.mean((2, 3), keepdim=True), (sp.var((2, 3), keepdim=True) + 1e-5).sqrt()
     (((cp - mu_c) / sd_c * sd_s + mu_s) * w.double()).sum().backward()
     assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4
+
+
+def test_random_shapes_and_misaligned_views(rpst):
+    """Seeded fuzz over the dispatch space: tiny / ragged / multi-chunk planes, pointers that are only 4-byte
+    aligned (views at an element offset -> scalar kernels), odd chunk tails on the TMA path (twin apply items
+    with an odd number of chunks), blend and plain, against the fp64 oracle."""
+    rng = torch.Generator().manual_seed(1234)
+    hws = [(1, 2), (3, 5), (17, 19), (64, 64), (100, 164), (128, 129), (160, 160), (192, 256), (257, 255), (384, 300)]
+    for i, (h, w) in enumerate(hws):
+        n = int(torch.randint(1, 3, (1,), generator=rng))
+        ch = int(torch.randint(1, 6, (1,), generator=rng))
+        numel = n * ch * h * w
+        for offset in (0, 1):
+            base_c = torch.randn(numel + 4, generator=rng) * 1.5 + 0.3
+            base_s = torch.randn(numel + 4, generator=rng) * 0.7 - 0.2
+            base_p = torch.randn(numel + 4, generator=rng)
+            cg, sg, pg = (b.cuda()[offset:offset + numel].view(n, ch, h, w) for b in (base_c, base_s, base_p))
+            c, s, p = (b[offset:offset + numel].view(n, ch, h, w) for b in (base_c, base_s, base_p))
+            assert cg.is_contiguous() and (cg.data_ptr() % 16 != 0) == (offset == 1)
+            want = R.adain(c, s, dtype=torch.float64)
+            tol = 1e-5 if h * w < 8 else TIGHT
+            assert R.rel_l2(rpst.adaptive_instance_normalization(cg, sg), want) < tol, (h, w, offset)
+            assert R.rel_l2(rpst.adain_blend(pg, cg, sg), want + p.double()) < tol, (h, w, offset)
+            assert R.rel_l2(rpst.mean_variance_norm(cg), R.mean_variance_norm(c, dtype=torch.float64)) < tol, (h, w, offset)
+            mu, sd = rpst.calc_mean_std(cg)
+            wmu, wsd = R.plane_stats(c, dtype=torch.float64)
+            assert R.rel_l2(mu, wmu) < tol and R.rel_l2(sd, wsd) < tol
+
+
+def test_twin_apply_matches_single_chunk_items(rpst):
+    """The twin-chunk apply items (no prev) must give the single-chunk result bit for bit."""
+    c, s = R.synth_features((2, 3, 300, 300), cfg=60)    # 90000 px = 21.97 chunks: odd tail, partial last chunk
+    cg, sg = c.cuda(), s.cuda()
+    rpst.set_tuning("adain_twin_apply", 0)
+    a = rpst.adaptive_instance_normalization(cg, sg)
+    rpst.set_tuning("adain_twin_apply", 1)
+    b = rpst.adaptive_instance_normalization(cg, sg)
+    assert torch.equal(a, b)
+    assert R.rel_l2(b, R.adain(c, s, dtype=torch.float64)) < TIGHT

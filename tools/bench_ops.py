@@ -66,6 +66,27 @@ def bench_bwd():
     emit(op="adain backward 8x256x512x512", ms=t, GBs=5 * E / t / 1e6, frac_of_peak=5 * E / t / 1e6 / PEAK_GBS)
 
 
+def bench_train5():
+    """config #5 training transform: AdaIN forward + backward on a Cityscapes-sized level (1x256x1024x2048)."""
+    shape = (1, 256, 1024, 2048)
+    c, s = R.synth_features(shape, cfg=5, device=dev)
+    c.requires_grad_(); s.requires_grad_()
+    g = torch.randn(shape, device=dev)
+
+    def step():
+        out = rpst.adaptive_instance_normalization(c, s)
+        return torch.autograd.grad(out, (c, s), g)
+    t = timeit(step, 5)
+    E = c.numel() * 4
+    out = rpst.adaptive_instance_normalization(c, s)
+    tb = timeit(lambda: torch.autograd.grad(out, (c, s), g, retain_graph=True), 5)
+    with torch.no_grad():
+        tf = timeit(lambda: rpst.adaptive_instance_normalization(c, s), 5)
+    emit(op="adain fwd+bwd config#5 level 1x256x1024x2048", ms=t, GBs=8 * E / t / 1e6, frac_of_peak=8 * E / t / 1e6 / PEAK_GBS,
+         fwd_ms=tf, fwd_GBs=3 * E / tf / 1e6, bwd_ms=tb, bwd_GBs=5 * E / tb / 1e6,
+         note="3E forward + 5E backward algorithmic bytes")
+
+
 def bench_seg():
     n, ch, h, w = 1, 256, 1024, 2048
     c, s = R.synth_features((n, ch, h, w), cfg=5, device=dev)
@@ -194,7 +215,7 @@ def bench_losses():
              content_norm_bwd_ms=tb, bwd_GBs=3 * E / tb / 1e6)
 
 
-ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "mrf": bench_mrf}
+ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "train5": bench_train5, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "mrf": bench_mrf}
 for name in (sys.argv[1:] or list(ALL)):
     try:
         ALL[name]()
