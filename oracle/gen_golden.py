@@ -162,6 +162,25 @@ def gen_losses(net):
           content_plain=sanet.SAModel.calc_content_loss(stub, x, y))
 
 
+def gen_channel_maps(net):
+    """shuffle / sort_by_weights are methods that read only config-derived attributes and the encoders'
+    stored attention maps: call them unbound on a stub."""
+    import types
+    adain_rp = sys.modules["network.adain_rp"]
+    base = sys.modules["network.base"]
+    c, s = synth_features((2, 8, 6, 5), cfg=9)
+    g = torch.Generator().manual_seed(99)
+    att = torch.rand(2, 8, 1, 1, generator=g)          # tie-free by construction (checked below)
+    assert att.reshape(2, 8).sort(dim=1).values.diff(dim=1).abs().min() > 1e-4
+    stub = types.SimpleNamespace(_shuffle_layers=10, rp_shared_encoder=[types.SimpleNamespace(attention_map=att)])
+    shuffled = adain_rp.MultiScaleAdaINRPNet.shuffle(stub, c, 0)
+    sorted_c = adain_rp.MultiScaleAdaINRPNet.sort_by_weights(stub, [c])[0]
+    sorted_s = adain_rp.MultiScaleAdaINRPNet.sort_by_weights(stub, [s])[0]
+    _save("channel_maps", content=c, style=s, attention=att, shuffled=shuffled, sorted_content=sorted_c,
+          adain_sorted=base.adaptive_instance_normalization(sorted_c, sorted_s),
+          adain_shuffled=base.adaptive_instance_normalization(shuffled, adain_rp.MultiScaleAdaINRPNet.shuffle(stub, s, 0)))
+
+
 def main():
     net = load_reference()
     with torch.no_grad():
@@ -172,6 +191,7 @@ def main():
         gen_mrf(net)
         gen_se(net)
         gen_losses(net)
+        gen_channel_maps(net)
 
 
 if __name__ == "__main__":

@@ -267,3 +267,15 @@ def test_twin_apply_matches_single_chunk_items(rpst):
     b = rpst.adaptive_instance_normalization(cg, sg)
     assert torch.equal(a, b)
     assert R.rel_l2(b, R.adain(c, s, dtype=torch.float64)) < TIGHT
+
+
+def test_golden_channel_maps(rpst, golden):
+    """shuffle / sort_by_weights outputs of the reference's own methods (tests/golden/channel_maps.npz)."""
+    g = golden("channel_maps")
+    c, s, att = g["content"].cuda(), g["style"].cuda(), g["attention"].cuda()
+    sm = rpst.sort_map(att)
+    assert R.rel_l2(rpst.adain_mapped(c, s, sm, sm), g["adain_sorted"]) < TIGHT
+    hm = rpst.shuffle_map(2, 8, 4, "cuda")
+    assert R.rel_l2(rpst.adain_mapped(c, s, hm, hm), g["adain_shuffled"]) < TIGHT
+    assert torch.equal(c.flatten(0, 1)[hm.long()].view_as(c).cpu(), g["shuffled"])
+    assert torch.equal(c.flatten(0, 1)[sm.long()].view_as(c).cpu(), g["sorted_content"])
