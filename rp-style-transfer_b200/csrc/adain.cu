@@ -1161,7 +1161,8 @@ template <int STAGES, bool GROUP_MERGE>
 int launch_tma_variant2(const AdainParams& p, cudaStream_t stream) {
     constexpr size_t smem = (size_t)STAGES * 2 * kItemElems * sizeof(float) + STAGES * sizeof(StageDesc) +
                             2 * STAGES * sizeof(uint64_t) + kTicketBatch * sizeof(DecodedItem);
-    static bool configured = false;
+    static PerDeviceFlag configured_on;
+    bool& configured = configured_on.get();
     if (!configured) {
         RPST_CUDA(cudaFuncSetAttribute(adain_tma_kernel<STAGES, GROUP_MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;

@@ -30,6 +30,17 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int sm_count();
 
+// cudaFuncSetAttribute is per device: a process that drives several GPUs (one host thread each, SURVEY.md §8b
+// threading contract) must configure every kernel once PER DEVICE, not once per process.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool& get() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+        return done[d];
+    }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

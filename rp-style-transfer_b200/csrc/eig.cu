@@ -300,7 +300,8 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
     cfg.numAttrs = 1;
 #define RPST_EIG_CASE(R)                                                                                           \
     case R: {                                                                                                      \
-        static bool configured = false;                                                                            \
+        static PerDeviceFlag configured_on;                                                                        \
+        bool& configured = configured_on.get();                                                                    \
         if (!configured) {                                                                                         \
             RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                            (int)smem));                                                            \

@@ -372,7 +372,8 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
     p.n_tiles128 = (int)((n + 127) / 128);
     p.passes = passes; p.alpha = alpha; p.row_add = row_add; p.col_add = col_add;
     constexpr size_t smem = kGemmSmemBytes;
-    static bool configured = false;
+    static PerDeviceFlag configured_on;
+    bool& configured = configured_on.get();
     if (!configured) {
         RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;

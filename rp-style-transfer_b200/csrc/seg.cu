@@ -996,7 +996,8 @@ int launch_seg_tma(const SegTmaParams& p, cudaStream_t st) {
     constexpr size_t smem = G * (kSegDepth * stage + cache) + G * kSegDepth * sizeof(SegDesc) + 2 * G * kSegDepth * sizeof(uint64_t) +
                             2 * kSegMailbox * sizeof(uint64_t) + kSegMailbox * sizeof(int64_t) +
                             kSegTicketBatch * sizeof(SegDecoded);
-    static bool configured = false;
+    static PerDeviceFlag configured_on;
+    bool& configured = configured_on.get();
     if (!configured) {
         RPST_CUDA(cudaFuncSetAttribute(seg_tma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
