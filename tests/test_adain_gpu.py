@@ -279,3 +279,32 @@ def test_golden_channel_maps(rpst, golden):
     assert R.rel_l2(rpst.adain_mapped(c, s, hm, hm), g["adain_shuffled"]) < TIGHT
     assert torch.equal(c.flatten(0, 1)[hm.long()].view_as(c).cpu(), g["shuffled"])
     assert torch.equal(c.flatten(0, 1)[sm.long()].view_as(c).cpu(), g["sorted_content"])
+
+
+def test_cuda_graph_capture_and_replay(rpst):
+    """The C-ABI calls only enqueue stream work (memsets + kernels, no host synchronisation, no allocation of
+    their own), so a whole multiscale transform step can be captured once and replayed on new data."""
+    levels = [(2, 4, 160, 160), (2, 8, 160, 160), (2, 16, 64, 64)]      # TMA kernel x2, direct kernel (top level)
+    cs = [torch.zeros(sh, device="cuda") for sh in levels]
+    ss = [torch.zeros(sh, device="cuda") for sh in levels]
+    ps = [torch.zeros(sh, device="cuda") for sh in levels[:-1]]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        rpst.multiscale_transform(cs, ss, ps)                             # warm-up outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = rpst.multiscale_transform(cs, ss, ps)
+    for seed in (1, 2):
+        g = torch.Generator().manual_seed(seed)
+        hc = [torch.randn(sh, generator=g) + 0.3 for sh in levels]
+        hs = [torch.randn(sh, generator=g) * 2 - 0.5 for sh in levels]
+        hp = [torch.randn(sh, generator=g) for sh in levels[:-1]]
+        for d, h in zip(cs + ss + ps, hc + hs + hp):
+            d.copy_(h)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = R.multiscale_transform(hc, hs, hp, dtype=torch.float64)
+        for o, w in zip(outs, want):
+            assert R.rel_l2(o, w) < TIGHT
