@@ -174,3 +174,23 @@ def test_sample_groups_match_per_sample_launches(rpst, monkeypatch):
     for other in results[1:]:
         for a, b_ in zip(results[0], other):
             assert torch.equal(a, b_)
+
+
+def test_long_rows_take_the_register_resident_row_kernels(rpst):
+    """L = 8192 (rows of 8192 columns -> attn_rows_reg_kernel / attn_bwd_rows_reg_kernel), forward and
+    backward against fp64 torch ops evaluated on the GPU (the fp64 formula of network/sanet.py:85-94)."""
+    b, c, hc, wc = 1, 64, 64, 128
+    g = torch.Generator().manual_seed(8192)
+    f, k, v, w = (torch.randn(b, c, hc, wc, generator=g).cuda() * sc for sc in (0.4, 0.4, 1.0, 1.0))
+    fd, kd, vd = (t.double().requires_grad_() for t in (f, k, v))
+    S = torch.softmax(torch.bmm(fd.reshape(b, c, -1).transpose(1, 2), kd.reshape(b, c, -1)), dim=-1)
+    O = torch.bmm(vd.reshape(b, c, -1), S.transpose(1, 2)).reshape(b, c, hc, wc)
+    (O * w.double()).sum().backward()
+    fg, kg, vg = (t.clone().requires_grad_() for t in (f, k, v))
+    out, attn = rpst.attention_core(fg, kg, vg, return_attn=True)
+    assert R.rel_l2(out, O.detach()) < TOL32
+    assert float((attn.sum(-1) - 1).abs().max()) < 1e-4
+    assert R.rel_l2(attn, S.detach()) < TOL32
+    (out * w).sum().backward()
+    for got, want in ((vg.grad, vd.grad), (fg.grad, fd.grad), (kg.grad, kd.grad)):
+        assert R.rel_l2(got, want) < TOL32, R.rel_l2(got, want)
