@@ -181,6 +181,69 @@ def gen_channel_maps(net):
           adain_shuffled=base.adaptive_instance_normalization(shuffled, adain_rp.MultiScaleAdaINRPNet.shuffle(stub, s, 0)))
 
 
+def decode_stub(kind, seed=0):
+    """A module with exactly the attributes the reference's decode()/test() methods touch; shared by the
+    generator (reference methods bound to it) and tests/test_decode_gpu.py (rpst mirrors bound to it)."""
+    import types
+    torch.manual_seed(seed)
+    m = torch.nn.Module()
+    if kind == "multiscale":          # features shallow -> deep: 4, 8, 16 channels (network/adain_rp.py:286-302)
+        m.rp_decoder = torch.nn.ModuleList([torch.nn.Conv2d(16, 8, 3, padding=1), torch.nn.Conv2d(8, 4, 3, padding=1),
+                                            torch.nn.Conv2d(4, 3, 3, padding=1)])
+        m.rp_shared_encoder = [types.SimpleNamespace(attention_map=None) for _ in range(3)]
+        m._sort, m._shuffle, m._shuffle_layers = False, False, 1
+        m.config = {"use_mask": False}
+    elif kind == "ldms":              # constant width 8 (network/adain_rp.py:538-553)
+        for i in range(3):
+            setattr(m, f"rp_dec{i}", torch.nn.Conv2d(8, 8 if i < 2 else 3, 3, padding=1))
+        m.stylized_layers = 3
+    elif kind == "ldcat":             # concat doubles the width (network/adain_rp.py:780-799)
+        m.rp_dec0 = torch.nn.Conv2d(8, 8, 3, padding=1)
+        m.rp_dec1 = torch.nn.Conv2d(16, 8, 3, padding=1)
+        m.rp_dec2 = torch.nn.Conv2d(16, 3, 3, padding=1)
+    return m
+
+
+def decode_inputs(kind):
+    chans = [4, 8, 16] if kind == "multiscale" else [8, 8, 8]
+    cs, ss = [], []
+    for i, ch in enumerate(chans):
+        c, s = synth_features((2, ch, 12, 10), cfg=40 + i, signed=True)
+        cs.append(c); ss.append(s)
+    g = torch.Generator().manual_seed(4242)
+    atts = [torch.rand(2, ch, 1, 1, generator=g) for ch in chans]
+    return cs, ss, atts
+
+
+def gen_decode(net):
+    """The reference's own decode()/test() methods, bound to the stub modules above."""
+    import types
+    adain_rp = sys.modules["network.adain_rp"]
+    arrays = {}
+    for kind, cls in (("multiscale", adain_rp.MultiScaleAdaINRPNet), ("ldms", adain_rp.LDMSAdaINRPNet),
+                      ("ldcat", adain_rp.LDMSAdaINRPNet4)):
+        m = decode_stub(kind)
+        cs, ss, atts = decode_inputs(kind)
+        arrays.update({f"{kind}.{k}": v for k, v in m.state_dict().items()})
+        arrays[f"{kind}.out"] = cls.decode(m, cs, ss)
+        if kind == "multiscale":
+            for enc, a in zip(m.rp_shared_encoder, atts):
+                enc.attention_map = a
+            m._sort = True
+            m.sort_by_weights = types.MethodType(cls.sort_by_weights, m)
+            arrays["multiscale.out_sorted"] = cls.decode(m, cs, ss)
+            # test(): shuffle levels <= _shuffle_layers, then decode (sort still on)
+            m._shuffle = True
+            m.shuffle = types.MethodType(cls.shuffle, m)
+            m.decode = types.MethodType(cls.decode, m)
+            feats = {"c": cs, "s": ss}
+            m.encode_rp_intermediate = lambda x: feats[x]
+            arrays["multiscale.test_out"] = cls.test(m, "c", "s")
+            for i, a in enumerate(atts):
+                arrays[f"multiscale.att{i}"] = a
+    _save("decode", **arrays)
+
+
 def main():
     net = load_reference()
     with torch.no_grad():
@@ -192,6 +255,7 @@ def main():
         gen_se(net)
         gen_losses(net)
         gen_channel_maps(net)
+        gen_decode(net)
 
 
 if __name__ == "__main__":
