@@ -244,6 +244,26 @@ def gen_decode(net):
     _save("decode", **arrays)
 
 
+def gen_sanet_grad(net):
+    """Autograd through the reference SANet module (what SAModel.forward trains, network/sanet.py:253-276):
+    gradients of the inputs and of every parameter for a weighted-sum loss."""
+    sanet = sys.modules["network.sanet"]
+    torch.manual_seed(7)
+    m = sanet.SANet(16)
+    c, s = synth_features((2, 16, 8, 8), cfg=12, signed=True)
+    g = torch.Generator().manual_seed(13)
+    w = torch.randn(2, 16, 8, 8, generator=g)
+    c.requires_grad_(); s.requires_grad_()
+    with torch.enable_grad():
+        out = m(c, s)
+        (out * w).sum().backward()
+    arrays = {"content": c.detach(), "style": s.detach(), "w": w, "out": out.detach(),
+              "grad_content": c.grad, "grad_style": s.grad}
+    arrays.update({"param." + k: v.detach() for k, v in m.state_dict().items()})
+    arrays.update({"grad." + k: p.grad for k, p in m.named_parameters()})
+    _save("sanet_grad", **arrays)
+
+
 def main():
     net = load_reference()
     with torch.no_grad():
@@ -256,6 +276,7 @@ def main():
         gen_losses(net)
         gen_channel_maps(net)
         gen_decode(net)
+    gen_sanet_grad(net)
 
 
 if __name__ == "__main__":

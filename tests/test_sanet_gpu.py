@@ -194,3 +194,23 @@ def test_long_rows_take_the_register_resident_row_kernels(rpst):
     (out * w).sum().backward()
     for got, want in ((vg.grad, vd.grad), (fg.grad, fd.grad), (kg.grad, kd.grad)):
         assert R.rel_l2(got, want) < TOL32, R.rel_l2(got, want)
+
+
+def test_golden_sanet_gradients(rpst, golden):
+    """Input and parameter gradients the REFERENCE SANet module produced through autograd on CPU
+    (tests/golden/sanet_grad.npz) against the rpst module (rpst_sanet_attn_bwd + AdaIN backward)."""
+    g = golden("sanet_grad")
+    m = rpst.SANet(16).cuda()
+    m.load_state_dict({k[6:]: v for k, v in g.items() if k.startswith("param.")})
+    c, s = g["content"].cuda().requires_grad_(), g["style"].cuda().requires_grad_()
+    out = m(c, s)
+    assert R.rel_l2(out, g["out"]) < TOL32
+    (out * g["w"].cuda()).sum().backward()
+    assert R.rel_l2(c.grad, g["grad_content"]) < TOL32 and R.rel_l2(s.grad, g["grad_style"]) < TOL32
+    scale = float(g["grad.g.weight"].abs().max())
+    for name, p in m.named_parameters():
+        want = g["grad." + name]
+        if name == "g.bias":      # exactly zero in exact arithmetic (softmax shift invariance): compare absolutely
+            assert float((p.grad.cpu() - want).abs().max()) < 1e-3 * scale
+            continue
+        assert R.rel_l2(p.grad, want) < TOL32, (name, R.rel_l2(p.grad, want))
