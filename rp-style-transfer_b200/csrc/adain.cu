@@ -837,12 +837,14 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(AdainParams p) {
     const float4* slots = p.part + plane * p.spp;
     const float k0 = __ldcg(slots).x;
     float d = 0.f;
+#pragma unroll 8   // independent loads: keep 8 in flight (2048 slots per plane at 1024x2048)
     for (int k = lane; k < p.spp; k += 32) {
         const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
         d = fmaf((float)(rem < p.slot_elems ? rem : p.slot_elems), __ldcg(slots + k).x - k0, d);
     }
     d = warp_sum(d) / (float)p.hw;
     float m2 = 0.f;
+#pragma unroll 8
     for (int k = lane; k < p.spp; k += 32) {
         const float4 v = __ldcg(slots + k);
         const int64_t rem = p.hw - (int64_t)k * p.slot_elems;

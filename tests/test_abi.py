@@ -91,3 +91,20 @@ def test_product_path_has_no_cpu_fallback():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", text, flags=re.S), f"{f} references the oracle"
+
+
+def test_library_is_sm_100a_with_tcgen05_and_tma_sass():
+    """The shipped library is built for sm_100a only and its SASS carries the Blackwell instructions the design
+    claims: tcgen05.mma (UTCHMMA), tcgen05.ld (LDTM), tcgen05.commit (UTCBAR), cp.async.bulk / TMA (UBLKCP)
+    and mbarriers (SYNCS) — B200_PROFILING.md's mnemonics."""
+    import shutil
+    import rpst
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", rpst._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", rpst._lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "SYNCS"):
+        assert mnemonic in sass, mnemonic
