@@ -102,7 +102,7 @@ __device__ __forceinline__ double rotate_pair(double* x, double* y, int lane) {
 }
 
 template <int ROWS>   // padded order np = 32*ROWS, cluster of ROWS CTAs
-__global__ void __launch_bounds__(kEigThreads, 1) jacobi_cluster_kernel(EigParams p) {
+__global__ void __launch_bounds__(kEigThreads, 2) jacobi_cluster_kernel(EigParams p) {
     extern __shared__ __align__(16) unsigned char eig_smem[];
     double* cols = reinterpret_cast<double*>(eig_smem);            // [32][np]
     double* conv = cols + (size_t)kCtaCols * p.np;                 // [2]: per-sweep local maxima (double buffered)

@@ -33,6 +33,7 @@ struct PackParams {
     int64_t row_tiles, k_tiles;
     // batch (blockIdx.y): element stride of x, byte stride of the tile buffers, element stride of scale/shift
     int64_t x_batch, tile_batch_bytes, vec_batch;
+    int vec_k;                  // stride_k == 1, x and every row start 16-byte aligned: 128-bit source loads
 };
 
 // One thread produces one 16-byte chunk (8 consecutive k of one row).  Threads of a warp walk the
@@ -56,12 +57,18 @@ __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
         const float sh = (p.row_shift && row < p.rows) ? __ldg(p.row_shift + row) : 0.f;
         __align__(16) __nv_bfloat16 h[8];
         __align__(16) __nv_bfloat16 l[8];
+        float v[8];
+        if (p.vec_k && row < p.rows && k0 + 8 <= p.k) {   // K-major source, 16-byte aligned rows: two 128-bit loads
+            const float4* src = reinterpret_cast<const float4*>(p.x + row * p.stride_r + k0);
+            const float4 a = __ldg(src), b = __ldg(src + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float v = 0.f;
-            if (row < p.rows && k0 + e < p.k) v = (__ldg(p.x + row * p.stride_r + (k0 + e) * p.stride_k) - sh) * sc;
-            split_bf16(v, h[e], l[e]);
+            for (int e = 0; e < 8; ++e)
+                v[e] = (row < p.rows && k0 + e < p.k) ? __ldg(p.x + row * p.stride_r + (k0 + e) * p.stride_k) : sh;
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16((row < p.rows && k0 + e < p.k) ? (v[e] - sh) * sc : 0.f, h[e], l[e]);
         const uint32_t off = tile_chunk_offset(r, c);
         *reinterpret_cast<uint4*>(hi_tile + off) = *reinterpret_cast<const uint4*>(h);
         if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = *reinterpret_cast<const uint4*>(l);
@@ -299,6 +306,7 @@ int pack_operand_batched(const float* x, int64_t rows, int64_t k, int64_t stride
                          int64_t tile_batch_bytes, int64_t vec_batch, cudaStream_t stream) {
     PackParams p{};
     p.x_batch = x_batch; p.tile_batch_bytes = tile_batch_bytes; p.vec_batch = vec_batch;
+    p.vec_k = (stride_k == 1 && stride_r % 4 == 0 && x_batch % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? 1 : 0;
     p.x = x; p.rows = rows; p.k = k; p.stride_r = stride_r; p.stride_k = stride_k; p.row_scale = row_scale;
     p.row_shift = row_shift;
     p.hi = static_cast<__nv_bfloat16*>(hi);
