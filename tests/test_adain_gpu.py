@@ -308,3 +308,25 @@ def test_cuda_graph_capture_and_replay(rpst):
         want = R.multiscale_transform(hc, hs, hp, dtype=torch.float64)
         for o, w in zip(outs, want):
             assert R.rel_l2(o, w) < TIGHT
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 1024, 2048), (2, 3, 1100, 1000)])
+def test_big_planes_group_merge_kernel(rpst, shape):
+    """Planes >= 4 MiB take the GROUP_MERGE instantiation (whole-group single-pass fp64 merge, 128 MiB lag):
+    plain / blend / mean_variance_norm / statistics saved for the backward pass, incl. a ragged last chunk."""
+    c, s = R.synth_features(shape, cfg=80, signed=True)
+    prev = torch.randn(shape, generator=torch.Generator().manual_seed(81))
+    cg, sg, pg = c.cuda(), s.cuda(), prev.cuda()
+    want = R.adain(c, s, dtype=torch.float64)
+    assert R.rel_l2(rpst.adaptive_instance_normalization(cg, sg), want) < TIGHT
+    assert R.rel_l2(rpst.adain_blend(pg, cg, sg), want + prev.double()) < TIGHT
+    assert R.rel_l2(rpst.mean_variance_norm(cg), R.mean_variance_norm(c, dtype=torch.float64)) < TIGHT
+    # autograd: forward saves (mu_c, sd_c, mu_s, sd_s) from the group merge, backward consumes them
+    w = torch.randn(shape, generator=torch.Generator().manual_seed(82))
+    cd, sd = c[:, :2].double().requires_grad_(), s[:, :2].double().requires_grad_()
+    mu_c, sd_c = cd.mean((2, 3), keepdim=True), (cd.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    mu_s, sd_s = sd.mean((2, 3), keepdim=True), (sd.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    (((cd - mu_c) / sd_c * sd_s + mu_s) * w[:, :2].double()).sum().backward()
+    cr, sr = cg[:, :2].contiguous().requires_grad_(), sg[:, :2].contiguous().requires_grad_()
+    (rpst.adaptive_instance_normalization(cr, sr) * w[:, :2].cuda()).sum().backward()
+    assert R.rel_l2(cr.grad, cd.grad) < 1e-4 and R.rel_l2(sr.grad, sd.grad) < 1e-4
