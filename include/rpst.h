@@ -255,6 +255,19 @@ RPST_API int rpst_sanet_attn_adaptive_fwd(const float* f, const float* g, const 
                                  int64_t ls, int64_t lh, int passes, void* workspace, size_t workspace_bytes,
                                  void* stream);
 
+/* a11 training path: clamped attention with the per-row clamp GIVEN (the clamp MLP f_psi and the cosine
+ * affinity stay in the caller's autograd graph; the L x L work — softmax, clamp, both products and their
+ * backward — is here).  mode 1 'aea': S' = sigmoid(scale (P - clamp_i)); mode 2 'relu': S' = softmax(relu(P -
+ * clamp_i)); P = softmax(f^T g); out = h S'^T.  clamp / grad_clamp [b, lc].  network/sanet.py:41-46,66-71,114-138 */
+RPST_API size_t rpst_sanet_attn_clamped_workspace_bytes(int64_t c, int64_t lc, int64_t ls);
+RPST_API int rpst_sanet_attn_clamped_fwd(const float* f, const float* g, const float* h, const float* clamp, int mode,
+                                float scale, float* out, int64_t b, int64_t c, int64_t lc, int64_t ls,
+                                int passes, void* workspace, size_t workspace_bytes, void* stream);
+RPST_API int rpst_sanet_attn_clamped_bwd(const float* f, const float* g, const float* h, const float* clamp, int mode,
+                                float scale, const float* grad_out, float* grad_f, float* grad_g,
+                                float* grad_h, float* grad_clamp, int64_t b, int64_t c, int64_t lc,
+                                int64_t ls, int passes, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Building blocks shared by the contraction kernels (exposed for tests and for callers that want to
  * keep packed operands around): fp32 matrix -> bf16 hi/lo operand tiles, and D = alpha*A.B^T

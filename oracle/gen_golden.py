@@ -264,6 +264,29 @@ def gen_sanet_grad(net):
     _save("sanet_grad", **arrays)
 
 
+def gen_adaptive_grad(net):
+    """Autograd through the reference AdaptiveSANet (AdaptiveSAModel.forward trains it, network/sanet.py:373-384):
+    input and parameter gradients, both clamp modules."""
+    sanet = sys.modules["network.sanet"]
+    arrays = {}
+    for mode in ("aea", "relu"):
+        torch.manual_seed(21)
+        m = sanet.AdaptiveSANet(16, 64, ada_module=mode)
+        c, s = synth_features((2, 16, 8, 8), cfg=14, signed=True)
+        g = torch.Generator().manual_seed(15)
+        w = torch.randn(2, 16, 8, 8, generator=g)
+        c.requires_grad_(); s.requires_grad_()
+        with torch.enable_grad():
+            out = m(c, s)
+            (out * w).sum().backward()
+        arrays.update({f"{mode}.content": c.detach(), f"{mode}.style": s.detach(), f"{mode}.w": w, f"{mode}.out": out.detach(),
+                       f"{mode}.grad_content": c.grad, f"{mode}.grad_style": s.grad,
+                       f"{mode}.clamp": m.claim_value.detach()})
+        arrays.update({f"{mode}.param." + k: v.detach() for k, v in m.state_dict().items()})
+        arrays.update({f"{mode}.grad." + k: p.grad for k, p in m.named_parameters()})
+    _save("adaptive_grad", **arrays)
+
+
 def main():
     net = load_reference()
     with torch.no_grad():
@@ -277,6 +300,7 @@ def main():
         gen_channel_maps(net)
         gen_decode(net)
     gen_sanet_grad(net)
+    gen_adaptive_grad(net)
 
 
 if __name__ == "__main__":

@@ -54,6 +54,10 @@ SIGNATURES = {
     "rpst_sanet_attn_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, P, c_size_t, P]),
     "rpst_sanet_attn_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_sanet_attn_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
+    "rpst_sanet_attn_clamped_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_sanet_attn_clamped_fwd": (c_int, [P, P, P, P, c_int, c_float, P, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
+    "rpst_sanet_attn_clamped_bwd": (c_int, [P, P, P, P, c_int, c_float, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64,
+                                            c_int, P, c_size_t, P]),
     "rpst_cosine_affinity_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_cosine_affinity": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "rpst_sanet_adaptive_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),

@@ -336,6 +336,67 @@ __global__ void __launch_bounds__(kRowThreads) attn_bwd_rows_reg_kernel(const fl
     }
 }
 
+// Backward of one row of the CLAMPED attention (network/sanet.py:41-46 'aea', :66-71 'relu') fused with the
+// softmax backward.  With U = P - cl (P = softmax row, cl = this row's clamp) and S' the forward result:
+//   'aea' : S' = sigmoid(k U)           dU = dS' * k * S' (1 - S')
+//   'relu': S' = softmax_j(relu(U))     dR = S' o (dS' - sum_j dS' S'),  dU = dR where U > 0 else 0
+//   dcl = -sum_j dU_j ;   dS = P o (dU - sum_j dU P)      (P depends on S through the plain softmax)
+// dS overwrites dS' in fp32 and is emitted as packed operand tiles; dcl goes to grad_clamp[row].
+__global__ void __launch_bounds__(kRowThreads) attn_clamped_bwd_rows_kernel(const float* __restrict__ prob,
+                                                                             const float* __restrict__ sp, float* dp,
+                                                                             const float* __restrict__ clamp,
+                                                                             float* __restrict__ grad_clamp, int mode, float scale,
+                                                                             __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t cols,
+                                                                             int k_tiles) {
+    __shared__ float red[kRowThreads / 32];
+    const int64_t row = blockIdx.x;
+    const float* pr = prob + row * cols;
+    const float* sr = sp + row * cols;
+    float* dr = dp + row * cols;
+    const float cl = __ldg(clamp + row);
+    float delta1 = 0.f;
+    if (mode == 2) {
+        float a = 0.f;
+        for (int64_t j = threadIdx.x; j < cols; j += kRowThreads) a = fmaf(dr[j], sr[j], a);
+        delta1 = block_sum(a, red);
+    }
+    auto d_u = [&](int64_t j) -> float {
+        const float s = sr[j];
+        if (mode == 1) return dr[j] * scale * s * (1.f - s);
+        return pr[j] - cl > 0.f ? s * (dr[j] - delta1) : 0.f;
+    };
+    float a1 = 0.f, a2 = 0.f;
+    for (int64_t j = threadIdx.x; j < cols; j += kRowThreads) {
+        const float du = d_u(j);
+        a1 += du;
+        a2 = fmaf(du, pr[j], a2);
+    }
+    const float sum_du = block_sum(a1, red);
+    const float delta2 = block_sum(a2, red);
+    if (threadIdx.x == 0) grad_clamp[row] = -sum_du;
+    const int64_t chunks = (cols + 7) / 8;
+    const int64_t rb = row / kTileRows;
+    const int r = (int)(row % kTileRows);
+    for (int64_t q = threadIdx.x; q < chunks; q += kRowThreads) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t j = q * 8 + e;
+            y[e] = j < cols ? pr[j] * (d_u(j) - delta2) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (q * 8 + e < cols) dr[q * 8 + e] = y[e];
+        __align__(16) __nv_bfloat16 h[8];
+        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(y[e], h[e], l[e]);
+        const size_t off = (size_t)(rb * k_tiles + (q >> 3)) * kTileBytes + tile_chunk_offset(r, (int)(q & 7));
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(hi) + off) = *reinterpret_cast<const uint4*>(h);
+        if (lo) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(lo) + off) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
 // workspace of the backward pass: the forward's buffers (Q/K/V tiles, S) plus dP and two L x L tile sets
 struct AttnBwdLayout {
     AttnLayout a;            // q: [lc x c] tiles, k: [ls x c], v: [c x ls], s: P (fp32), p: [lc x ls] tiles (dS)
@@ -548,6 +609,107 @@ extern "C" int rpst_sanet_attn_bwd(const float* f, const float* g, const float* 
         if ((rc = pack_operand_batched(dp, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), kb, mat, (int64_t)l.t_b, 0, st))) return rc;
         if ((rc = gemm_packed_batched(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_g + i * c * ls, c, ls, lc, ls,
                                       passes, 1.f, nullptr, nullptr, 1, 0, kb, (int64_t)l.w_b, (int64_t)l.t_b, c * ls, st))) return rc;
+    }
+    return RPST_OK;
+}
+
+// ---- clamped attention with the clamp given (training path of AdaptiveSANet: the clamp MLP and the cosine
+//      affinity stay in the caller's autograd graph, the L x L work is here) --------------------------------
+extern "C" size_t rpst_sanet_attn_clamped_workspace_bytes(int64_t c, int64_t lc, int64_t ls) {
+    if (c <= 0 || lc <= 0 || ls <= 0) return 256;
+    return attn_bwd_layout(c, lc, ls).total + align_up((size_t)lc * ls * sizeof(float), 256);   // + S' (fp32)
+}
+
+extern "C" int rpst_sanet_attn_clamped_fwd(const float* f, const float* g, const float* h, const float* clamp, int mode,
+                                           float scale, float* out, int64_t b, int64_t c, int64_t lc, int64_t ls,
+                                           int passes, void* workspace, size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(b >= 0 && c > 0 && lc > 0 && ls > 0, "sanet_clamped: bad size");
+    if (b == 0) return RPST_OK;
+    RPST_CHECK_ARG(f && g && h && clamp && out, "sanet_clamped: null pointer");
+    RPST_CHECK_ARG(mode == 1 || mode == 2, "sanet_clamped: mode must be 1 ('aea') or 2 ('relu')");
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet_clamped: passes must be 1 or 3");
+    const AttnLayout l = attn_layout(c, lc, ls);
+    if (!workspace || workspace_bytes < l.total) {
+        set_error("sanet_clamped: workspace too small (%zu < %zu bytes)", workspace_bytes, l.total);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet_clamped: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    float* s = reinterpret_cast<float*>(w + l.s);
+    int rc;
+    for (int64_t i = 0; i < b; ++i) {
+        if ((rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l, s, st))) return rc;
+        if ((rc = launch_rows(s, s, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;                       // P
+        if ((rc = launch_rows(s, nullptr, w + l.p_hi, passes == 3 ? w + l.p_lo : nullptr, clamp + i * lc, lc, ls, mode,
+                              scale, st))) return rc;                                                                // S' tiles
+        if ((rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l, out + i * c * lc, st))) return rc;
+    }
+    return RPST_OK;
+}
+
+extern "C" int rpst_sanet_attn_clamped_bwd(const float* f, const float* g, const float* h, const float* clamp, int mode,
+                                           float scale, const float* grad_out, float* grad_f, float* grad_g,
+                                           float* grad_h, float* grad_clamp, int64_t b, int64_t c, int64_t lc,
+                                           int64_t ls, int passes, void* workspace, size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(b >= 0 && c > 0 && lc > 0 && ls > 0, "sanet_clamped_bwd: bad size");
+    if (b == 0) return RPST_OK;
+    RPST_CHECK_ARG(f && g && h && clamp && grad_out && grad_f && grad_g && grad_h && grad_clamp, "sanet_clamped_bwd: null pointer");
+    RPST_CHECK_ARG(mode == 1 || mode == 2, "sanet_clamped_bwd: mode must be 1 ('aea') or 2 ('relu')");
+    RPST_CHECK_ARG(passes == 1 || passes == 3, "sanet_clamped_bwd: passes must be 1 or 3");
+    const size_t need = rpst_sanet_attn_clamped_workspace_bytes(c, lc, ls);
+    if (!workspace || workspace_bytes < need) {
+        set_error("sanet_clamped_bwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet_clamped_bwd: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* w = static_cast<char*>(workspace);
+    const bool x3 = passes == 3;
+    auto lo = [&](size_t off) -> void* { return x3 ? w + off : nullptr; };
+    const AttnBwdLayout l = attn_bwd_layout(c, lc, ls);
+    const AttnLayout& a = l.a;
+    float* prob = reinterpret_cast<float*>(w + a.s);
+    float* dp = reinterpret_cast<float*>(w + l.dp);
+    float* sp = reinterpret_cast<float*>(w + l.total);
+    int rc;
+    for (int64_t i = 0; i < b; ++i) {
+        const float* fi = f + i * c * lc;
+        const float* gi = g + i * c * ls;
+        const float* hi_ = h + i * c * ls;
+        const float* doi = grad_out + i * c * lc;
+        const float* cli = clamp + i * lc;
+        // P and S' = act(P - clamp), both kept in fp32
+        if ((rc = scores(fi, gi, c, lc, ls, passes, w, a, prob, st))) return rc;
+        if ((rc = launch_rows(prob, prob, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;
+        if ((rc = launch_rows(prob, sp, nullptr, nullptr, cli, lc, ls, mode, scale, st))) return rc;
+        // dH = dO S'      (A = dO rows c, K = i;  B = S'^T rows j, K = i)
+        if ((rc = pack_operand_shift(doi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), st))) return rc;
+        if ((rc = pack_operand_shift(sp, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_h + i * c * ls, c, ls, lc, ls, passes,
+                                     1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        // dS' = dO^T H    (A = dO^T rows i, K = c;  B = H^T rows j, K = c)
+        if ((rc = pack_operand_shift(doi, lc, c, 1, lc, nullptr, nullptr, w + a.q_hi, lo(a.q_lo), st))) return rc;
+        if ((rc = pack_operand_shift(hi_, ls, c, 1, ls, nullptr, nullptr, w + a.k_hi, lo(a.k_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + a.q_hi, w + a.q_lo, w + a.k_hi, w + a.k_lo, dp, lc, ls, c, ls, passes, 1.f, nullptr,
+                                     nullptr, 1, 0, st))) return rc;
+        // clamp + softmax backward: dS (fp32 in place of dS' + tiles rows i, K = j), grad_clamp
+        if (lc % kTileRows != 0 || ls % kTileK != 0) {
+            RPST_CUDA(cudaMemsetAsync(w + a.p_hi, 0, a.p_b, st));
+            if (x3) RPST_CUDA(cudaMemsetAsync(w + a.p_lo, 0, a.p_b, st));
+        }
+        attn_clamped_bwd_rows_kernel<<<(unsigned)lc, kRowThreads, 0, st>>>(
+            prob, sp, dp, cli, grad_clamp + i * lc, mode, scale, reinterpret_cast<__nv_bfloat16*>(w + a.p_hi),
+            x3 ? reinterpret_cast<__nv_bfloat16*>(w + a.p_lo) : nullptr, ls, (int)((ls + kTileK - 1) / kTileK));
+        RPST_CUDA(cudaGetLastError());
+        // dF = G dS^T, dG = F dS
+        if ((rc = pack_operand_shift(gi, c, ls, ls, 1, nullptr, nullptr, w + a.v_hi, lo(a.v_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + a.v_hi, w + a.v_lo, w + a.p_hi, w + a.p_lo, grad_f + i * c * lc, c, lc, ls, lc, passes,
+                                     1.f, nullptr, nullptr, 1, 0, st))) return rc;
+        if ((rc = pack_operand_shift(fi, c, lc, lc, 1, nullptr, nullptr, w + l.w_hi, lo(l.w_lo), st))) return rc;
+        if ((rc = pack_operand_shift(dp, ls, lc, 1, ls, nullptr, nullptr, w + l.t_hi, lo(l.t_lo), st))) return rc;
+        if ((rc = gemm_packed_splitk(w + l.w_hi, w + l.w_lo, w + l.t_hi, w + l.t_lo, grad_g + i * c * ls, c, ls, lc, ls, passes,
+                                     1.f, nullptr, nullptr, 1, 0, st))) return rc;
     }
     return RPST_OK;
 }

@@ -27,13 +27,6 @@ def _group_ws(per_sample: int, b: int, device) -> torch.Tensor:
     return _ws(k * int(per_sample), device)
 
 
-def _no_grad_guard(*tensors):
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            "rpst: the ADAPTIVE attention (AEA clamps) is forward-only; the static SANet core is differentiable "
-            "(rpst_sanet_attn_bwd).  Call this under torch.no_grad() (as `AdaptiveSAModel.test` does) or detach the inputs")
-
-
 def cal_affinity_matrix(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/sanet.py:12 — [b,c,h,w] x2 -> [b,hw,hw] cosine affinity."""
     assert content_feat.size() == style_feat.size()
@@ -99,6 +92,65 @@ def attention_core(F: torch.Tensor, G: torch.Tensor, H: torch.Tensor, precision:
             return out, _attn_fwd_raw(F, G, H, precision, True)[1]
     out, attn = _attn_fwd_raw(F, G, H, precision, return_attn)
     return (out, attn) if return_attn else out
+
+
+class _AffinityFn(torch.autograd.Function):
+    """Differentiable cosine affinity (network/sanet.py:12-18): forward is the tcgen05 kernel; the backward
+    pass is two plain [C,L]x[L,L] library GEMMs and the normalisation's closed-form Jacobian."""
+
+    @staticmethod
+    def forward(ctx, content, style):
+        ctx.save_for_backward(content, style)
+        with torch.no_grad():
+            return cal_affinity_matrix(content, style)
+
+    @staticmethod
+    def backward(ctx, daff):
+        content, style = ctx.saved_tensors
+        b, c = content.shape[:2]
+        cv, sv = content.reshape(b, c, -1), style.reshape(b, c, -1)
+        nc, ns = cv.norm(dim=1, keepdim=True).clamp_min(1e-12), sv.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        ch, sh = cv / nc, sv / ns
+        dch = torch.bmm(sh, daff.transpose(1, 2))      # d c^[c,i] = sum_j s^[c,j] daff[i,j]
+        dsh = torch.bmm(ch, daff)                      # d s^[c,j] = sum_i c^[c,i] daff[i,j]
+        dc = (dch - ch * (ch * dch).sum(1, keepdim=True)) / nc
+        ds = (dsh - sh * (sh * dsh).sum(1, keepdim=True)) / ns
+        return dc.view_as(content), ds.view_as(style)
+
+
+class _ClampedAttnFn(torch.autograd.Function):
+    """out = H S'^T with S' = clamp-activation(softmax(F^T G), clamp) (network/sanet.py:41-46, 66-71, 114-138),
+    forward and backward in librpst (rpst_sanet_attn_clamped_fwd / _bwd); differentiable w.r.t. F, G, H and the
+    per-row clamp, so the clamp MLP trains through ordinary autograd."""
+
+    @staticmethod
+    def forward(ctx, F, G, H, clamp, mode, scale, precision):
+        b, c, hc, wc = F.shape
+        lc, ls = hc * wc, G.shape[2] * G.shape[3]
+        out = torch.empty(b, c, hc, wc, dtype=torch.float32, device=F.device)
+        L = _lib.lib()
+        ws = _ws(L.rpst_sanet_attn_clamped_workspace_bytes(c, lc, ls), F.device)
+        _lib.check(L.rpst_sanet_attn_clamped_fwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), clamp.data_ptr(), mode, scale,
+                                                 out.data_ptr(), b, c, lc, ls, PRECISION[precision], ws.data_ptr(),
+                                                 ws.numel(), _stream()))
+        ctx.save_for_backward(F, G, H, clamp)
+        ctx.mode, ctx.scale, ctx.precision = mode, scale, precision
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        F, G, H, clamp = ctx.saved_tensors
+        b, c, hc, wc = F.shape
+        lc, ls = hc * wc, G.shape[2] * G.shape[3]
+        go = _prep(grad_out, "grad_out")
+        dF, dG, dH, dcl = torch.empty_like(F), torch.empty_like(G), torch.empty_like(H), torch.empty_like(clamp)
+        L = _lib.lib()
+        ws = _ws(L.rpst_sanet_attn_clamped_workspace_bytes(c, lc, ls), F.device)
+        _lib.check(L.rpst_sanet_attn_clamped_bwd(F.data_ptr(), G.data_ptr(), H.data_ptr(), clamp.data_ptr(), ctx.mode,
+                                                 ctx.scale, go.data_ptr(), dF.data_ptr(), dG.data_ptr(), dH.data_ptr(),
+                                                 dcl.data_ptr(), b, c, lc, ls, PRECISION[ctx.precision], ws.data_ptr(),
+                                                 ws.numel(), _stream()))
+        return dF, dG, dH, dcl, None, None, None
 
 
 class AEAModule(nn.Module):
@@ -196,7 +248,8 @@ class AdaptiveSANet(nn.Module):
         F = self.f(mean_variance_norm(content))
         G = self.g(mean_variance_norm(style))
         H = self.h(style)
-        _no_grad_guard(F, G, H, content, style)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (F, G, H, content, style)):
+            return self._forward_training(content, style, F, G, H)
         F, G, H = (_prep(t.detach(), n) for t, n in ((F, "F"), (G, "G"), (H, "H")))
         c_raw, s_raw = _prep(content.detach(), "content"), _prep(style.detach(), "style")
         b, c, hh, ww = F.shape
@@ -227,6 +280,30 @@ class AdaptiveSANet(nn.Module):
         O += content
         self.claim_value = clamp
         return O
+
+
+def _adaptive_forward_training(self, content, style, F, G, H):
+    """Training path (network/sanet.py:114-138 under autograd): the cosine affinity and the clamped attention
+    are librpst kernels with their own backward passes; the small clamp MLP `f_psi` (Linear L -> L/16 -> 1 on
+    the affinity rows) runs as the module's own layers so its parameters train through autograd."""
+    b, c, hh, ww = F.shape
+    l = hh * ww
+    al = self.attention_layer
+    assert al.f_psi[0].in_features == l, f"spatial_dims={al.f_psi[0].in_features} does not match H*W={l}"
+    aff = _AffinityFn.apply(_prep(content, "content"), _prep(style, "style"))
+    z = al.f_psi(aff.view(b * l, l))
+    clamp = z * al.value_interval + al.from_value if al.mode == 1 else (z + 1) / 2
+    clamp = clamp.view(b, l)
+    out = _ClampedAttnFn.apply(_prep(F, "F"), _prep(G, "G"), _prep(H, "H"), clamp.contiguous(), al.mode,
+                               float(al.scale_value), self.precision)
+    self.claim_before = self.claim_after = None      # not materialised in training
+    self.claim_value = clamp.detach().view(b, l, 1)
+    O = self.out_conv(out)
+    O = O + content
+    return O
+
+
+AdaptiveSANet._forward_training = _adaptive_forward_training
 
 
 class Transform(nn.Module):

@@ -148,11 +148,32 @@ def test_sanet_module_training_step_matches_fp64(rpst):
     assert R.rel_l2(cg.grad, cd.grad) < TOL32 and R.rel_l2(sg.grad, sd.grad) < TOL32
 
 
-def test_adaptive_requires_grad_is_refused_loudly(rpst):
-    m = rpst.AdaptiveSANet(8, 16).cuda()
-    x = torch.randn(1, 8, 4, 4, device="cuda")
-    with pytest.raises(NotImplementedError):
-        m(x, x)
+@pytest.mark.parametrize("mode", ["aea", "relu"])
+def test_golden_adaptive_gradients(rpst, golden, mode):
+    """AdaptiveSANet under autograd (the AdaptiveSAModel training path, network/sanet.py:373-384): output, input
+    gradients and every parameter gradient — including the clamp MLP f_psi — against what the REFERENCE module
+    produced through autograd on CPU (tests/golden/adaptive_grad.npz)."""
+    g = golden("adaptive_grad")
+    pre = mode + "."
+    m = rpst.AdaptiveSANet(16, 64, ada_module=mode).cuda()
+    m.load_state_dict({k[len(pre) + 6:]: v for k, v in g.items() if k.startswith(pre + "param.")})
+    c, s = g[pre + "content"].cuda().requires_grad_(), g[pre + "style"].cuda().requires_grad_()
+    out = m(c, s)
+    assert R.rel_l2(m.claim_value, g[pre + "clamp"]) < TOL32
+    assert R.rel_l2(out, g[pre + "out"]) < 2e-3             # sigmoid(50 x) amplifies S errors, as in the forward test
+    (out * g[pre + "w"].cuda()).sum().backward()
+    tol = 5e-3 if mode == "aea" else 2e-3
+    assert R.rel_l2(c.grad, g[pre + "grad_content"]) < tol, R.rel_l2(c.grad, g[pre + "grad_content"])
+    assert R.rel_l2(s.grad, g[pre + "grad_style"]) < tol, R.rel_l2(s.grad, g[pre + "grad_style"])
+    scale = float(g[pre + "grad.g.weight"].abs().max())
+    for name, p in m.named_parameters():
+        want = g[pre + "grad." + name]
+        assert p.grad is not None, name
+        if float(want.abs().max()) < 1e-6 * max(scale, 1e-30):     # exactly-zero gradients (e.g. g.bias under plain softmax)
+            assert float((p.grad.cpu() - want).abs().max()) < 1e-3 * scale, name
+            continue
+        assert R.rel_l2(p.grad, want) < tol, (name, R.rel_l2(p.grad, want))
+
 
 
 def test_sample_groups_match_per_sample_launches(rpst, monkeypatch):
