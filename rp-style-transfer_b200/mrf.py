@@ -77,9 +77,35 @@ def cal_affinity_map(content_feat, style_feat, k=3, reverse=False, c_mask=None, 
     return mrf_match(content_feat, style_feat, k, reverse, want_affinity=True)[2]
 
 
+class _MRFLossFn(torch.autograd.Function):
+    """loss = sum(A o dist) / norm with the (non-differentiable) top-k affinity A from librpst; like the
+    reference, the gradient flows through `cal_dist` alone: d/da_i = 2/norm * sum_j A_ij (a_i - b_j)."""
+
+    @staticmethod
+    def forward(ctx, content_feat, style_feat, k, mean):
+        _, _, aff, loss = mrf_match(content_feat, style_feat, k, want_affinity=True, want_loss=True, mean=mean)
+        ctx.save_for_backward(content_feat, style_feat, aff)
+        n, c, h, w = content_feat.shape
+        ctx.norm = float(h * w * k) if mean == "mean" else float(h * w) ** 2
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        cf, sf, aff = ctx.saved_tensors
+        c = cf.shape[1]
+        a, b = cf.reshape(c, -1), sf.reshape(c, -1)
+        s = 2.0 * g / ctx.norm
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = (s * (a * aff.sum(1)[None, :] - b @ aff.t())).view_as(cf)
+        if ctx.needs_input_grad[1]:
+            gb = (s * (b * aff.sum(0)[None, :] - a @ aff)).view_as(sf)
+        return ga, gb, None, None
+
+
 class MRFLoss(nn.Module):
-    """network/mrf_rp.py:4-23.  Forward only (the reference's own gradient flows through `cal_dist`
-    alone; `mrf_weight` is 0 in every shipped config)."""
+    """network/mrf_rp.py:4-23.  Matching, distances and the loss are one librpst call; under autograd the
+    gradient flows through `cal_dist` alone, as in the reference (the top-k affinity is piecewise constant)."""
 
     def __init__(self, k, mask=None, mean='mean') -> None:
         super().__init__()
@@ -88,4 +114,6 @@ class MRFLoss(nn.Module):
         self.mean = mean
 
     def forward(self, content_feat, style_feat):
-        return mrf_match(content_feat.detach(), style_feat.detach(), self.k, want_loss=True, mean=self.mean)[3]
+        if torch.is_grad_enabled() and (content_feat.requires_grad or style_feat.requires_grad):
+            return _MRFLossFn.apply(_prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"), self.k, self.mean)
+        return mrf_match(content_feat, style_feat, self.k, want_loss=True, mean=self.mean)[3]

@@ -108,3 +108,21 @@ def test_k_out_of_range_is_rejected(rpst):
     x = torch.zeros(1, 4, 4, 4).cuda()
     with pytest.raises(rpst.RpstError):
         rpst.mrf_match(x, x, k=9)
+
+
+def test_mrf_loss_gradient_flows_through_the_distances(rpst):
+    """network/mrf_rp.py:12-23 under autograd: the affinity map is piecewise constant, so the gradient is that of
+    sum(A o cal_dist) with A fixed; compared with fp64 autograd of exactly that expression (A from the oracle)."""
+    c, s = R.synth_features((1, 32, 12, 12), cfg=6, signed=True)
+    k = 3
+    aff = R.mrf_affinity_map(c, s, k).double()
+    cd, sd = c.double().requires_grad_(), s.double().requires_grad_()
+    a, b = cd.view(32, -1), sd.view(32, -1)
+    dist = (a * a).sum(0)[:, None] + (b * b).sum(0)[None, :] - 2 * a.t() @ b
+    want = (aff * dist).sum() / (144 * k)
+    (want * 1.7).backward()
+    cg, sg = c.cuda().requires_grad_(), s.cuda().requires_grad_()
+    got = rpst.MRFLoss(k)(cg, sg)
+    (got * 1.7).backward()
+    assert abs(float(got.detach()) - float(want.detach())) / abs(float(want.detach())) < 1e-4
+    assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4
