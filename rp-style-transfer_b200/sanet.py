@@ -28,8 +28,14 @@ def _group_ws(per_sample: int, b: int, device) -> torch.Tensor:
 
 
 def cal_affinity_matrix(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
-    """Drop-in for network/sanet.py:12 — [b,c,h,w] x2 -> [b,hw,hw] cosine affinity."""
+    """Drop-in for network/sanet.py:12 — [b,c,h,w] x2 -> [b,hw,hw] cosine affinity (differentiable)."""
     assert content_feat.size() == style_feat.size()
+    if torch.is_grad_enabled() and (content_feat.requires_grad or style_feat.requires_grad):
+        return _AffinityFn.apply(_prep(content_feat, "content_feat"), _prep(style_feat, "style_feat"))
+    return _cal_affinity_raw(content_feat, style_feat)
+
+
+def _cal_affinity_raw(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     c4, s4 = _prep(content_feat.detach(), "content_feat"), _prep(style_feat.detach(), "style_feat")
     b, c, h, w = c4.shape
     l = h * w
@@ -101,8 +107,7 @@ class _AffinityFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, content, style):
         ctx.save_for_backward(content, style)
-        with torch.no_grad():
-            return cal_affinity_matrix(content, style)
+        return _cal_affinity_raw(content, style)
 
     @staticmethod
     def backward(ctx, daff):

@@ -235,3 +235,16 @@ def test_golden_sanet_gradients(rpst, golden):
             assert float((p.grad.cpu() - want).abs().max()) < 1e-3 * scale
             continue
         assert R.rel_l2(p.grad, want) < TOL32, (name, R.rel_l2(p.grad, want))
+
+
+def test_cal_affinity_matrix_is_differentiable(rpst):
+    """network/sanet.py:12-18 under autograd: gradient of the cosine affinity w.r.t. both feature maps."""
+    c, s = R.synth_features((2, 12, 6, 5), cfg=16, signed=True)
+    w = torch.randn(2, 30, 30, generator=torch.Generator().manual_seed(17))
+    cd, sd = c.double().requires_grad_(), s.double().requires_grad_()
+    nc = torch.nn.functional.normalize(cd.view(2, 12, -1), dim=1)
+    ns = torch.nn.functional.normalize(sd.view(2, 12, -1), dim=1)
+    (torch.bmm(nc.permute(0, 2, 1), ns) * w.double()).sum().backward()
+    cg, sg = c.cuda().requires_grad_(), s.cuda().requires_grad_()
+    (rpst.cal_affinity_matrix(cg, sg) * w.cuda()).sum().backward()
+    assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4
