@@ -45,6 +45,11 @@ def seg_adain_batch(content_feat: torch.Tensor, style_feat: torch.Tensor, c_labe
     With `return_info` also returns the [N,256,3] int32 table (cnt_c, cnt_s, usable)."""
     assert content_feat.dim() == 4 and style_feat.dim() == 4
     assert content_feat.shape[:2] == style_feat.shape[:2], "batch/channel mismatch"
+    if torch.is_grad_enabled() and (content_feat.requires_grad or style_feat.requires_grad or
+                                    (prev is not None and prev.requires_grad)):
+        raise NotImplementedError(
+            "rpst: segment AdaIN has no backward pass (the reference only calls it from test() under "
+            "torch.no_grad(), network/adain_rp.py:251-262); call it under torch.no_grad() or detach the inputs")
     c = _prep(content_feat, "content_feat")
     s = _prep(style_feat, "style_feat")
     n, ch, hc, wc = c.shape

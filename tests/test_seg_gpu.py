@@ -134,3 +134,12 @@ def test_many_labels_take_every_flush_and_fallback_path(rpst, classes):
     # test_config5_plane_properties)
     again = rpst.seg_adain_batch(c.cuda(), s.cuda(), cl.cuda(), sl.cuda())
     assert R.rel_l2(again, got) < 1e-6
+
+
+def test_gradient_request_is_refused_loudly(rpst):
+    c = torch.randn(1, 2, 16, 16, device="cuda", requires_grad=True)
+    lab = torch.zeros(1, 16, 16, dtype=torch.uint8, device="cuda")
+    with pytest.raises(NotImplementedError):
+        rpst.seg_adain_batch(c, c.detach(), lab, lab)
+    with torch.no_grad():
+        rpst.seg_adain_batch(c, c.detach(), lab, lab)
