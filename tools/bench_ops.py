@@ -174,6 +174,37 @@ def bench_sanet_bwd():
              TFLOPs_fp32grade=flops / t3 / 1e9, TFLOPs_bf16=flops / t1 / 1e9, speedup_fp32grade=te / t3, speedup_bf16=te / t1)
 
 
+def bench_adaptive():
+    """AdaptiveSANet attention (config #4, 'aea' clamp) forward at relu5_1 / relu4_1 sizes of a 1024^2 image:
+    whole module (convs in cuDNN) vs the reference's op sequence in eager torch on the same GPU."""
+    for l_side in (64, 128):
+        ch, L = 512, l_side * l_side
+        torch.manual_seed(0)
+        m = rpst.AdaptiveSANet(ch, L, ada_module="aea").to(dev)
+        m.keep_claims = False
+        c, s = R.synth_features((1, ch, l_side, l_side), cfg=4, device=dev)
+
+        def eager():
+            al = m.attention_layer
+            mvn = lambda x: (x - x.mean((2, 3), keepdim=True)) / (x.var((2, 3), keepdim=True) + 1e-5).sqrt()
+            F = m.f(mvn(c)).view(1, ch, L).permute(0, 2, 1)
+            G = m.g(mvn(s)).view(1, ch, L)
+            H = m.h(s).view(1, ch, L)
+            aff = torch.bmm(torch.nn.functional.normalize(c.view(1, ch, L), dim=1).permute(0, 2, 1),
+                            torch.nn.functional.normalize(s.view(1, ch, L), dim=1))
+            S = torch.softmax(torch.bmm(F, G), -1)
+            clamp = (al.f_psi(aff.view(L, L)) * al.value_interval + al.from_value).view(1, L, 1)
+            S = torch.sigmoid(al.scale_value * (S - clamp))
+            return m.out_conv(torch.bmm(H, S.permute(0, 2, 1)).view(1, ch, l_side, l_side)) + c
+        with torch.no_grad():
+            t = timeit(lambda: m(c, s), 3, 1)
+            te = timeit(eager, 3, 1)
+            err = float((m(c, s) - eager()).norm() / eager().norm())
+        flops = (2 * L * L * ch * 3 + 2 * L * L * (L // 16))
+        emit(op=f"adaptive sanet ('aea') module forward config#4 L={L} C=512", rpst_ms=t, eager_gpu_ms=te, speedup=te / t,
+             algorithmic_TFLOPs=flops / t / 1e9, rel_l2_vs_eager_tf32_default=err)
+
+
 def bench_mrf():
     ch, side, k = 512, 64, 5
     c, s = R.synth_features((1, ch, side, side), cfg=6, device=dev)
@@ -215,7 +246,7 @@ def bench_losses():
              content_norm_bwd_ms=tb, bwd_GBs=3 * E / tb / 1e6)
 
 
-ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "train5": bench_train5, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "mrf": bench_mrf}
+ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "train5": bench_train5, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "adaptive": bench_adaptive, "mrf": bench_mrf}
 for name in (sys.argv[1:] or list(ALL)):
     try:
         ALL[name]()
