@@ -1,0 +1,139 @@
+"""Out-of-bounds write detection without compute-sanitizer: outputs and workspaces are carved out of larger
+buffers whose margins hold a canary pattern; after each C-ABI call the margins must be untouched.  The
+workspace is passed at EXACTLY the size the `*_workspace_bytes` query returned."""
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+MARGIN = 1 << 16           # bytes on each side
+CANARY = 0xA5
+
+
+class Guarded:
+    """A CUDA byte buffer with canary margins; `.inner` is the 256-byte aligned payload view."""
+
+    def __init__(self, nbytes: int):
+        nbytes = max(int(nbytes), 256)
+        self.raw = torch.full((nbytes + 2 * MARGIN + 512,), CANARY, dtype=torch.uint8, device="cuda")
+        off = MARGIN + (-(self.raw.data_ptr() + MARGIN)) % 256
+        self.off, self.n = off, nbytes
+        self.inner = self.raw[off:off + nbytes]
+
+    def floats(self, *shape):
+        return self.inner.view(torch.float32).view(*shape)
+
+    def check(self, what):
+        head, tail = self.raw[:self.off], self.raw[self.off + self.n:]
+        assert bool((head == CANARY).all()) and bool((tail == CANARY).all()), f"{what}: write outside the buffer"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import rpst
+    return rpst._lib
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("shape,blend", [((2, 3, 300, 300), False), ((1, 4, 512, 512), True), ((1, 2, 1100, 1000), False),
+                                         ((2, 5, 33, 31), True), ((1, 2, 1024, 2048), True)])
+def test_adain_fwd_and_stats(lib, shape, blend):
+    L = lib.lib()
+    n, c, h, w = shape
+    hw = h * w
+    cf, sf = R.synth_features(shape, cfg=90, device="cuda")
+    prev = torch.randn(shape, device="cuda") if blend else None
+    out = Guarded(cf.numel() * 4)
+    ws = Guarded(L.rpst_adain_workspace_bytes(n, c, hw))
+    lib.check(L.rpst_adain_fwd(cf.data_ptr(), sf.data_ptr(), None if prev is None else prev.data_ptr(), out.inner.data_ptr(),
+                               n, c, hw, c * hw, 1e-5, None, ws.inner.data_ptr(), ws.n, stream()))
+    torch.cuda.synchronize()
+    out.check("adain out"); ws.check("adain workspace")
+    want = R.adain(cf.cpu(), sf.cpu(), dtype=torch.float64) + (0 if prev is None else prev.cpu().double())
+    assert R.rel_l2(out.floats(*shape), want) < 2e-6
+    mean, std = Guarded(n * c * 4), Guarded(n * c * 4)
+    ws2 = Guarded(L.rpst_stats_workspace_bytes(n * c, hw))
+    lib.check(L.rpst_stats_nchw(cf.data_ptr(), n * c, hw, 1e-5, mean.inner.data_ptr(), std.inner.data_ptr(),
+                                ws2.inner.data_ptr(), ws2.n, stream()))
+    torch.cuda.synchronize()
+    mean.check("mean"); std.check("std"); ws2.check("stats workspace")
+
+
+def test_seg_adain(lib):
+    L = lib.lib()
+    n, c, h, w = 2, 3, 256, 256
+    cf, sf = R.synth_features((n, c, h, w), cfg=91, device="cuda")
+    cl = R.synth_labels(n, h, w, classes=19, block=8, seed=4300, device="cuda")
+    sl = R.synth_labels(n, h, w, classes=19, block=8, seed=5300, device="cuda")
+    out = Guarded(cf.numel() * 4)
+    ws = Guarded(L.rpst_seg_adain_workspace_bytes(n, c, h * w, h * w))
+    lib.check(L.rpst_seg_adain_fwd(cf.data_ptr(), sf.data_ptr(), cl.data_ptr(), sl.data_ptr(), None, out.inner.data_ptr(),
+                                   n, c, h * w, h * w, 1e-5, None, ws.inner.data_ptr(), ws.n, stream()))
+    torch.cuda.synchronize()
+    out.check("seg out"); ws.check("seg workspace")
+    assert R.rel_l2(out.floats(n, c, h, w), R.seg_adain_batch(cf.cpu(), sf.cpu(), cl.cpu(), sl.cpu(), dtype=torch.float64)) < 2e-6
+
+
+def test_pair_stats_and_backward(lib):
+    L = lib.lib()
+    shape = (2, 5, 129, 131)
+    x, y = R.synth_features(shape, cfg=92, device="cuda")
+    planes, hw = 10, 129 * 131
+    stats, losses, g = Guarded(planes * 8 * 4), Guarded(8), Guarded(4)
+    ws = Guarded(L.rpst_pair_stats_workspace_bytes(planes, hw))
+    lib.check(L.rpst_pair_stats(x.data_ptr(), y.data_ptr(), planes, hw, 1e-5, stats.inner.data_ptr(), losses.inner.data_ptr(),
+                                ws.inner.data_ptr(), ws.n, stream()))
+    g.inner.view(torch.float32).fill_(1.0)
+    dx = Guarded(x.numel() * 4)
+    lib.check(L.rpst_pair_loss_bwd(x.data_ptr(), y.data_ptr(), stats.inner.data_ptr(), g.inner.data_ptr(), 1, 0,
+                                   dx.inner.data_ptr(), planes, hw, stream()))
+    torch.cuda.synchronize()
+    for b, name in ((stats, "stats"), (losses, "losses"), (ws, "pair workspace"), (dx, "dx"), (g, "g")):
+        b.check(name)
+    assert abs(float(losses.inner.view(torch.float32)[0]) - float(R.style_loss(x.cpu(), y.cpu(), dtype=torch.float64))) < 1e-4
+
+
+def test_sanet_forward_backward_ragged(lib):
+    L = lib.lib()
+    b, c, lc, ls = 2, 40, 9 * 11, 10 * 7
+    g = torch.Generator(device="cuda").manual_seed(93)
+    f, k, v, go = (torch.randn(b, c, l, device="cuda", generator=g) * 0.5 for l in (lc, ls, ls, lc))
+    out, attn = Guarded(b * c * lc * 4), Guarded(b * lc * ls * 4)
+    ws = Guarded(L.rpst_sanet_attn_workspace_bytes(c, lc, ls) * 2)       # two samples per launch
+    lib.check(L.rpst_sanet_attn_fwd(f.data_ptr(), k.data_ptr(), v.data_ptr(), out.inner.data_ptr(), b, c, lc, ls, 3,
+                                    attn.inner.data_ptr(), ws.inner.data_ptr(), ws.n, stream()))
+    df, dk, dv = Guarded(f.numel() * 4), Guarded(k.numel() * 4), Guarded(v.numel() * 4)
+    wsb = Guarded(L.rpst_sanet_attn_bwd_workspace_bytes(c, lc, ls))      # one sample per launch
+    lib.check(L.rpst_sanet_attn_bwd(f.data_ptr(), k.data_ptr(), v.data_ptr(), go.data_ptr(), df.inner.data_ptr(),
+                                    dk.inner.data_ptr(), dv.inner.data_ptr(), b, c, lc, ls, 3, wsb.inner.data_ptr(), wsb.n, stream()))
+    torch.cuda.synchronize()
+    for buf, name in ((out, "out"), (attn, "attn"), (ws, "attn workspace"), (df, "df"), (dk, "dk"), (dv, "dv"), (wsb, "bwd workspace")):
+        buf.check(name)
+    want = R.attention_core(f.cpu().double(), k.cpu().double(), v.cpu().double())
+    assert R.rel_l2(out.floats(b, c, lc), want) < 1e-3
+
+
+def test_wct_and_mrf(lib):
+    L = lib.lib()
+    n, c, h, w = 2, 24, 20, 28
+    cf, sf = R.synth_features((n, c, h, w), cfg=94, device="cuda")
+    out = Guarded(cf.numel() * 4)
+    ws = Guarded(L.rpst_wct_workspace_bytes(n, c, h * w, h * w))
+    lib.check(L.rpst_wct_fuse(cf.data_ptr(), sf.data_ptr(), out.inner.data_ptr(), n, c, h * w, h * w, 0, 3, None,
+                              ws.inner.data_ptr(), ws.n, stream()))
+    torch.cuda.synchronize()
+    out.check("wct out"); ws.check("wct workspace")
+    assert R.rel_l2(out.floats(n, c, h, w), R.wct_fuse(cf.cpu(), sf.cpu())) < 1e-3
+    l, k = h * w, 3
+    idx0, idx1, loss = Guarded(k * l * 8), Guarded(l * k * 8), Guarded(4)
+    wsm = Guarded(L.rpst_mrf_workspace_bytes(c, l, k))
+    lib.check(L.rpst_mrf_match(cf[:1].contiguous().data_ptr(), sf[:1].contiguous().data_ptr(), c, l, k, 0, 3,
+                               idx0.inner.data_ptr(), idx1.inner.data_ptr(), None, loss.inner.data_ptr(), 0,
+                               wsm.inner.data_ptr(), wsm.n, stream()))
+    torch.cuda.synchronize()
+    for buf, name in ((idx0, "idx0"), (idx1, "idx1"), (loss, "loss"), (wsm, "mrf workspace")):
+        buf.check(name)
