@@ -66,6 +66,18 @@ def bench_bwd():
     emit(op="adain backward 8x256x512x512", ms=t, GBs=5 * E / t / 1e6, frac_of_peak=5 * E / t / 1e6 / PEAK_GBS)
 
 
+def bench_stats():
+    """calc_mean_std / mean_variance_norm alone (E and 2E algorithmic bytes)."""
+    for shape in ((8, 256, 512, 512), (1, 256, 1024, 2048)):
+        x, _ = R.synth_features(shape, cfg=2, device=dev)
+        E = x.numel() * 4
+        t = timeit(lambda: rpst.calc_mean_std(x), 10)
+        tm = timeit(lambda: rpst.mean_variance_norm(x), 10)
+        te = timeit(lambda: eager_stats(x), 5)
+        emit(op=f"calc_mean_std {shape}", ms=t, GBs=E / t / 1e6, frac_of_peak=E / t / 1e6 / PEAK_GBS, eager_gpu_ms=te,
+             mvn_ms=tm, mvn_GBs=2 * E / tm / 1e6)
+
+
 def bench_train5():
     """config #5 training transform: AdaIN forward + backward on a Cityscapes-sized level (1x256x1024x2048)."""
     shape = (1, 256, 1024, 2048)
@@ -246,7 +258,7 @@ def bench_losses():
              content_norm_bwd_ms=tb, bwd_GBs=3 * E / tb / 1e6)
 
 
-ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "train5": bench_train5, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "adaptive": bench_adaptive, "mrf": bench_mrf}
+ALL = {"losses": bench_losses, "sanet_bwd": bench_sanet_bwd, "adain1": bench_adain1, "bwd": bench_bwd, "stats": bench_stats, "train5": bench_train5, "seg": bench_seg, "wct": bench_wct, "sanet": bench_sanet, "adaptive": bench_adaptive, "mrf": bench_mrf}
 for name in (sys.argv[1:] or list(ALL)):
     try:
         ALL[name]()
