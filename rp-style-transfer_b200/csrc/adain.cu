@@ -55,6 +55,8 @@ struct AdainParams {
     int hints;
     // pipelined kernel only
     int ipp;             // items (chunks) per plane
+    int ips;             // TMA kernel: statistics items per plane (ipp with a style tensor; ceil(ipp/2) without:
+                         // the item then carries two content chunks — calc_mean_std / mean_variance_norm)
     int ipa;             // TMA kernel: apply items per plane (ipp with prev; ceil(ipp/2) without: an apply item
                          // then carries two content chunks, so every stage moves 32 KiB whatever the item kind)
     int spp;             // statistics slots per plane
@@ -488,7 +490,7 @@ struct DecodedItem {
 };
 
 __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int& kind, int64_t& plane, int& chunk) {
-    const unsigned I = (unsigned)p.ipp;
+    const unsigned I = (unsigned)p.ips;    // statistics items per plane
     if (p.stats_only) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
     const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = L / 2, A = (unsigned)p.ipa;
     // rounds: [S only] x (L-Lm), [S,M] x Lm, [S,M,A] x (P-L), [M,A] x (L-Lm), [A] x Lm
@@ -678,7 +680,8 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                     const int stage = (int)(seq % STAGES);
                     mbar_wait(&empty[stage], ((seq / STAGES) & 1u) ^ 1u);
                     StageDesc* d = &desc[stage];
-                    const bool twin = kind == 1 && p.ipa != p.ipp;    // apply item carrying two content chunks
+                    // twin items carry two consecutive content chunks (apply without prev; statistics without style)
+                    const bool twin = (kind == 1 && p.ipa != p.ipp) || (kind == 0 && p.ips != p.ipp);
                     const int64_t e0 = (int64_t)chunk * (twin ? 2 * kItemElems : kItemElems);
                     const int64_t rem = p.hw - e0;
                     const int nvec = (int)((rem < kItemElems ? rem : kItemElems) / 4);
@@ -691,9 +694,11 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                     const float* csrc = p.content + dec[i].cplane * p.hw + e0;
                     if (kind == 0) {
                         const bool has_style = p.style != nullptr;
-                        mbar_arrive_expect_tx(&full[stage], has_style ? 2u * bytes : bytes);
-                        tma_load_1d(buf_a, csrc, bytes, &full[stage], p.stats_only ? pol_first : pol_last);
+                        const uint64_t cpol = p.stats_only ? pol_first : pol_last;
+                        mbar_arrive_expect_tx(&full[stage], (has_style ? 2u * bytes : bytes) + (uint32_t)nvec2 * 16u);
+                        tma_load_1d(buf_a, csrc, bytes, &full[stage], cpol);
                         if (has_style) tma_load_1d(buf_b, p.style + dec[i].splane * p.hw + e0, bytes, &full[stage], pol_first);
+                        if (nvec2 > 0) tma_load_1d(buf_b, csrc + kItemElems, (uint32_t)nvec2 * 16u, &full[stage], cpol);
                     } else if (kind == 1) {
                         const bool has_prev = p.prev != nullptr;
                         mbar_arrive_expect_tx(&full[stage], (has_prev ? 2u * bytes : bytes) + (uint32_t)nvec2 * 16u + 16u);
@@ -745,18 +750,29 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
             for (int j = 0; j < kTmaVecs; ++j) v[j] = j < my_vecs ? a4[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
             const Moments mc = warp_moments(v, my_vecs, full_warp);
             Moments ms = {0.f, 0.f, 0.f};
+            const bool twin_s = !has_style && p.ips != p.ipp;   // buffer b holds the NEXT content chunk
+            int wvec2 = 0;
             if (has_style) {
 #pragma unroll
                 for (int j = 0; j < kTmaVecs; ++j) v[j] = j < my_vecs ? b4[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
                 ms = warp_moments(v, my_vecs, full_warp);
+            } else if (twin_s) {
+                wvec2 = min(max(d->nvec2 - gw * (kTmaSlotElems / 4), 0), kTmaSlotElems / 4);
+                const int my_vecs2 = wvec2 > lane ? min((wvec2 - lane + 31) / 32, kTmaVecs) : 0;
+#pragma unroll
+                for (int j = 0; j < kTmaVecs; ++j) v[j] = j < my_vecs2 ? b4[j * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                ms = warp_moments(v, my_vecs2, wvec2 == kTmaSlotElems / 4);   // moments of the second chunk's 4 KiB
             }
             // the stage has been consumed (the moments depend on every value read from it)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty[stage]);
+                const int64_t slot_chunk = twin_s ? 2 * (int64_t)chunk : chunk;
                 if (wvec > 0)
-                    st_slot(&p.part[plane * p.spp + (int64_t)chunk * kTmaGroupWarps + gw],
-                            make_float4(mc.mean, mc.m2, ms.mean, ms.m2));
+                    st_slot(&p.part[plane * p.spp + slot_chunk * kTmaGroupWarps + gw],
+                            twin_s ? make_float4(mc.mean, mc.m2, 0.f, 0.f) : make_float4(mc.mean, mc.m2, ms.mean, ms.m2));
+                if (wvec2 > 0)
+                    st_slot(&p.part[plane * p.spp + (slot_chunk + 1) * kTmaGroupWarps + gw], make_float4(ms.mean, ms.m2, 0.f, 0.f));
             }
         } else if (kind == 1) {
             // ---------------- apply: out = (c - mu_c) * a + mu_s (+ prev)
@@ -1198,7 +1214,8 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     p.slot_elems = use_tma ? kTmaSlotElems : kItemElems;
     p.spp = (int)((p.hw + p.slot_elems - 1) / p.slot_elems);
     p.ipa = (use_tma && !p.stats_only && p.prev == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
-    const int64_t total = p.stats_only ? p.planes * p.ipp : p.planes * ((int64_t)p.ipp + p.ipa + (use_tma ? 1 : 0));
+    p.ips = (use_tma && p.style == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
+    const int64_t total = p.stats_only ? p.planes * p.ips : p.planes * ((int64_t)p.ips + p.ipa + (use_tma ? 1 : 0));
     RPST_CHECK_ARG(total < (1ll << 31), "adain: too many work items (%lld); split the call", (long long)total);
     p.total_items = (unsigned)total;
     p.ticket = reinterpret_cast<unsigned*>(base);
