@@ -37,26 +37,24 @@ class GradBucket:
         if self._flat is None or self._flat.device != dev:
             self._flat = torch.zeros(self.numel + 64, dtype=torch.float32, device=dev)
         flat = self._flat
-        off = 0
+        views, off = [], 0
         for p in self.params:
-            n = p.numel()
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        have = [(v, p.grad) for v, p in zip(views, self.params) if p.grad is not None]
+        for v, p in zip(views, self.params):
             if p.grad is None:
-                flat[off:off + n].zero_()
-            else:
-                flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+                v.zero_()
+        if have:   # one fused multi-tensor copy in, one out (dozens of parameters, two launches)
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         assert len(names) <= 64
         for i, k in enumerate(names):
             flat[self.numel + i] = extra_scalars[k].detach().float()
         if world > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
             flat.div_(world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-            off += n
+        if have:
+            torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
         return {k: flat[self.numel + i].clone() for i, k in enumerate(names)}
 
 
