@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "librpst.so")
+LIB_PATH = os.environ.get("RPST_LIB") or os.path.join(PKG, "librpst.so")   # RPST_LIB: A/B a second build
 
 RPST_OK = 0
 RPST_ERR_INVALID = -1

@@ -33,6 +33,7 @@ struct Tuning {
     int64_t stages = 6;  // TMA ring depth (32 KiB per stage)
     int64_t seg_lag_bytes = 256ll << 20;  // segment AdaIN: content bytes between statistics and apply
     int64_t group_merge_min_spp = 512;    // see merge_plane_coef_group
+    int64_t merge_lead = 0;               // 0: lag / 2
     int64_t twin_apply = 1;               // TMA kernel, no prev: apply items carry two content chunks (32 KiB per stage)
     int64_t seg_groups = 4;               // consumer groups (= stages) of the segment TMA kernel
     int64_t seg_flush = 2;                // final flush: 0 shared atomics per lane, 1 warp-aggregated, 2 staged gather (atomic-free)
@@ -71,6 +72,7 @@ struct AdainParams {
     const int* cmap;
     const int* smap;
     int group_merge_min_spp;   // TMA kernel: planes with at least this many statistics slots are merged by the whole group
+    int merge_lead;            // TMA kernel: planes between a plane's MERGE ticket and its first APPLY ticket (1 .. lag-1)
 };
 
 __device__ __forceinline__ int64_t src_plane(const int* map, int64_t plane) {
@@ -245,6 +247,76 @@ __device__ __forceinline__ Item decode_item(unsigned t, const AdainParams& p) {
 // first chunk's mean K, so the result keeps the plane mean to better than fp32 (returned as hi+lo):
 //   mean = K + d,  d = sum n_k (mean_k - K) / N,   M2 = sum M2_k + sum n_k (mean_k - K - d)^2
 // Every caller computes bit-identical values (fixed lane assignment, fixed reduction tree).
+// Up to 256 slots (planes of <= 256 Ki elements, e.g. 512x512): every lane keeps its <= 8 slots in registers —
+// all loads in flight at once instead of one validity branch (= one L2 round trip) per slot, and the second
+// pass needs no reload.  Same arithmetic in the same order as the generic path below: bit-identical results.
+__device__ __forceinline__ float4 merge_plane_coef_small(const AdainParams& p, int64_t plane, int lane) {
+    const float4* slots = p.part + plane * p.spp;
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < p.spp) v[u] = ld_slot(slots + k);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        if (k < p.spp && !slot_valid(v[u])) {   // straggling statistics item: wait for it
+            const uint64_t t0 = global_timer_ns();
+            do {
+                __nanosleep(40);
+                v[u] = ld_slot(slots + k);
+                if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+            } while (!slot_valid(v[u]));
+        }
+    }
+    const float kc = __shfl_sync(0xffffffffu, v[0].x, 0), ks = __shfl_sync(0xffffffffu, v[0].z, 0);
+    float dc = 0.f, ds = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        if (k < p.spp) {
+            const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+            const float n = (float)(rem < p.slot_elems ? rem : p.slot_elems);
+            dc = fmaf(n, v[u].x - kc, dc);
+            ds = fmaf(n, v[u].z - ks, ds);
+        }
+    }
+    const float inv_n = 1.f / (float)p.hw;
+    dc = warp_sum(dc) * inv_n;
+    ds = warp_sum(ds) * inv_n;
+    float m2c = 0.f, m2s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        if (k < p.spp) {
+            const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
+            const float n = (float)(rem < p.slot_elems ? rem : p.slot_elems);
+            const float ec = v[u].x - kc - dc, es = v[u].z - ks - ds;
+            m2c += fmaf(n * ec, ec, v[u].y);
+            m2s += fmaf(n * es, es, v[u].w);
+        }
+    }
+    m2c = warp_sum(m2c);
+    m2s = warp_sum(m2s);
+    const float mu_hi = kc + dc;
+    const float mu_lo = (kc - mu_hi) + dc;
+    const float denom = (float)p.hw - 1.f;
+    const float sd_c = sqrtf(m2c / denom + p.eps);
+    float mu_s = 0.f, sd_s = 1.f;
+    if (p.style != nullptr) {
+        mu_s = ks + ds;
+        sd_s = sqrtf(m2s / denom + p.eps);
+    }
+    const float4 cf = make_float4(mu_hi, sd_s / sd_c, mu_s, mu_lo);
+    if (lane == 0) {
+        st_slot(&p.coef[plane], cf);
+        if (p.saved) reinterpret_cast<float4*>(p.saved)[plane] = make_float4(mu_hi, sd_c, mu_s, sd_s);
+    }
+    return cf;
+}
+
 __device__ __forceinline__ float4 merge_plane_coef(const AdainParams& p, int64_t plane, int lane) {
     const float4* slots = p.part + plane * p.spp;
     // pass 1 (polling): K = first chunk's means, d = sum n_k (mean_k - K) / N
@@ -435,7 +507,8 @@ constexpr int kTmaGroupWarps = 4;
 constexpr int kTmaGroupThreads = kTmaGroupWarps * 32;
 constexpr int kTmaSlotElems = kItemElems / kTmaGroupWarps;   // one warp summarises 1024 contiguous elements
 constexpr int kTmaVecs = kTmaSlotElems / 4 / 32;             // float4 per lane per tensor per item (8)
-constexpr int kTicketBatch = 8;
+constexpr int kTicketBatch = 8;   // 4 was measured: mean_variance_norm 4.7 -> 5.8 TB/s (a plane's last statistics ticket
+                                  // waits behind fewer items of its SM's batch) but plain 6.4 -> 6.1 and blend 6.9 -> 6.2
 
 // moments of 4*kTmaVecs register values per lane, then a warp tree.  `full` (warp-uniform): every lane
 // holds exactly 4*kTmaVecs valid values, so every merge joins equal counts and needs no division.
@@ -492,7 +565,7 @@ struct DecodedItem {
 __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int& kind, int64_t& plane, int& chunk) {
     const unsigned I = (unsigned)p.ips;    // statistics items per plane
     if (p.stats_only) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
-    const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = L / 2, A = (unsigned)p.ipa;
+    const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = (unsigned)p.merge_lead, A = (unsigned)p.ipa;
     // rounds: [S only] x (L-Lm), [S,M] x Lm, [S,M,A] x (P-L), [M,A] x (L-Lm), [A] x Lm
     unsigned n = (L - Lm) * I;
     if (t < n) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
@@ -618,7 +691,7 @@ __device__ __noinline__ void merge_plane_coef_group(const AdainParams& p, int64_
 // GROUP_MERGE is a separate instantiation so that the small-plane kernel (the benchmark's) carries neither the
 // call nor its register/barrier footprint: with a run-time switch the 512x512 path lost 10 % (5.66 vs 6.3 TB/s).
 template <int STAGES, bool GROUP_MERGE>
-__global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_kernel(AdainParams p) {
+__global__ void __launch_bounds__(64 + STAGES * kTmaGroupThreads, 1) adain_tma_kernel(AdainParams p) {
     constexpr int kTmaGroups = STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* bufs = reinterpret_cast<float*>(smem_raw);
@@ -627,12 +700,24 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
     uint64_t* empty = full + STAGES;
     DecodedItem* dec = reinterpret_cast<DecodedItem*>(empty + STAGES);
     __shared__ double merge_scratch[GROUP_MERGE ? STAGES : 1][kTmaGroupWarps][5];
+    // MERGE tickets of the single-warp merge bypass the stage ring: the producer posts the plane id into a
+    // mailbox served by a dedicated merge warp (the last warp of the CTA).  Through the ring a merge queued
+    // behind ~7 us of data items, twice per plane (statistics -> merge, merge -> apply), and that latency — not
+    // HBM — set the time per plane: mean_variance_norm ran as slowly as full AdaIN.
+    constexpr int kMailbox = 8;
+    __shared__ uint64_t mfull[kMailbox], mempty[kMailbox];
+    __shared__ int64_t mbox[kMailbox];
+    constexpr bool mailbox = !GROUP_MERGE;   // small planes: always; the consumer loop then carries no merge code at all
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTmaGroupWarps);
+        }
+        for (int s = 0; s < kMailbox; ++s) {
+            mbar_init(&mfull[s], 1);
+            mbar_init(&mempty[s], 1);
         }
         mbar_fence_init();
     }
@@ -646,7 +731,14 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
         const uint64_t pol_last = policy_evict_last();
         unsigned next_base = 0;
         if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kTicketBatch) + 1u;
-        unsigned seq = 0;
+        unsigned seq = 0, mseq = 0;
+        auto post_merge = [&](int64_t plane_or_stop) {
+            const int ms = (int)(mseq % kMailbox);
+            mbar_wait(&mempty[ms], ((mseq / kMailbox) & 1u) ^ 1u);
+            mbox[ms] = plane_or_stop;
+            mbar_arrive(&mfull[ms]);
+            ++mseq;
+        };
         for (;;) {
             const unsigned base = __shfl_sync(0xffffffffu, next_base, 0);
             if (lane == 0) next_base = atomicAdd(p.ticket, (unsigned)kTicketBatch) + 1u;
@@ -672,8 +764,13 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                             desc[stage].kind = -1;
                             mbar_arrive(&full[stage]);
                         }
+                        post_merge(-1);
                         finished = true;
                         break;
+                    }
+                    if (kind == 2 && mailbox) {   // merge ticket: straight to the merge warp, no stage
+                        post_merge(dec[i].plane);
+                        continue;
                     }
                     const int chunk = dec[i].chunk;
                     const int64_t plane = dec[i].plane;
@@ -716,6 +813,21 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
             if (finished) return;
             __syncwarp();
         }
+    }
+
+    if (warp == 1 + STAGES * kTmaGroupWarps) {
+        // ================================================================ merge warp (mailbox)
+        for (unsigned mseq = 0;; ++mseq) {
+            const int ms = (int)(mseq % kMailbox);
+            mbar_wait(&mfull[ms], (mseq / kMailbox) & 1u);
+            const int64_t plane = mbox[ms];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mempty[ms]);
+            if (plane < 0) break;
+            if (p.spp <= 256) merge_plane_coef_small(p, plane, lane);
+            else merge_plane_coef(p, plane, lane);
+        }
+        return;
     }
 
     // ==================================================================== consumers
@@ -838,7 +950,6 @@ __global__ void __launch_bounds__(32 + STAGES * kTmaGroupThreads, 1) adain_tma_k
             // few slots (512x512 planes: 256): one warp folds them while the other three go on to the next item;
             // many slots (1024x2048: 2048): the whole group takes one round trip instead of 2 x 64 serialized ones
             if constexpr (GROUP_MERGE) merge_plane_coef_group(p, plane, gw * 32 + lane, 1 + group, merge_scratch[group]);
-            else if (gw == 0) merge_plane_coef(p, plane, lane);
         }
     }
 }
@@ -1187,7 +1298,7 @@ int launch_tma_variant2(const AdainParams& p, cudaStream_t stream) {
     }
     int64_t grid = sm_count();
     if (grid > (int64_t)p.total_items) grid = p.total_items;
-    adain_tma_kernel<STAGES, GROUP_MERGE><<<(int)grid, 32 + STAGES * kTmaGroupThreads, smem, stream>>>(p);
+    adain_tma_kernel<STAGES, GROUP_MERGE><<<(int)grid, 64 + STAGES * kTmaGroupThreads, smem, stream>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
@@ -1213,6 +1324,12 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const bool use_tma = VEC == 4 && g_tuning.path == 0;
     p.slot_elems = use_tma ? kTmaSlotElems : kItemElems;
     p.spp = (int)((p.hw + p.slot_elems - 1) / p.slot_elems);
+    {
+        int64_t lead = g_tuning.merge_lead > 0 ? g_tuning.merge_lead : p.lag / 2;
+        if (lead > p.lag - 1) lead = p.lag - 1;
+        if (lead < 1) lead = 1;
+        p.merge_lead = (int)lead;
+    }
     p.ipa = (use_tma && !p.stats_only && p.prev == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
     p.ips = (use_tma && p.style == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
     const int64_t total = p.stats_only ? p.planes * p.ips : p.planes * ((int64_t)p.ips + p.ipa + (use_tma ? 1 : 0));
@@ -1332,6 +1449,7 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     else if (!strcmp(name, "seg_groups")) slot = &g_tuning.seg_groups;
     else if (!strcmp(name, "adain_twin_apply")) slot = &g_tuning.twin_apply;
     else if (!strcmp(name, "adain_group_merge_min_spp")) slot = &g_tuning.group_merge_min_spp;
+    else if (!strcmp(name, "adain_merge_lead")) slot = &g_tuning.merge_lead;
     if (!slot) return 0;
     if (set) *slot = v;
     if (out) *out = *slot;
