@@ -19,5 +19,5 @@ PY
 for i in 1 2; do
   run librpst_prev.so ""
   run librpst.so ""
-  run librpst.so 5
+
 done
