@@ -67,12 +67,21 @@ def test_multiscale(self, content, style, iterations=0, bid=0, c_mask_path=None,
     with torch.no_grad():
         content_feats = self.encode_rp_intermediate(content)
         style_feats = self.encode_rp_intermediate(style)
-        maps = None
-        if self._shuffle:
-            maps = [None if idx > self._shuffle_layers else
-                    F.shuffle_map(c.shape[0], c.shape[1], 4, c.device) for idx, c in enumerate(content_feats)]
-        stylized = decode_multiscale(self, content_feats, style_feats, use_mask=self.config['use_mask'],
-                                     c_mask_path=c_mask_path, s_mask_path=s_mask_path, plane_maps=maps)
+        if type(self).decode is decode_multiscale:
+            maps = None
+            if self._shuffle:
+                maps = [None if idx > self._shuffle_layers else
+                        F.shuffle_map(c.shape[0], c.shape[1], 4, c.device) for idx, c in enumerate(content_feats)]
+            stylized = decode_multiscale(self, content_feats, style_feats, use_mask=self.config['use_mask'],
+                                         c_mask_path=c_mask_path, s_mask_path=s_mask_path, plane_maps=maps)
+        else:
+            # subclasses that inherit test() but bring their own decode loop (CCAM, MST, SELast, LDMS*): shuffle as
+            # the reference does (:256-260) and hand over to THEIR decode
+            if self._shuffle:
+                content_feats = [self.shuffle(c, idx) for idx, c in enumerate(content_feats)]
+                style_feats = [self.shuffle(s, idx) for idx, s in enumerate(style_feats)]
+            stylized = self.decode(content_feats, style_feats, use_mask=self.config['use_mask'],
+                                   c_mask_path=c_mask_path, s_mask_path=s_mask_path)
         self.train()
         return stylized
 

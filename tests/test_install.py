@@ -61,3 +61,37 @@ def test_state_dict_names_match_reference():
         assert list(a.keys()) == list(b.keys())
         assert all(a[k].shape == b[k].shape for k in a)
         ours.load_state_dict(b)   # reference checkpoints load unchanged
+
+
+def test_patched_test_respects_subclass_decode():
+    """CCAM / MST / SELast / LDMS* inherit MultiScaleAdaINRPNet.test() but define their own decode(): the patched
+    test() must shuffle like the reference and call THEIR decode, not the fused multiscale one."""
+    import torch
+    import rpst
+    load_reference()
+    adain_rp = sys.modules["network.adain_rp"]
+    rpst.install()
+    try:
+        calls = {}
+
+        class Sub(adain_rp.SELastMultiScaleAdaINRPNet):
+            def __init__(self):                       # bypass the heavy constructor
+                torch.nn.Module.__init__(self)
+                self._shuffle, self._shuffle_layers, self._sort = True, 0, False
+                self.config = {"use_mask": False}
+
+            def encode_rp_intermediate(self, x):
+                return [x, x * 2]
+
+            def decode(self, content_feats, style_feats, use_mask=False, c_mask_path=None, s_mask_path=None):
+                calls["feats"] = content_feats
+                return content_feats[0]
+
+        assert adain_rp.SELastMultiScaleAdaINRPNet.test is adain_rp.MultiScaleAdaINRPNet.test   # inherited, patched
+        x = torch.arange(2 * 8 * 2 * 2, dtype=torch.float32).view(2, 8, 2, 2)
+        out = Sub().test(x, x)
+        want0 = x.view(2, 4, 2, 2, 2).permute(0, 2, 1, 3, 4).contiguous().view(2, 8, 2, 2)    # level 0 shuffled (:304-311)
+        assert torch.equal(calls["feats"][0], want0) and torch.equal(calls["feats"][1], x * 2)  # level 1 > _shuffle_layers
+        assert torch.equal(out, want0)
+    finally:
+        rpst.uninstall()
