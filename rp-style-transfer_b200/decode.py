@@ -67,7 +67,7 @@ def test_multiscale(self, content, style, iterations=0, bid=0, c_mask_path=None,
     with torch.no_grad():
         content_feats = self.encode_rp_intermediate(content)
         style_feats = self.encode_rp_intermediate(style)
-        if type(self).decode is decode_multiscale:
+        if getattr(type(self), "decode", decode_multiscale) is decode_multiscale:
             maps = None
             if self._shuffle:
                 maps = [None if idx > self._shuffle_layers else
