@@ -51,3 +51,27 @@ def test_ld_concat_decode(golden):
     g, m, cs, ss, _ = _stub(golden, "ldcat")
     with torch.no_grad():
         assert R.rel_l2(D.decode_ld_concat(m, cs, ss), g["ldcat.out"]) < TOL
+
+
+def test_multiscale_decode_with_masks_and_sort(golden):
+    """use_mask=True through the decode mirror: segment AdaIN at every level with the running decoder state
+    blended in the same call (`prev`), the sort permutation materialised first (the segment op takes dense
+    tensors).  Expected values restated with the oracle's seg_adain_batch on the reference's loop
+    (network/adain_rp.py:286-302, 313-319)."""
+    from rpst import decode as D
+    g, m, cs, ss, atts = _stub(golden, "multiscale")
+    n, _, h, w = cs[0].shape
+    cl = R.synth_labels(n, h, w, classes=3, block=4, seed=4400)
+    sl = R.synth_labels(n, h, w, classes=3, block=4, seed=5400)
+    for enc, a in zip(m.rp_shared_encoder, atts):
+        enc.attention_map = a.cuda()
+    m._sort = True
+    with torch.no_grad():
+        got = D.decode_multiscale(m, cs, ss, use_mask=True, c_mask_path=cl.cuda(), s_mask_path=sl.cuda())
+        m64 = m.double().cpu()
+        csd = [R.sort_by_weights(c.cpu().double(), a.double()) for c, a in zip(cs, atts)]
+        ssd = [R.sort_by_weights(s.cpu().double(), a.double()) for s, a in zip(ss, atts)]
+        st = m64.rp_decoder[0](R.seg_adain_batch(csd[-1], ssd[-1], cl, sl, dtype=torch.float64))
+        for i, l in enumerate((1, 0)):
+            st = m64.rp_decoder[i + 1](st + R.seg_adain_batch(csd[l], ssd[l], cl, sl, dtype=torch.float64))
+    assert R.rel_l2(got, st) < TOL
