@@ -95,3 +95,31 @@ def test_patched_test_respects_subclass_decode():
         assert torch.equal(out, want0)
     finally:
         rpst.uninstall()
+
+
+def test_label_map_loader_matches_the_reference_png_path(tmp_path):
+    """`test.py` hands PNG paths to the segment transform; the reference reads and resizes them with PIL
+    (network/base.py:448-449).  The rpst loader must produce the same label maps, and the validity table the
+    reference derives from them (`compute_label_info`, :421-439) must match the oracle's rule."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    import rpst
+    from oracle import restate as R
+    load_reference()
+    base = sys.modules["network.base"]
+    rng = np.random.default_rng(0)
+    big_c = np.kron(rng.integers(0, 5, (6, 8)), np.ones((16, 16))).astype(np.uint8)     # 96 x 128 blocky map
+    big_s = np.kron(rng.integers(0, 5, (5, 7)), np.ones((16, 16))).astype(np.uint8)     # 80 x 112
+    cp, sp = str(tmp_path / "c.png"), str(tmp_path / "s.png")
+    Image.fromarray(big_c).save(cp)
+    Image.fromarray(big_s).save(sp)
+    (wc, hc), (ws, hs) = (32, 24), (28, 20)                                              # feature resolutions (W, H)
+    c_seg, s_seg, label_set, label_indicator = base.get_segment_and_info(cp, sp, (wc, hc), (ws, hs))
+    got_c = rpst.load_label_map(cp, wc, hc, "cpu")
+    got_s = rpst.load_label_map(sp, ws, hs, "cpu")
+    assert got_c.dtype == torch.uint8 and tuple(got_c.shape) == (hc, wc)
+    assert np.array_equal(got_c.numpy(), c_seg) and np.array_equal(got_s.numpy(), s_seg)
+    valid = R.segment_label_validity(got_c, got_s)
+    for lab in label_set:
+        assert bool(label_indicator[lab]) == valid[int(lab)], lab
