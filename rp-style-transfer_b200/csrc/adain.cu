@@ -42,6 +42,27 @@ Tuning g_tuning;
 
 constexpr int kItemElems = 4096;  // one work item: 16 KiB of each tensor (256 threads x 4 float4)
 
+// Unsigned 32-bit division by a launch-time constant (Granlund-Montgomery round-up method): two multiplies and
+// shifts instead of the ~20-instruction software division; the ticket decode of the TMA kernel does up to eight
+// of them per batch on the producer's critical path.
+struct FastDiv {
+    uint32_t d, m, sh1, sh2;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d < 1u ? 1u : d;
+    uint32_t l = 0;
+    while ((1ull << l) < f.d) ++l;                                   // ceil(log2 d)
+    f.m = (uint32_t)((((1ull << l) - f.d) << 32) / f.d + 1ull);
+    f.sh1 = l < 1u ? l : 1u;
+    f.sh2 = l > 0u ? l - 1u : 0u;
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+    const uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 struct AdainParams {
     const float* content;
     const float* style;  // may be null
@@ -71,6 +92,7 @@ struct AdainParams {
     // takes its content from plane cmap[p] and its style from plane smap[p] (null = identity)
     const int* cmap;
     const int* smap;
+    FastDiv div_s, div_s1, div_s1a, div_a1, div_a;   // by ips, ips+1, ips+1+ipa, ipa+1, ipa (decode_tma)
     int group_merge_min_spp;   // TMA kernel: planes with at least this many statistics slots are merged by the whole group
     int merge_lead;            // TMA kernel: planes between a plane's MERGE ticket and its first APPLY ticket (1 .. lag-1)
 };
@@ -564,21 +586,21 @@ struct DecodedItem {
 
 __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int& kind, int64_t& plane, int& chunk) {
     const unsigned I = (unsigned)p.ips;    // statistics items per plane
-    if (p.stats_only) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
+    if (p.stats_only) { const unsigned q = fdiv(t, p.div_s); kind = 0; plane = q; chunk = (int)(t - q * I); return; }
     const unsigned P = (unsigned)p.planes, L = (unsigned)p.lag, Lm = (unsigned)p.merge_lead, A = (unsigned)p.ipa;
     // rounds: [S only] x (L-Lm), [S,M] x Lm, [S,M,A] x (P-L), [M,A] x (L-Lm), [A] x Lm
     unsigned n = (L - Lm) * I;
-    if (t < n) { kind = 0; plane = t / I; chunk = (int)(t % I); return; }
+    if (t < n) { const unsigned q = fdiv(t, p.div_s); kind = 0; plane = q; chunk = (int)(t - q * I); return; }
     t -= n; n = Lm * (I + 1);
     if (t < n) {
-        const unsigned j = t / (I + 1), u = t % (I + 1);
+        const unsigned j = fdiv(t, p.div_s1), u = t - j * (I + 1);
         if (u < I) { kind = 0; plane = (L - Lm) + j; chunk = (int)u; }
         else { kind = 2; plane = j; chunk = 0; }
         return;
     }
     t -= n; n = (P - L) * (I + 1 + A);
     if (t < n) {
-        const unsigned j = t / (I + 1 + A), u = t % (I + 1 + A);
+        const unsigned j = fdiv(t, p.div_s1a), u = t - j * (I + 1 + A);
         if (u < I) { kind = 0; plane = L + j; chunk = (int)u; }
         else if (u == I) { kind = 2; plane = Lm + j; chunk = 0; }
         else { kind = 1; plane = j; chunk = (int)(u - I - 1); }
@@ -586,13 +608,14 @@ __device__ __forceinline__ void decode_tma(unsigned t, const AdainParams& p, int
     }
     t -= n; n = (L - Lm) * (A + 1);
     if (t < n) {
-        const unsigned j = t / (A + 1), u = t % (A + 1);
+        const unsigned j = fdiv(t, p.div_a1), u = t - j * (A + 1);
         if (u == 0) { kind = 2; plane = (P - L + Lm) + j; chunk = 0; }
         else { kind = 1; plane = (P - L) + j; chunk = (int)(u - 1); }
         return;
     }
     t -= n;
-    kind = 1; plane = (P - Lm) + t / A; chunk = (int)(t % A);
+    const unsigned q = fdiv(t, p.div_a);
+    kind = 1; plane = (P - Lm) + q; chunk = (int)(t - q * A);
 }
 
 // Plane merge by a whole consumer group (128 threads), used by the TMA kernel's MERGE items.  A plane of
@@ -1332,6 +1355,11 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     }
     p.ipa = (use_tma && !p.stats_only && p.prev == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
     p.ips = (use_tma && p.style == nullptr && g_tuning.twin_apply) ? (p.ipp + 1) / 2 : p.ipp;
+    p.div_s = make_fastdiv((uint32_t)p.ips);
+    p.div_s1 = make_fastdiv((uint32_t)p.ips + 1u);
+    p.div_s1a = make_fastdiv((uint32_t)p.ips + 1u + (uint32_t)p.ipa);
+    p.div_a1 = make_fastdiv((uint32_t)p.ipa + 1u);
+    p.div_a = make_fastdiv((uint32_t)p.ipa);
     const int64_t total = p.stats_only ? p.planes * p.ips : p.planes * ((int64_t)p.ips + p.ipa + (use_tma ? 1 : 0));
     RPST_CHECK_ARG(total < (1ll << 31), "adain: too many work items (%lld); split the call", (long long)total);
     p.total_items = (unsigned)total;
