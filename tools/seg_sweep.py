@@ -12,7 +12,7 @@ peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEAS
 for flush in (4,):
   for lag_mib in [int(a) for a in sys.argv[1:]] or [24, 32, 48, 64, 96, 128, 256]:
     rpst.set_tuning("seg_lag_bytes", lag_mib << 20)
-    for _ in range(2):
+    for _ in range(6):   # the first configuration of a fresh process needs a long warm-up (clock ramp, lazy kernel load)
         rpst.seg_adain_batch(c, s, cl, sl)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
