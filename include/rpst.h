@@ -90,6 +90,12 @@ RPST_API int rpst_adain_fwd_mapped(const float* content, const float* style, con
                           const int32_t* content_map, const int32_t* style_map, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Test hook (no data touched): the ticket schedule the TMA-staged AdaIN kernel walks for a call shape.
+ * info[5] (host) = {tickets, statistics items per plane, apply items per plane, lag, merge lead};
+ * tickets (device, [max_tickets,3] int32, may be NULL) = (kind, plane, chunk), kind 0 statistics / 1 apply / 2 merge. */
+RPST_API int rpst_debug_adain_schedule(int64_t planes, int64_t hw, int has_style, int has_prev, int stats_only,
+                              int32_t* tickets, int64_t max_tickets, int64_t* info, void* stream);
+
 /* Backward of rpst_adain_fwd w.r.t. content and style (autograd gives this to the reference for
  * free; gradients reach the shared RP encoder through both arguments, SURVEY.md §7 hard part 7).
  *   grad_out [n,c,hw]; saved_stats from the forward; grad_content / grad_style [n,c,hw]

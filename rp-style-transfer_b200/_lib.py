@@ -31,6 +31,7 @@ SIGNATURES = {
     "rpst_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_adain_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
     "rpst_adain_fwd_mapped": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, c_size_t, P]),
+    "rpst_debug_adain_schedule": (c_int, [c_int64, c_int64, c_int, c_int, c_int, P, c_int64, P, P]),
     "rpst_adain_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_adain_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "rpst_plane_affine": (c_int, [P, P, P, P, c_int64, c_int64, P]),

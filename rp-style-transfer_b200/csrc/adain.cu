@@ -1326,15 +1326,9 @@ int launch_tma_variant2(const AdainParams& p, cudaStream_t stream) {
     return RPST_OK;
 }
 
-template <int VEC>
-int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    const PipeLayout l = pipe_layout(p.planes, p.hw);
-    if (ws == nullptr || ws_bytes < l.total) {
-        set_error("adain: workspace too small (%zu < %zu bytes)", ws_bytes, l.total);
-        return RPST_ERR_WORKSPACE;
-    }
-    RPST_CHECK_ARG(aligned16(ws), "adain: workspace must be 16-byte aligned");
-    char* base = static_cast<char*>(ws);
+// Item geometry and ticket schedule of the pipelined kernels for one call (host side): chunks per plane, lag,
+// merge lead, twin items, the decode's division constants.  Returns the number of tickets.
+int64_t plan_schedule(AdainParams& p, bool use_tma) {
     p.ipp = (int)((p.hw + kItemElems - 1) / kItemElems);
     const int64_t plane_bytes = p.hw * (int64_t)sizeof(float);
     // planes of >= 4 MiB: the statistics -> merge -> apply chain (>= 3 dependent global round trips of ~4.5 us
@@ -1344,7 +1338,6 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     int64_t lag = (lag_bytes + plane_bytes - 1) / plane_bytes;
     if (lag < 3) lag = 3;
     p.lag = (int)(lag < p.planes ? lag : p.planes);
-    const bool use_tma = VEC == 4 && g_tuning.path == 0;
     p.slot_elems = use_tma ? kTmaSlotElems : kItemElems;
     p.spp = (int)((p.hw + p.slot_elems - 1) / p.slot_elems);
     {
@@ -1360,7 +1353,20 @@ int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     p.div_s1a = make_fastdiv((uint32_t)p.ips + 1u + (uint32_t)p.ipa);
     p.div_a1 = make_fastdiv((uint32_t)p.ipa + 1u);
     p.div_a = make_fastdiv((uint32_t)p.ipa);
-    const int64_t total = p.stats_only ? p.planes * p.ips : p.planes * ((int64_t)p.ips + p.ipa + (use_tma ? 1 : 0));
+    return p.stats_only ? p.planes * p.ips : p.planes * ((int64_t)p.ips + p.ipa + (use_tma ? 1 : 0));
+}
+
+template <int VEC>
+int launch_pipe(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    const PipeLayout l = pipe_layout(p.planes, p.hw);
+    if (ws == nullptr || ws_bytes < l.total) {
+        set_error("adain: workspace too small (%zu < %zu bytes)", ws_bytes, l.total);
+        return RPST_ERR_WORKSPACE;
+    }
+    RPST_CHECK_ARG(aligned16(ws), "adain: workspace must be 16-byte aligned");
+    char* base = static_cast<char*>(ws);
+    const bool use_tma = VEC == 4 && g_tuning.path == 0;
+    const int64_t total = plan_schedule(p, use_tma);
     RPST_CHECK_ARG(total < (1ll << 31), "adain: too many work items (%lld); split the call", (long long)total);
     p.total_items = (unsigned)total;
     p.ticket = reinterpret_cast<unsigned*>(base);
@@ -1446,6 +1452,18 @@ int launch_bwd(BwdParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     adain_bwd_pipe_kernel<VEC><<<(int)grid, kPipeThreads, 0, stream>>>(p);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
+}
+
+// Schedule dump for tests: ticket t -> (kind, plane, chunk) through the REAL decode of the TMA kernel.
+__global__ void schedule_dump_kernel(AdainParams p, int32_t* out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.total_items) return;
+    int kind = -1, chunk = 0;
+    int64_t plane = 0;
+    decode_tma(t, p, kind, plane, chunk);
+    out[3 * (size_t)t + 0] = kind;
+    out[3 * (size_t)t + 1] = (int32_t)plane;
+    out[3 * (size_t)t + 2] = chunk;
 }
 
 int run_adain(AdainParams p, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -1568,6 +1586,30 @@ int adain_fwd_impl(const float* content, const float* style, const float* prev, 
     return run_adain(p, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 }  // namespace
+
+// Test hook: the ticket schedule the TMA kernel would walk for this call shape.  info = {tickets, stats items
+// per plane, apply items per plane, lag, merge lead}; tickets [max_tickets,3] receives (kind, plane, chunk) with
+// kind 0 statistics, 1 apply, 2 merge.  Used by tests/test_schedule_gpu.py to check the schedule's invariants
+// for shapes that no data test covers.
+extern "C" int rpst_debug_adain_schedule(int64_t planes, int64_t hw, int has_style, int has_prev, int stats_only,
+                                         int32_t* tickets, int64_t max_tickets, int64_t* info, void* stream) {
+    RPST_CHECK_ARG(planes > 0 && hw > 0 && info != nullptr, "debug_schedule: bad arguments");
+    AdainParams p{};
+    p.planes = planes; p.hw = hw; p.channels = 1; p.stats_only = stats_only;
+    p.content = reinterpret_cast<const float*>(16);            // only null-ness is inspected
+    p.style = has_style ? reinterpret_cast<const float*>(16) : nullptr;
+    p.prev = has_prev ? reinterpret_cast<const float*>(16) : nullptr;
+    const int64_t total = plan_schedule(p, true);
+    RPST_CHECK_ARG(total < (1ll << 31), "debug_schedule: too many tickets");
+    p.total_items = (unsigned)total;
+    info[0] = total; info[1] = p.ips; info[2] = p.ipa; info[3] = p.lag; info[4] = p.merge_lead;
+    if (tickets != nullptr) {
+        RPST_CHECK_ARG(max_tickets >= total, "debug_schedule: ticket buffer too small (%lld < %lld)", (long long)max_tickets, (long long)total);
+        schedule_dump_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, tickets);
+        RPST_CUDA(cudaGetLastError());
+    }
+    return RPST_OK;
+}
 
 extern "C" size_t rpst_adain_bwd_workspace_bytes(int64_t n, int64_t c, int64_t hw) {
     if (n <= 0 || c <= 0 || hw <= 0) return 256;
