@@ -155,6 +155,12 @@ RPST_API int rpst_seg_adain_fwd(const float* content, const float* style, const 
                        int64_t hw_c, int64_t hw_s, float eps, int32_t* label_info, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Test hook: ticket schedule of the segment kernel (see rpst_debug_adain_schedule).  info[5] = {tickets, content
+ * statistics items, style statistics items, apply items per plane, lag}; kind 0 content statistics, 1 style
+ * statistics, 2 apply, 3 merge. */
+RPST_API int rpst_debug_seg_schedule(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s, int has_prev, int32_t* tickets,
+                            int64_t max_tickets, int64_t* info, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a12 cal_dist(A, B)                                                  network/base.py:349-360
  *   a [d,m], b [d,n] (d-dimensional column vectors) -> out [m,n] = |a_i|^2 + |b_j|^2 - 2 a_i.b_j

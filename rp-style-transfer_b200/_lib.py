@@ -40,6 +40,7 @@ SIGNATURES = {
     "rpst_plane_affine2": (c_int, [P, P, P, P, P, P, c_int64, c_int64, P]),
     "rpst_pair_loss_bwd": (c_int, [P, P, P, P, c_int, c_int, P, c_int64, c_int64, P]),
     "rpst_seg_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "rpst_debug_seg_schedule": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, P, c_int64, P, P]),
     "rpst_pairwise_sqdist_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_pairwise_sqdist": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, c_size_t, P]),
     "rpst_mrf_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),

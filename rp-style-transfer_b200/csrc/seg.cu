@@ -1015,7 +1015,56 @@ int64_t adain_tuning_value(const char* name);
 
 }  // namespace rpst
 
+namespace rpst {
+namespace {
+// item geometry and ticket schedule of seg_tma_kernel for one call (q.n, q.channels, q.hw_c, q.hw_s set); returns the ticket count
+int64_t seg_plan_schedule(SegTmaParams& q, bool has_prev) {
+    const int64_t planes = q.n * q.channels;
+    q.ic = (int)((q.hw_c + kSegItemElems - 1) / kSegItemElems);
+    q.is = (int)((q.hw_s + kSegItemElems - 1) / kSegItemElems);
+    q.imax = q.ic > q.is ? q.ic : q.is;
+    q.apply_elems = has_prev ? kSegPrevElems : kSegItemElems;
+    q.ia = (int)((q.hw_c + q.apply_elems - 1) / q.apply_elems);
+    const int64_t plane_bytes = q.hw_c * (int64_t)sizeof(float);
+    int64_t lag = (adain_tuning_value("seg_lag_bytes") + plane_bytes - 1) / plane_bytes;
+    if (lag < 3) lag = 3;
+    q.lag = (int)(lag < planes ? lag : planes);
+    return planes * ((int64_t)q.ic + q.is + 1 + q.ia);
+}
+
+__global__ void seg_schedule_dump_kernel(SegTmaParams p, int32_t* out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.total_items) return;
+    int kind = -1, chunk = 0;
+    int64_t plane = 0;
+    seg_decode(t, p, kind, plane, chunk);
+    out[3 * (size_t)t + 0] = kind;
+    out[3 * (size_t)t + 1] = (int32_t)plane;
+    out[3 * (size_t)t + 2] = chunk;
+}
+}  // namespace
+}  // namespace rpst
+
 using namespace rpst;
+
+// Test hook, see rpst_debug_adain_schedule: kind 0 content statistics, 1 style statistics, 2 apply, 3 merge;
+// info = {tickets, content items, style items, apply items, lag}.
+extern "C" int rpst_debug_seg_schedule(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s, int has_prev, int32_t* tickets,
+                                       int64_t max_tickets, int64_t* info, void* stream) {
+    RPST_CHECK_ARG(n > 0 && c > 0 && hw_c > 0 && hw_s > 0 && info != nullptr, "debug_seg_schedule: bad arguments");
+    SegTmaParams q{};
+    q.n = n; q.channels = c; q.hw_c = hw_c; q.hw_s = hw_s;
+    const int64_t total = seg_plan_schedule(q, has_prev != 0);
+    RPST_CHECK_ARG(total < (1ll << 31), "debug_seg_schedule: too many tickets");
+    q.total_items = (unsigned)total;
+    info[0] = total; info[1] = q.ic; info[2] = q.is; info[3] = q.ia; info[4] = q.lag;
+    if (tickets != nullptr) {
+        RPST_CHECK_ARG(max_tickets >= total, "debug_seg_schedule: ticket buffer too small");
+        seg_schedule_dump_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, tickets);
+        RPST_CUDA(cudaGetLastError());
+    }
+    return RPST_OK;
+}
 
 extern "C" size_t rpst_seg_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     if (n <= 0 || c <= 0) return 256;
@@ -1082,17 +1131,8 @@ extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, cons
         const int64_t planes = n * c;
         seg_shift_kernel<<<(unsigned)((planes * 2 * kLabels + 255) / 256), 256, 0, st>>>(q);
         RPST_CUDA(cudaGetLastError());
-        q.ic = (int)((hw_c + kSegItemElems - 1) / kSegItemElems);
-        q.is = (int)((hw_s + kSegItemElems - 1) / kSegItemElems);
-        q.imax = q.ic > q.is ? q.ic : q.is;
-        q.apply_elems = prev ? kSegPrevElems : kSegItemElems;
-        q.ia = (int)((hw_c + q.apply_elems - 1) / q.apply_elems);
-        const int64_t plane_bytes = hw_c * (int64_t)sizeof(float);
         q.flush_mode = (int)adain_tuning_value("seg_flush");
-        int64_t lag = (adain_tuning_value("seg_lag_bytes") + plane_bytes - 1) / plane_bytes;
-        if (lag < 3) lag = 3;
-        q.lag = (int)(lag < planes ? lag : planes);
-        const int64_t total = planes * ((int64_t)q.ic + q.is + 1 + q.ia);
+        const int64_t total = seg_plan_schedule(q, prev != nullptr);
         RPST_CHECK_ARG(total < (1ll << 31), "seg_adain: too many work items (%lld); split the call", (long long)total);
         q.total_items = (unsigned)total;
         const int64_t groups = adain_tuning_value("seg_groups");

@@ -54,3 +54,41 @@ def test_schedule_invariants(planes, hw, has_style, has_prev, stats_only):
     # keeps the content of `lag` planes between its two reads
     ahead = np.minimum(np.arange(planes) + lag - 1, planes - 1)
     assert (last_stat[ahead] < first_apply).all()
+
+
+def dump_seg(n, c, hw_c, hw_s, has_prev):
+    import rpst
+    L = rpst._lib.lib()
+    info = (ctypes.c_int64 * 5)()
+    rpst._lib.check(L.rpst_debug_seg_schedule(n, c, hw_c, hw_s, has_prev, None, 0, info, None))
+    total = int(info[0])
+    buf = torch.empty(total, 3, dtype=torch.int32, device="cuda")
+    rpst._lib.check(L.rpst_debug_seg_schedule(n, c, hw_c, hw_s, has_prev, buf.data_ptr(), total, info,
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return buf.cpu().numpy(), [int(v) for v in info]
+
+
+@pytest.mark.parametrize("n,c", [(1, 1), (1, 2), (2, 3), (1, 40), (3, 11)])
+@pytest.mark.parametrize("hw_c,hw_s", [(4096, 4096), (65536, 40000), (90000, 262144), (2097152, 2097152)])
+@pytest.mark.parametrize("has_prev", [0, 1])
+def test_seg_schedule_invariants(n, c, hw_c, hw_s, has_prev):
+    """Segment kernel: content statistics (0), style statistics (1), merge (3), apply (2) of every plane exactly
+    once, statistics < merge < apply per plane, apply trailing by the lag."""
+    t, (total, ic, is_, ia, lag) = dump_seg(n, c, hw_c, hw_s, has_prev)
+    planes = n * c
+    kind, plane, chunk = t[:, 0], t[:, 1], t[:, 2]
+    idx = np.arange(total)
+    assert ic == -(-hw_c // 4096) and is_ == -(-hw_s // 4096) and ia == -(-hw_c // (2048 if has_prev else 4096))
+    assert total == planes * (ic + is_ + 1 + ia) and set(np.unique(kind)) == {0, 1, 2, 3}
+    for k, per in ((0, ic), (1, is_), (2, ia), (3, 1)):
+        sel = kind == k
+        assert sel.sum() == planes * per
+        assert np.array_equal(plane[sel], np.repeat(np.arange(planes), per))
+        assert np.array_equal(chunk[sel], np.tile(np.arange(per), planes) if k != 3 else np.zeros(planes, dtype=np.int32))
+    last_stat = np.array([idx[(kind <= 1) & (plane == p)].max() for p in range(planes)])
+    merge_at = np.array([idx[(kind == 3) & (plane == p)][0] for p in range(planes)])
+    first_apply = np.array([idx[(kind == 2) & (plane == p)].min() for p in range(planes)])
+    assert (last_stat < merge_at).all() and (merge_at < first_apply).all()
+    ahead = np.minimum(np.arange(planes) + lag - 1, planes - 1)
+    assert (last_stat[ahead] < first_apply).all()
