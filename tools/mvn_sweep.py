@@ -13,12 +13,11 @@ def t(fn):
     for _ in range(10): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / 10
-for mb, lag, lead in [(1, 32, 0), (1, 32, 8), (1, 28, 0), (1, 24, 0), (1, 24, 8), (1, 20, 0), (1, 16, 0), (0, 32, 0)]:
-    rpst.set_tuning("adain_merge_mailbox", mb)
+for lag, lead in [(32, 0), (32, 8), (28, 0), (24, 0), (24, 8), (20, 0), (16, 0), (40, 0)]:
     rpst.set_tuning("adain_lag_bytes", lag << 20)
-    rpst.set_tuning("adain_merge_lead", lead)
+    rpst.set_tuning("adain_merge_lead", lead)      # 0 = lag / 2
     tm = t(lambda: rpst.mean_variance_norm(x))
     ta = t(lambda: rpst.adaptive_instance_normalization(x, s))
     tb = t(lambda: rpst.adain_blend(s, x, s))
-    print(json.dumps({"mailbox": mb, "lag_MiB": lag, "lead": lead, "mvn_GBs": round(2 * E / tm / 1e6), "adain_GBs": round(3 * E / ta / 1e6),
+    print(json.dumps({"lag_MiB": lag, "lead": lead, "mvn_GBs": round(2 * E / tm / 1e6), "adain_GBs": round(3 * E / ta / 1e6),
                       "blend_GBs": round(4 * E / tb / 1e6)}), flush=True)
