@@ -12,6 +12,7 @@ plus the fused forms the reference spells as two ops:
 """
 from __future__ import annotations
 
+import functools
 from typing import Optional, Tuple
 
 import torch
@@ -25,6 +26,44 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _cuda_tensors(values):
+    for v in values:
+        if isinstance(v, torch.Tensor):
+            if v.is_cuda:
+                yield v
+        elif isinstance(v, (list, tuple)):
+            for w in v:
+                if isinstance(w, torch.Tensor) and w.is_cuda:
+                    yield w
+
+
+def device_guard(fn):
+    """Entry-point decorator: librpst launches on the CURRENT device and stream, so every tensor argument must
+    live on one device and the call runs with that device current (the reference's torch ops follow their
+    tensors' device; a model on cuda:1 must keep working while cuda:0 is current)."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for t in _cuda_tensors(args):
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise RuntimeError(f"rpst.{fn.__name__}: tensor arguments live on different devices ({dev} and {t.device})")
+        if kwargs:
+            for t in _cuda_tensors(kwargs.values()):
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise RuntimeError(f"rpst.{fn.__name__}: tensor arguments live on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"rpst: `{name}` must be a CUDA tensor (there is no CPU path)")
@@ -33,7 +72,8 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
-_DIRECT_MAX_HW = 16384   # planes up to this size take the register-resident kernel: no workspace needed
+_DIRECT_MAX_HW = 16384        # vectorised register-resident kernel: hw % 4 == 0, every pointer 16-byte aligned
+_DIRECT_MAX_HW_SCALAR = 4096  # scalar register-resident kernel (odd plane sizes / 4-byte aligned views)
 _tiny_ws = {}
 
 
@@ -41,10 +81,19 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def _plane_workspace(query, args, hw: int, device) -> torch.Tensor:
-    """Workspace for the plane kernels; small planes never touch it, so a cached 256-byte buffer is
-    passed and the size query is skipped (config #1 is launch-latency bound, every host us counts)."""
-    if hw <= _DIRECT_MAX_HW:
+def _goes_direct(hw: int, tensors) -> bool:
+    """Mirror of the dispatch in csrc/adain.cu (`run_adain`, `rpst_adain_bwd`): the workspace-free direct
+    kernel serves planes <= 4096 elements always, and <= 16384 only on the 128-bit path."""
+    if hw <= _DIRECT_MAX_HW_SCALAR:
+        return True
+    return hw <= _DIRECT_MAX_HW and hw % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in tensors)
+
+
+def _plane_workspace(query, args, hw: int, device, tensors=()) -> torch.Tensor:
+    """Workspace for the plane kernels; planes that are certain to take the register-resident kernel never
+    touch it, so a cached 256-byte buffer is passed and the size query is skipped (config #1 is
+    launch-latency bound, every host us counts).  Everything else asks the library."""
+    if _goes_direct(hw, tensors):
         key = (device.type, device.index)
         ws = _tiny_ws.get(key)
         if ws is None:
@@ -64,7 +113,7 @@ def _stats_raw(feat: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tens
     mean = torch.empty(n * c, dtype=torch.float32, device=feat.device)
     std = torch.empty_like(mean)
     L = _lib.lib()
-    ws = _plane_workspace(L.rpst_stats_workspace_bytes, (n * c, hw), hw, feat.device)
+    ws = _plane_workspace(L.rpst_stats_workspace_bytes, (n * c, hw), hw, feat.device, (feat,))
     _lib.check(L.rpst_stats_nchw(feat.data_ptr(), n * c, hw, eps, mean.data_ptr(), std.data_ptr(),
                                  ws.data_ptr(), ws.numel(), _stream()))
     return mean, std
@@ -75,7 +124,9 @@ def _adain_raw(content, style, prev, out, out_batch_stride, eps, want_saved):
     hw = content[0, 0].numel() if content.numel() else 0
     saved = torch.empty(n * c, 4, dtype=torch.float32, device=content.device) if want_saved else None
     L = _lib.lib()
-    ws = _plane_workspace(L.rpst_adain_workspace_bytes, (n, c, hw), hw, content.device)
+    ws = _plane_workspace(L.rpst_adain_workspace_bytes, (n, c, hw), hw, content.device, (content, style, prev, out))
+    if out_batch_stride % 4:
+        ws = _workspace(L.rpst_adain_workspace_bytes(n, c, hw), content.device)
     _lib.check(L.rpst_adain_fwd(content.data_ptr(), _ptr(style), _ptr(prev), out.data_ptr(), n, c, hw,
                                 out_batch_stride, eps, _ptr(saved), ws.data_ptr(), ws.numel(), _stream()))
     return saved
@@ -87,7 +138,8 @@ def _adain_bwd_raw(grad_out, content, style, saved, need_style):
     dc = torch.empty_like(content)
     ds = torch.empty_like(content) if need_style else None
     L = _lib.lib()
-    ws = _plane_workspace(L.rpst_adain_bwd_workspace_bytes, (n, c, hw), hw, content.device)
+    ws = _plane_workspace(L.rpst_adain_bwd_workspace_bytes, (n, c, hw), hw, content.device,
+                          (grad_out, content, style if need_style else None, dc, ds))
     _lib.check(L.rpst_adain_bwd(grad_out.data_ptr(), content.data_ptr(), _ptr(style) if need_style else None,
                                 saved.data_ptr(), dc.data_ptr(), _ptr(ds), n, c, hw,
                                 ws.data_ptr(), ws.numel(), _stream()))
@@ -106,12 +158,15 @@ class _AdaINFn(torch.autograd.Function):
         saved = _adain_raw(content, style, prev, out, c * hw, EPS, need_grad)
         if need_grad:
             ctx.save_for_backward(content, style if style is not None else content, saved)
+        ctx.only_prev = not need_grad      # frozen encoder / detached features: only the decoder state carries grad
         ctx.has_style = style is not None
         ctx.has_prev = prev is not None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.only_prev:
+            return None, None, (grad_out if ctx.has_prev else None)
         content, style, saved = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         need_style = ctx.has_style and ctx.needs_input_grad[1]
@@ -121,6 +176,7 @@ class _AdaINFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------ public API
+@device_guard
 def calc_mean_std(feat: torch.Tensor, eps: float = EPS) -> Tuple[torch.Tensor, torch.Tensor]:
     """Drop-in for network/base.py:399 — returns (mean, std), both [N,C,1,1]."""
     size = feat.size()
@@ -169,6 +225,7 @@ def _adain_nograd(content, style, prev):
     return out
 
 
+@device_guard
 def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/base.py:410."""
     assert (content_feat.size() == style_feat.size())
@@ -179,6 +236,7 @@ def adaptive_instance_normalization(content_feat: torch.Tensor, style_feat: torc
     return _AdaINFn.apply(c, s, None)
 
 
+@device_guard
 def adain_blend(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """`prev + AdaIN(content_feat, style_feat)` in one pass (network/adain_rp.py:300-301)."""
     assert (content_feat.size() == style_feat.size())
@@ -189,6 +247,7 @@ def adain_blend(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torc
     return _AdaINFn.apply(c, s, p)
 
 
+@device_guard
 def adain_concat(prev: torch.Tensor, content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """`torch.cat([prev, AdaIN(content_feat, style_feat)], dim=1)` with the AdaIN half written
     straight into the channel slice of the result (network/adain_rp.py:793).  Inference only."""
@@ -234,6 +293,7 @@ def compose_maps(first: Optional[torch.Tensor], then: Optional[torch.Tensor]) ->
     return first[then.long()].contiguous()
 
 
+@device_guard
 def adain_mapped(content_feat: torch.Tensor, style_feat: torch.Tensor, content_map: Optional[torch.Tensor] = None,
                  style_map: Optional[torch.Tensor] = None, prev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`[prev +] AdaIN(content_feat.flatten(0,1)[content_map], style_feat.flatten(0,1)[style_map])` without
@@ -260,12 +320,13 @@ def adain_mapped(content_feat: torch.Tensor, style_feat: torch.Tensor, content_m
         return _AdaINFn.apply(cg.contiguous(), sg.contiguous(), p)
     out = torch.empty_like(c)
     L = _lib.lib()
-    ws = _plane_workspace(L.rpst_adain_workspace_bytes, (n, ch, hw), hw, c.device)
+    ws = _plane_workspace(L.rpst_adain_workspace_bytes, (n, ch, hw), hw, c.device, (c, s, p, out))
     _lib.check(L.rpst_adain_fwd_mapped(c.data_ptr(), s.data_ptr(), _ptr(p), out.data_ptr(), n, ch, hw, ch * hw, EPS,
                                        _ptr(cm), _ptr(sm), ws.data_ptr(), ws.numel(), _stream()))
     return out
 
 
+@device_guard
 def mean_variance_norm(feat: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/sanet.py:20."""
     assert feat.dim() == 4
@@ -275,6 +336,7 @@ def mean_variance_norm(feat: torch.Tensor) -> torch.Tensor:
     return _AdaINFn.apply(x, None, None)
 
 
+@device_guard
 def plane_affine(x: torch.Tensor, scale: torch.Tensor, shift: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[n,c,:,:] = x[n,c,:,:] * scale[n,c] (+ shift[n,c])."""
     x = _prep(x, "x")

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .functional import EPS, _prep, _stream, _workspace
+from .functional import EPS, _prep, _stream, _workspace, device_guard
 
 
 def _pair_stats_raw(x: torch.Tensor, y: torch.Tensor, eps: float, want_stats: bool):
@@ -67,11 +67,13 @@ def _pair(input: torch.Tensor, target: torch.Tensor, which: int) -> torch.Tensor
     return losses[which]
 
 
+@device_guard
 def calc_style_loss(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """Drop-in for the `calc_style_loss` methods (network/adain_rp.py:84-88)."""
     return _pair(input, target, 0)
 
 
+@device_guard
 def calc_content_loss(input: torch.Tensor, target: torch.Tensor, norm: bool = False) -> torch.Tensor:
     """Drop-in for `calc_content_loss` (network/sanet.py:226-230).  `norm=False` is a plain MSE with
     no statistics in it (network/adain_rp.py:81-82) and stays torch's own `mse_loss`."""
@@ -80,6 +82,7 @@ def calc_content_loss(input: torch.Tensor, target: torch.Tensor, norm: bool = Fa
     return _pair(input, target, 1)
 
 
+@device_guard
 def pair_statistics(input: torch.Tensor, target: torch.Tensor):
     """(style_loss, content_norm_loss, stats[N*C, 8]) from one pass; see include/rpst.h."""
     x, y = _prep(input, "input"), _prep(target, "target")

@@ -6,6 +6,29 @@ import torch
 from torch import nn
 
 from . import functional as F
+from .losses import _pair_stats_raw
+
+
+class _GateFn(torch.autograd.Function):
+    """out[n,c,:,:] = x[n,c,:,:] * gate[n,c] with both gradients from librpst: dx = g * gate (plane-affine kernel),
+    dgate[n,c] = sum_hw g*x = C_gx + HW*mean_g*mean_x (one pass of the pair-moments kernel over (g, x))."""
+
+    @staticmethod
+    def forward(ctx, x, gate):
+        ctx.save_for_backward(x, gate)
+        return F.plane_affine(x, gate)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gate = ctx.saved_tensors
+        g = g.contiguous()
+        dx = F.plane_affine(g, gate) if ctx.needs_input_grad[0] else None
+        dgate = None
+        if ctx.needs_input_grad[1]:
+            _, st = _pair_stats_raw(g, x, F.EPS, True)
+            hw = x[0, 0].numel()
+            dgate = (st[:, 6] + hw * st[:, 0] * st[:, 2]).view_as(gate)
+        return dx, dgate
 
 
 class SELayer(nn.Module):
@@ -31,7 +54,7 @@ class SELayer(nn.Module):
             mean, _ = F.calc_mean_std(x) if x.requires_grad else (F.calc_mean_std(x.detach())[0], None)
             y = self.fc(mean.view(b, c)).view(b, c, 1, 1)
             self.attention_map = y
-            return x * y.expand_as(x)
+            return _GateFn.apply(F._prep(x, "x"), y.contiguous())
         mean, _ = F.calc_mean_std(x)
         y = self.fc(mean.view(b, c)).view(b, c, 1, 1)
         self.attention_map = y

@@ -9,35 +9,46 @@ import torch
 from torch import nn
 
 from . import _lib
-from .functional import _prep, _ptr, _stream
+from .functional import _prep, _ptr, _stream, device_guard
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def packed_gemm(a: torch.Tensor, b: torch.Tensor, passes: int = 3, alpha: float = 1.0) -> torch.Tensor:
-    """alpha * a @ b.T for fp32 a [M,K], b [N,K] on tcgen05 (passes=3: bf16x3, fp32-grade)."""
-    a, b = _prep(a, "a"), _prep(b, "b")
+@device_guard
+def packed_gemm(a: torch.Tensor, b: torch.Tensor, passes: int = 3, alpha: float = 1.0,
+                row_add: torch.Tensor = None, col_add: torch.Tensor = None) -> torch.Tensor:
+    """alpha * a @ b.T (+ row_add[:, None] + col_add[None, :]) for fp32 a [M,K], b [N,K] on tcgen05
+    (passes=3: bf16x3, fp32-grade; 1: plain bf16).  `a` and `b` may be arbitrary 2-D strided views (a transposed
+    view costs nothing: the pack kernel reads through the strides)."""
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1]
+    for t, name in ((a, "a"), (b, "b")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise TypeError(f"rpst.packed_gemm: `{name}` must be a CUDA float32 tensor")
     m, k = a.shape
     n = b.shape[0]
     L = _lib.lib()
     na, nb_ = L.rpst_packed_operand_bytes(m, k), L.rpst_packed_operand_bytes(n, k)
-    ta = [_ws(na, a.device) for _ in range(2)]
-    tb = [_ws(nb_, a.device) for _ in range(2)]
-    _lib.check(L.rpst_pack_operand(a.data_ptr(), m, k, k, 1, None, ta[0].data_ptr(), ta[1].data_ptr(), _stream()))
-    _lib.check(L.rpst_pack_operand(b.data_ptr(), n, k, k, 1, None, tb[0].data_ptr(), tb[1].data_ptr(), _stream()))
+    lo = passes == 3
+    ta = [_ws(na, a.device) for _ in range(2 if lo else 1)]
+    tb = [_ws(nb_, a.device) for _ in range(2 if lo else 1)]
+    _lib.check(L.rpst_pack_operand(a.data_ptr(), m, k, a.stride(0), a.stride(1), None, ta[0].data_ptr(),
+                                   ta[1].data_ptr() if lo else None, _stream()))
+    _lib.check(L.rpst_pack_operand(b.data_ptr(), n, k, b.stride(0), b.stride(1), None, tb[0].data_ptr(),
+                                   tb[1].data_ptr() if lo else None, _stream()))
     out = torch.empty(m, n, dtype=torch.float32, device=a.device)
-    _lib.check(L.rpst_gemm_packed(ta[0].data_ptr(), ta[1].data_ptr(), tb[0].data_ptr(), tb[1].data_ptr(),
-                                  out.data_ptr(), m, n, k, n, passes, alpha, None, None, _stream()))
+    ra = None if row_add is None else _prep(row_add.reshape(-1), "row_add")
+    ca = None if col_add is None else _prep(col_add.reshape(-1), "col_add")
+    assert ra is None or ra.numel() == m
+    assert ca is None or ca.numel() == n
+    _lib.check(L.rpst_gemm_packed(ta[0].data_ptr(), ta[1].data_ptr() if lo else None, tb[0].data_ptr(),
+                                  tb[1].data_ptr() if lo else None, out.data_ptr(), m, n, k, n, passes, alpha,
+                                  _ptr(ra), _ptr(ca), _stream()))
     return out
 
 
-def cal_dist(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
-    """Drop-in for network/base.py:349 — A (d,m), B (d,n) column vectors -> (m,n) squared distances."""
-    A, B = _prep(A, "A"), _prep(B, "B")
-    assert A.dim() == 2 and B.dim() == 2 and A.shape[0] == B.shape[0]
+def _cal_dist_raw(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     d, m = A.shape
     n = B.shape[1]
     L = _lib.lib()
@@ -47,6 +58,39 @@ def cal_dist(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     return out
 
 
+class _CalDistFn(torch.autograd.Function):
+    """dist[i,j] = |a_i|^2 + |b_j|^2 - 2 a_i.b_j  =>  dA = 2 (A o rowsum(g) - B g^T), dB = 2 (B o colsum(g) - A g);
+    both products run on the tcgen05 GEMM block."""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        ctx.save_for_backward(A, B)
+        return _cal_dist_raw(A, B)
+
+    @staticmethod
+    def backward(ctx, g):
+        A, B = ctx.saved_tensors
+        g = g.contiguous()
+        dA = dB = None
+        if ctx.needs_input_grad[0]:
+            dA = 2.0 * (A * g.sum(1)[None, :] - packed_gemm(B, g))          # [d,n] x [m,n]^T
+        if ctx.needs_input_grad[1]:
+            dB = 2.0 * (B * g.sum(0)[None, :] - packed_gemm(A, g.t()))      # [d,m] x [n,m]^T
+        return dA, dB
+
+
+@device_guard
+def cal_dist(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """Drop-in for network/base.py:349 — A (d,m), B (d,n) column vectors -> (m,n) squared distances
+    (differentiable, like the reference's torch ops)."""
+    A, B = _prep(A, "A"), _prep(B, "B")
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[0] == B.shape[0]
+    if torch.is_grad_enabled() and (A.requires_grad or B.requires_grad):
+        return _CalDistFn.apply(A, B)
+    return _cal_dist_raw(A, B)
+
+
+@device_guard
 def mrf_match(content_feat: torch.Tensor, style_feat: torch.Tensor, k: int = 3, reverse: bool = False,
               want_affinity: bool = False, want_loss: bool = False, mean: str = "mean", precision: str = "fp32"):
     """Top-k matching of one content/style pair.  Returns (idx_dim0 [k,L], idx_dim1 [L,k], affinity|None, loss|None)
@@ -72,6 +116,7 @@ def mrf_match(content_feat: torch.Tensor, style_feat: torch.Tensor, k: int = 3, 
     return idx0, idx1, aff, (loss[0] if loss is not None else None)
 
 
+@device_guard
 def cal_affinity_map(content_feat, style_feat, k=3, reverse=False, c_mask=None, s_mask=None) -> torch.Tensor:
     """Drop-in for network/base.py:317 — the dense binary [HW,HW] affinity map."""
     return mrf_match(content_feat, style_feat, k, reverse, want_affinity=True)[2]
@@ -97,9 +142,9 @@ class _MRFLossFn(torch.autograd.Function):
         s = 2.0 * g / ctx.norm
         ga = gb = None
         if ctx.needs_input_grad[0]:
-            ga = (s * (a * aff.sum(1)[None, :] - b @ aff.t())).view_as(cf)
+            ga = (s * (a * aff.sum(1)[None, :] - packed_gemm(b, aff))).view_as(cf)        # b [c,L] x aff[i,:]
         if ctx.needs_input_grad[1]:
-            gb = (s * (b * aff.sum(0)[None, :] - a @ aff)).view_as(sf)
+            gb = (s * (b * aff.sum(0)[None, :] - packed_gemm(a, aff.t()))).view_as(sf)
         return ga, gb, None, None
 
 

@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .functional import _prep, _ptr, _stream, mean_variance_norm
+from .functional import _prep, _ptr, _stream, device_guard, mean_variance_norm
 
 PRECISION = {"fp32": 3, "bf16": 1}
 
@@ -27,6 +27,7 @@ def _group_ws(per_sample: int, b: int, device) -> torch.Tensor:
     return _ws(k * int(per_sample), device)
 
 
+@device_guard
 def cal_affinity_matrix(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/sanet.py:12 — [b,c,h,w] x2 -> [b,hw,hw] cosine affinity (differentiable)."""
     assert content_feat.size() == style_feat.size()
@@ -85,6 +86,7 @@ class _AttnFn(torch.autograd.Function):
         return dF, dG, dH, None
 
 
+@device_guard
 def attention_core(F: torch.Tensor, G: torch.Tensor, H: torch.Tensor, precision: str = "fp32", return_attn: bool = False):
     """softmax(F^T G) applied to H: F [b,c,hc,wc], G/H [b,c,hs,ws] -> [b,c,hc,wc] (network/sanet.py:85-94).
     Differentiable w.r.t. F, G and H (the attention matrix itself is returned detached)."""
@@ -102,7 +104,8 @@ def attention_core(F: torch.Tensor, G: torch.Tensor, H: torch.Tensor, precision:
 
 class _AffinityFn(torch.autograd.Function):
     """Differentiable cosine affinity (network/sanet.py:12-18): forward is the tcgen05 kernel; the backward
-    pass is two plain [C,L]x[L,L] library GEMMs and the normalisation's closed-form Jacobian."""
+    pass is two [C,L]x[L,L] products per sample on the same tcgen05 GEMM block (bf16x3) and the normalisation's
+    closed-form Jacobian."""
 
     @staticmethod
     def forward(ctx, content, style):
@@ -111,16 +114,49 @@ class _AffinityFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, daff):
+        from .mrf import packed_gemm
         content, style = ctx.saved_tensors
         b, c = content.shape[:2]
         cv, sv = content.reshape(b, c, -1), style.reshape(b, c, -1)
         nc, ns = cv.norm(dim=1, keepdim=True).clamp_min(1e-12), sv.norm(dim=1, keepdim=True).clamp_min(1e-12)
         ch, sh = cv / nc, sv / ns
-        dch = torch.bmm(sh, daff.transpose(1, 2))      # d c^[c,i] = sum_j s^[c,j] daff[i,j]
-        dsh = torch.bmm(ch, daff)                      # d s^[c,j] = sum_i c^[c,i] daff[i,j]
+        daff = daff.contiguous()
+        # d c^[c,i] = sum_j s^[c,j] daff[i,j] ;  d s^[c,j] = sum_i c^[c,i] daff[i,j]
+        dch = torch.stack([packed_gemm(sh[i], daff[i]) for i in range(b)])
+        dsh = torch.stack([packed_gemm(ch[i], daff[i].t()) for i in range(b)])
         dc = (dch - ch * (ch * dch).sum(1, keepdim=True)) / nc
         ds = (dsh - sh * (sh * dsh).sum(1, keepdim=True)) / ns
         return dc.view_as(content), ds.view_as(style)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM block (bias in the epilogue); dx = g W, dW = g^T x, db = colsum(g).
+    Used for f_psi's Linear(L -> L/16) — 550 GFLOP per sample at L = 16384 (network/sanet.py:34-39)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from .mrf import packed_gemm
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return packed_gemm(x, weight, col_add=bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .mrf import packed_gemm
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        dx = packed_gemm(g, weight.t()) if ctx.needs_input_grad[0] else None
+        dw = packed_gemm(g.t(), x.t()) if ctx.needs_input_grad[1] else None
+        db = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def _f_psi(al, x2d: torch.Tensor) -> torch.Tensor:
+    """The clamp MLP of AEAModule / AEALReluModule on [rows, L] affinity rows with the module's own parameters:
+    Linear(L -> L/16) on tensor cores, the rest (LeakyReLU, Linear(L/16 -> 1), sigmoid/tanh) is O(rows * L/16)."""
+    lin0 = al.f_psi[0]
+    hid = _LinearFn.apply(x2d.contiguous(), lin0.weight, lin0.bias)
+    return al.f_psi[3](al.f_psi[2](torch.nn.functional.leaky_relu(hid, 0.2)))
 
 
 class _ClampedAttnFn(torch.autograd.Function):
@@ -178,7 +214,7 @@ class AEAModule(nn.Module):
     def forward(self, x, f_x):
         # stand-alone use (the fused path is AdaptiveSANet.forward): same algebra on the module's own layers
         b, hw, c = x.size()
-        clamp_value = self.f_psi(x.view(b * hw, c)) * self.value_interval + self.from_value
+        clamp_value = _f_psi(self, x.reshape(b * hw, c)) * self.value_interval + self.from_value
         clamp_value = clamp_value.view(b, hw, 1)
         return torch.sigmoid(self.scale_value * (f_x - clamp_value)), clamp_value
 
@@ -203,7 +239,7 @@ class AEALReluModule(nn.Module):
 
     def forward(self, x, f_x):
         b, hw, c = x.size()
-        clamp_value = ((self.f_psi(x.view(b * hw, c)) + 1) / 2).view(b, hw, 1)
+        clamp_value = ((_f_psi(self, x.reshape(b * hw, c)) + 1) / 2).view(b, hw, 1)
         return self.clamp_sig(f_x - clamp_value), clamp_value
 
 
@@ -296,7 +332,7 @@ def _adaptive_forward_training(self, content, style, F, G, H):
     al = self.attention_layer
     assert al.f_psi[0].in_features == l, f"spatial_dims={al.f_psi[0].in_features} does not match H*W={l}"
     aff = _AffinityFn.apply(_prep(content, "content"), _prep(style, "style"))
-    z = al.f_psi(aff.view(b * l, l))
+    z = _f_psi(al, aff.view(b * l, l))
     clamp = z * al.value_interval + al.from_value if al.mode == 1 else (z + 1) / 2
     clamp = clamp.view(b, l)
     out = _ClampedAttnFn.apply(_prep(F, "F"), _prep(G, "G"), _prep(H, "H"), clamp.contiguous(), al.mode,

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .functional import EPS, _prep, _ptr, _stream, _workspace
+from .functional import EPS, _prep, _ptr, _stream, _workspace, device_guard
 
 LabelArg = Union[str, torch.Tensor, np.ndarray]
 
@@ -38,6 +38,7 @@ def load_label_map(src: LabelArg, width: int, height: int, device) -> torch.Tens
     return lab.to(device).contiguous()
 
 
+@device_guard
 def seg_adain_batch(content_feat: torch.Tensor, style_feat: torch.Tensor, c_labels: torch.Tensor,
                     s_labels: torch.Tensor, prev: Optional[torch.Tensor] = None, return_info: bool = False):
     """Batched segment AdaIN.  content [N,C,Hc,Wc], style [N,C,Hs,Ws], labels uint8 [N,Hc,Wc] /
@@ -70,6 +71,7 @@ def seg_adain_batch(content_feat: torch.Tensor, style_feat: torch.Tensor, c_labe
     return (out, info) if return_info else out
 
 
+@device_guard
 def adaptive_instance_normalization_with_segment(content_feat: torch.Tensor, style_feat: torch.Tensor,
                                                  content_seg_path: LabelArg, style_seg_path: LabelArg) -> torch.Tensor:
     """Drop-in for network/base.py:494 — (1,c,hc,wc), (1,c,hs,ws), two label maps (paths, arrays or
@@ -82,6 +84,7 @@ def adaptive_instance_normalization_with_segment(content_feat: torch.Tensor, sty
     return seg_adain_batch(content_feat, style_feat, cl[None], sl[None])
 
 
+@device_guard
 def do_mask_stylized(content_feat: torch.Tensor, style_feat: torch.Tensor, c_masks: Sequence[LabelArg],
                      s_masks: Sequence[LabelArg], prev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Replacement for the per-sample Python loop network/adain_rp.py:313-319: one launch for the

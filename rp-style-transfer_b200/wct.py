@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .functional import _prep, _ptr, _stream
+from .functional import _prep, _ptr, _stream, device_guard
 
 _METHODS = {"closed-form": 0, "original": 1}
 
@@ -31,16 +31,19 @@ def _sym_fn(A: torch.Tensor, want_sqrt: bool, want_inv: bool, diag_add: float = 
     return fix(rs), fix(ri)
 
 
+@device_guard
 def matrix_sqrt(A: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/wct_rp.py:25 (also accepts a batch [B,n,n])."""
     return _sym_fn(A, True, False)[0]
 
 
+@device_guard
 def matrix_inv_sqrt(A: torch.Tensor) -> torch.Tensor:
     """Drop-in for network/wct_rp.py:7."""
     return _sym_fn(A, False, True)[1]
 
 
+@device_guard
 def wct_fuse(content_feats: torch.Tensor, style_feats: torch.Tensor, method: str = "closed-form",
              precision: str = "fp32", return_transform: bool = False):
     """Batched `WCTRPNet.fuse`: [N,C,H,W] x [N,C,Hs,Ws] -> [N,C,H,W] fp32, inputs detached like the
@@ -60,6 +63,7 @@ def wct_fuse(content_feats: torch.Tensor, style_feats: torch.Tensor, method: str
     return (out, tr) if return_transform else out
 
 
+@device_guard
 def whiten_and_color(cF: torch.Tensor, sF: torch.Tensor, method: str = "closed-form") -> torch.Tensor:
     """Function form of network/wct_rp.py:82 — cF [C,HWc], sF [C,HWs] (any float dtype; the reference
     passes fp64) -> [C,HWc] in cF's dtype."""

@@ -330,3 +330,63 @@ def test_big_planes_group_merge_kernel(rpst, shape):
     cr, sr = cg[:, :2].contiguous().requires_grad_(), sg[:, :2].contiguous().requires_grad_()
     (rpst.adaptive_instance_normalization(cr, sr) * w[:, :2].cuda()).sum().backward()
     assert R.rel_l2(cr.grad, cd.grad) < 1e-4 and R.rel_l2(sr.grad, sd.grad) < 1e-4
+
+
+# ---- round-2 regressions --------------------------------------------------------------
+def _ref_adain_autograd(c, s):
+    """the reference formula (network/base.py:399-418) on tensors that keep their autograd graph"""
+    mu_c, sd_c = c.mean((2, 3), keepdim=True), (c.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    mu_s, sd_s = s.mean((2, 3), keepdim=True), (s.var((2, 3), keepdim=True) + 1e-5).sqrt()
+    return (c - mu_c) / sd_c * sd_s + mu_s
+
+
+# planes with 4096 < hw <= 16384 that cannot take the vectorised direct kernel (odd sizes, 4-byte aligned views)
+# go to the pipelined kernels and need the real workspace, forward and backward
+@pytest.mark.parametrize("shape", [(1, 2, 75, 75), (1, 2, 127, 127), (2, 3, 65, 65), (1, 2, 101, 101)])
+def test_mid_size_odd_planes_forward_backward(rpst, shape):
+    c, s = R.synth_features(shape, cfg=11)
+    prev = torch.randn(shape, generator=torch.Generator().manual_seed(3))
+    w = torch.randn(shape, generator=torch.Generator().manual_seed(4))
+    want = R.adain(c, s, dtype=torch.float64)
+    assert R.rel_l2(rpst.adaptive_instance_normalization(dev(c), dev(s)), want) < TIGHT
+    assert R.rel_l2(rpst.adain_blend(dev(prev), dev(c), dev(s)), want + prev.double()) < TIGHT
+    assert R.rel_l2(rpst.mean_variance_norm(dev(c)), R.mean_variance_norm(c, dtype=torch.float64)) < TIGHT
+    mean, std = rpst.calc_mean_std(dev(c))
+    wm, wsd = R.plane_stats(c, dtype=torch.float64)
+    assert R.rel_l2(mean, wm) < TIGHT and R.rel_l2(std, wsd) < TIGHT
+    cg, sg = dev(c).requires_grad_(), dev(s).requires_grad_()
+    gc, gs = torch.autograd.grad(rpst.adaptive_instance_normalization(cg, sg), (cg, sg), dev(w))
+    c64, s64 = c.double().requires_grad_(), s.double().requires_grad_()
+    rc, rs = torch.autograd.grad(_ref_adain_autograd(c64, s64), (c64, s64), w.double())
+    assert R.rel_l2(gc, rc) < 1e-4 and R.rel_l2(gs, rs) < 1e-4
+
+
+def test_offset_view_of_mid_size_plane(rpst):
+    """a +1-element view of a 96x96 plane is 4-byte aligned only: scalar pipelined path, real workspace"""
+    shape = (1, 2, 96, 96)
+    c, s = R.synth_features(shape, cfg=12)
+    n = c.numel()
+    cb, sb = torch.zeros(n + 1).cuda(), torch.zeros(n + 1).cuda()
+    cb[1:].copy_(c.reshape(-1)); sb[1:].copy_(s.reshape(-1))
+    cv, sv = cb[1:].view(shape), sb[1:].view(shape)
+    assert cv.data_ptr() % 16 != 0 and cv.is_contiguous()
+    want = R.adain(c, s, dtype=torch.float64)
+    assert R.rel_l2(rpst.adaptive_instance_normalization(cv, sv), want) < TIGHT
+    cg, sg = cv.detach().requires_grad_(), sv.detach().requires_grad_()
+    w = torch.randn(shape, generator=torch.Generator().manual_seed(6))
+    gc, _ = torch.autograd.grad(rpst.adaptive_instance_normalization(cg, sg), (cg, sg), dev(w))
+    c64, s64 = c.double().requires_grad_(), s.double().requires_grad_()
+    rc, _ = torch.autograd.grad(_ref_adain_autograd(c64, s64), (c64, s64), w.double())
+    assert R.rel_l2(gc, rc) < 1e-4
+
+
+def test_only_prev_requires_grad(rpst):
+    """frozen encoder / detached features: the decoder state alone carries grad through `prev + AdaIN(c, s)`"""
+    shape = (2, 3, 40, 40)
+    c, s = R.synth_features(shape, cfg=13)
+    prev = dev(torch.randn(shape, generator=torch.Generator().manual_seed(8))).requires_grad_()
+    out = rpst.adain_blend(prev, dev(c).detach(), dev(s).detach())
+    w = dev(torch.randn(shape, generator=torch.Generator().manual_seed(9)))
+    (gp,) = torch.autograd.grad(out, (prev,), w)
+    assert torch.equal(gp, w)
+    assert R.rel_l2(out, R.adain(c, s, dtype=torch.float64) + prev.detach().cpu().double()) < TIGHT

@@ -126,3 +126,15 @@ def test_mrf_loss_gradient_flows_through_the_distances(rpst):
     (got * 1.7).backward()
     assert abs(float(got.detach()) - float(want.detach())) / abs(float(want.detach())) < 1e-4
     assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4
+
+
+def test_cal_dist_is_differentiable(rpst):
+    """the reference's cal_dist is plain torch ops; the drop-in must not detach silently."""
+    g = torch.Generator().manual_seed(21)
+    a = torch.randn(24, 70, generator=g); b = torch.randn(24, 45, generator=g); w = torch.randn(70, 45, generator=g)
+    ag, bg = a.cuda().requires_grad_(), b.cuda().requires_grad_()
+    ga, gb = torch.autograd.grad(rpst.cal_dist(ag, bg), (ag, bg), w.cuda())
+    a64, b64 = a.double().requires_grad_(), b.double().requires_grad_()
+    dist = (a64 * a64).sum(0)[:, None] + (b64 * b64).sum(0)[None, :] - 2.0 * a64.t() @ b64   # network/base.py:349-360
+    ra, rb = torch.autograd.grad(dist, (a64, b64), w.double())
+    assert R.rel_l2(ga, ra) < 1e-4 and R.rel_l2(gb, rb) < 1e-4

@@ -28,3 +28,19 @@ def test_second_device_runs_every_kernel_family():
             assert R.rel_l2(rpst.attention_core(f.to(dev), k.to(dev), v.to(dev)).reshape(1, 32, -1), want_attn) < 1e-3
             assert R.rel_l2(rpst.wct_fuse(c[:, :, :32, :32].contiguous().to(dev), s[:, :, :32, :32].contiguous().to(dev)), want_wct) < 1e-3
             assert float(rpst.calc_style_loss(c.to(dev), s.to(dev))) > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+def test_tensors_on_a_non_current_device_need_no_device_context():
+    """a model on cuda:1 while cuda:0 is current must work like the reference's torch ops do."""
+    import rpst
+    torch.cuda.set_device(0)
+    c, s = R.synth_features((2, 4, 256, 256), cfg=71)
+    want = R.adain(c, s, dtype=torch.float64)
+    got = rpst.adaptive_instance_normalization(c.to("cuda:1"), s.to("cuda:1"))
+    assert got.device == torch.device("cuda:1") and R.rel_l2(got, want) < 2e-6
+    assert torch.cuda.current_device() == 0
+    small = rpst.adaptive_instance_normalization(c[:, :, :32, :32].contiguous().to("cuda:1"), s[:, :, :32, :32].contiguous().to("cuda:1"))
+    assert R.rel_l2(small, R.adain(c[:, :, :32, :32], s[:, :, :32, :32], dtype=torch.float64)) < 2e-6
+    with pytest.raises(RuntimeError, match="different devices"):
+        rpst.adaptive_instance_normalization(c.to("cuda:0"), s.to("cuda:1"))
