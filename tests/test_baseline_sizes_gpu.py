@@ -1,0 +1,191 @@
+"""Parity at the BASELINE.json config sizes and on the bf16 contract (VERDICT r1 "next" item 1).
+
+Contract (BASELINE.json north_star): transformed features within rel-L2 <= 1e-3 (fp32) or <= 1e-2 (bf16) of the
+reference path.  "Transformed features" of SANet are what the module returns (`out_conv(O) + content`,
+network/sanet.py:95-98), so the bf16 contract is asserted THROUGH the module on reference-like inputs
+(instance-normalised F / G).  The bare attention core has no temperature (network/sanet.py:90-91): with
+C = 512 the logits have sigma ~ 6-8, a 2^-9 operand rounding moves them by ~1e-2 absolute, and the core's own
+bf16 error is therefore a few 1e-2 — documented in DESIGN.md, asserted at 5e-2 in test_sanet_gpu.py.
+The gradient tolerance in bf16 mode (two more bf16 products behind the forward) is 5e-2 as well.
+
+Full-size cases are checked against an fp64 evaluation of a ROW SLICE (256 query positions): every attention row
+is independent (softmax over the style axis), so a slice is an exact sub-problem."""
+import pytest
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TOL32 = 1e-3
+TOL16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def rpst():
+    import rpst as m
+    return m
+
+
+def _mvn64(x):
+    b, c = x.shape[:2]
+    f = x.double().reshape(b, c, -1)
+    return (f - f.mean(2, keepdim=True)) / (f.var(2, keepdim=True) + 1e-5).sqrt()
+
+
+def _conv64(sd, name, x):   # 1x1 convolution on [b, c, l] in fp64
+    w = sd[name + ".weight"].double()
+    return torch.einsum("oc,ncl->nol", w.reshape(w.shape[0], w.shape[1]), x) + sd[name + ".bias"].double().reshape(1, -1, 1)
+
+
+def _sanet_rows_fp64(m, c, s, rows, clamp_mode=None):
+    """fp64 evaluation of (Adaptive)SANet.forward (network/sanet.py:82-99 / 114-138) restricted to the query
+    positions `rows`; returns [b, C, len(rows)]."""
+    sd = m.state_dict()
+    b, ch = c.shape[:2]
+    F = _conv64(sd, "f", _mvn64(c))[:, :, rows]                  # [b, C, R]
+    G = _conv64(sd, "g", _mvn64(s))                              # [b, C, L]
+    H = _conv64(sd, "h", s.double().reshape(b, ch, -1))
+    S = torch.softmax(torch.bmm(F.transpose(1, 2), G), dim=-1)   # [b, R, L]
+    if clamp_mode is not None:
+        al = m.attention_layer
+        cn = torch.nn.functional.normalize(c.double().reshape(b, ch, -1), dim=1)[:, :, rows]
+        sn = torch.nn.functional.normalize(s.double().reshape(b, ch, -1), dim=1)
+        aff = torch.bmm(cn.transpose(1, 2), sn)                  # [b, R, L]
+        z = torch.nn.functional.leaky_relu(aff @ sd["attention_layer.f_psi.0.weight"].double().t() +
+                                           sd["attention_layer.f_psi.0.bias"].double(), 0.2)
+        z = z @ sd["attention_layer.f_psi.2.weight"].double().t() + sd["attention_layer.f_psi.2.bias"].double()
+        if clamp_mode == "aea":
+            clamp = torch.sigmoid(z) * al.value_interval + al.from_value
+            S = torch.sigmoid(al.scale_value * (S - clamp))
+        else:
+            clamp = (torch.tanh(z) + 1) / 2
+            S = torch.softmax(torch.relu(S - clamp), dim=-1)
+    O = torch.bmm(H, S.transpose(1, 2))                          # [b, C, R]
+    return _conv64(sd, "out_conv", O) + c.double().reshape(b, ch, -1)[:, :, rows]
+
+
+# ---------------------------------------------------------------------------- bf16 contract (item 1a)
+@pytest.mark.parametrize("side", [32, 64])
+def test_sanet_module_bf16_contract(rpst, side):
+    """SANet(512) on relu5_1 / relu4_1 shapes of a 512^2 image, bf16 tensor-core operands: <= 1e-2 on the
+    transformed features; fp32-grade path <= 1e-3 on the same inputs."""
+    torch.manual_seed(0)
+    m = rpst.SANet(512).cuda()
+    c, s = R.synth_features((2, 512, side, side), cfg=41, device="cuda")
+    rows = torch.arange(0, side * side, max(1, side * side // 256), device="cuda")
+    with torch.no_grad():
+        want = _sanet_rows_fp64(m, c, s, rows)
+        got32 = m(c, s).reshape(2, 512, -1)[:, :, rows]
+        m.precision = "bf16"
+        got16 = m(c, s).reshape(2, 512, -1)[:, :, rows]
+    assert R.rel_l2(got32, want) < TOL32
+    assert R.rel_l2(got16, want) < TOL16, R.rel_l2(got16, want)
+
+
+def test_sanet_module_bf16_gradients(rpst):
+    """bf16 training step of the module: parameter and input gradients against fp64 autograd; the documented
+    gradient tolerance in bf16 mode is 5e-2 (forward contract 1e-2)."""
+    torch.manual_seed(5)
+    m = rpst.SANet(64).cuda()
+    m.precision = "bf16"
+    c, s = R.synth_features((2, 64, 24, 24), cfg=42, device="cuda", signed=True)
+    w = torch.randn(2, 64, 24, 24, device="cuda")
+    cg, sg = c.clone().requires_grad_(), s.clone().requires_grad_()
+    out = m(cg, sg)
+    (out * w).sum().backward()
+    sd = {k: v.detach().double().requires_grad_() for k, v in m.state_dict().items()}
+    c64, s64 = c.double().requires_grad_(), s.double().requires_grad_()
+
+    def mvn(x):
+        f = x.reshape(2, 64, -1)
+        return (f - f.mean(2, keepdim=True)) / (f.var(2, keepdim=True) + 1e-5).sqrt()
+    conv = lambda x, n: torch.einsum("oc,ncl->nol", sd[n + ".weight"].reshape(64, 64), x) + sd[n + ".bias"].reshape(1, -1, 1)
+    F, G, H = conv(mvn(c64), "f"), conv(mvn(s64), "g"), conv(s64.reshape(2, 64, -1), "h")
+    P = torch.softmax(torch.bmm(F.transpose(1, 2), G), dim=-1)
+    ref = (conv(torch.bmm(H, P.transpose(1, 2)), "out_conv") + c64.reshape(2, 64, -1)).reshape(2, 64, 24, 24)
+    (ref * w.double()).sum().backward()
+    assert R.rel_l2(out, ref) < TOL16
+    assert R.rel_l2(cg.grad, c64.grad) < 5e-2 and R.rel_l2(sg.grad, s64.grad) < 5e-2
+    for n, p in m.named_parameters():
+        assert R.rel_l2(p.grad, sd[n].grad) < 5e-2, n
+
+
+# ---------------------------------------------------------------------------- WCT bf16 (item 1b)
+@pytest.mark.parametrize("n,c,h,w", [(2, 64, 64, 64), (1, 256, 128, 128)])
+def test_wct_bf16_vs_oracle(rpst, n, c, h, w):
+    """`wct_fuse(precision="bf16")` (network/wct_rp.py:82-114,157-166) against the fp64 oracle at <= 1e-2."""
+    ct = torch.relu(torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(1)) + 0.5)
+    st = torch.relu(torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(2)) * 2 + 1)
+    mix = torch.randn(c, c, generator=torch.Generator().manual_seed(3)) / c ** 0.5
+    ct = torch.einsum("oc,nchw->nohw", mix, ct)
+    st = torch.einsum("oc,nchw->nohw", mix.t(), st)
+    for method in ("closed-form", "original"):
+        want = R.wct_fuse(ct, st, method)
+        got = rpst.wct_fuse(ct.cuda(), st.cuda(), method, precision="bf16")
+        assert R.rel_l2(got, want) < TOL16, (method, R.rel_l2(got, want))
+        assert R.rel_l2(rpst.wct_fuse(ct.cuda(), st.cuda(), method), want) < TOL32
+
+
+# ---------------------------------------------------------------------------- config #4: L = 16384 (item 1c)
+def test_sanet_L16384_static_row_slice(rpst):
+    """BASELINE configs[3]: SANet at relu4_1 of a 1024^2 image, C=512, L=16384 — module output on 256 query rows
+    against fp64 (network/sanet.py:82-99)."""
+    torch.manual_seed(0)
+    m = rpst.SANet(512).cuda()
+    c, s = R.synth_features((1, 512, 128, 128), cfg=4, device="cuda")
+    rows = torch.arange(37, 16384, 64, device="cuda")
+    with torch.no_grad():
+        want = _sanet_rows_fp64(m, c, s, rows)
+        got = m(c, s).reshape(1, 512, -1)[:, :, rows]
+        m.precision = "bf16"
+        got16 = m(c, s).reshape(1, 512, -1)[:, :, rows]
+    assert R.rel_l2(got, want) < TOL32, R.rel_l2(got, want)
+    assert R.rel_l2(got16, want) < TOL16, R.rel_l2(got16, want)
+
+
+def test_attention_core_L16384_row_slice(rpst):
+    """The bare attention core at C=512, L=16384 (fp32-grade) on a row slice, and rows of P sum to one."""
+    g = torch.Generator(device="cuda").manual_seed(44)
+    f = torch.randn(1, 512, 128, 128, device="cuda", generator=g) * 0.3
+    k = torch.randn(1, 512, 128, 128, device="cuda", generator=g) * 0.3
+    v = torch.randn(1, 512, 128, 128, device="cuda", generator=g)
+    rows = torch.arange(5, 16384, 64, device="cuda")
+    got = rpst.attention_core(f, k, v).reshape(1, 512, -1)[:, :, rows]
+    F, G, H = (t.double().reshape(1, 512, -1) for t in (f, k, v))
+    P = torch.softmax(torch.bmm(F[:, :, rows].transpose(1, 2), G), dim=-1)
+    want = torch.bmm(H, P.transpose(1, 2))
+    assert R.rel_l2(got, want) < TOL32, R.rel_l2(got, want)
+
+
+@pytest.mark.parametrize("mode", ["aea", "relu"])
+def test_adaptive_sanet_L16384_row_slice(rpst, mode):
+    """AdaptiveSANet at L=16384 (f_psi = Linear(16384 -> 1024 -> 1)), inference path, against fp64 on a row slice
+    (network/sanet.py:114-138).  sigmoid(50 (S - clamp)) amplifies logit errors 50x: tolerance 2e-3 like the
+    golden test of the same module."""
+    torch.manual_seed(0)
+    m = rpst.AdaptiveSANet(512, 16384, ada_module=mode).cuda()
+    m.keep_claims = False
+    c, s = R.synth_features((1, 512, 128, 128), cfg=4, device="cuda")
+    rows = torch.arange(11, 16384, 128, device="cuda")
+    with torch.no_grad():
+        want = _sanet_rows_fp64(m, c, s, rows, clamp_mode=mode)
+        got = m(c, s).reshape(1, 512, -1)[:, :, rows]
+    assert R.rel_l2(got, want) < 2e-3, R.rel_l2(got, want)
+
+
+# ---------------------------------------------------------------------------- config #3: N = 16 (item 1d)
+def test_wct_batch16_oversubscribed_jacobi(rpst):
+    """BASELINE configs[2] batch: N=16, C=256 (128x128 planes keep the oracle fast): 32 + 16 Jacobi solves of
+    256x256 in flight, more clusters than are co-resident (eig.cu), every sample against the fp64 oracle."""
+    n, c, h, w = 16, 256, 128, 128
+    ct, st = R.synth_features((n, c, h, w), cfg=3)
+    mix = torch.randn(c, c, generator=torch.Generator().manual_seed(3)) / c ** 0.5
+    ct = torch.einsum("oc,nchw->nohw", mix, ct)
+    st = torch.einsum("oc,nchw->nohw", mix.t(), st)
+    got = rpst.wct_fuse(ct.cuda(), st.cuda())
+    want = R.wct_fuse(ct, st)
+    for i in range(n):
+        assert R.rel_l2(got[i], want[i]) < TOL32, (i, R.rel_l2(got[i], want[i]))
+    # per-sample launches give the same bits as the batched call
+    one = rpst.wct_fuse(ct[5:6].cuda(), st[5:6].cuda())
+    assert R.rel_l2(one[0], want[5]) < TOL32
