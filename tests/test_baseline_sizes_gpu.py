@@ -107,6 +107,10 @@ def test_sanet_module_bf16_gradients(rpst):
     assert R.rel_l2(out, ref) < TOL16
     assert R.rel_l2(cg.grad, c64.grad) < 5e-2 and R.rel_l2(sg.grad, s64.grad) < 5e-2
     for n, p in m.named_parameters():
+        if n == "g.bias":
+            # a bias on G shifts every logit of a row by the same amount: softmax cancels it, the exact gradient is 0
+            assert float(p.grad.norm()) < 5e-2 * float(m.g.weight.grad.norm())
+            continue
         assert R.rel_l2(p.grad, sd[n].grad) < 5e-2, n
 
 
