@@ -15,6 +15,8 @@
 //                       accumulator to the epilogue
 //   warps 2..5        : epilogue — tcgen05.ld (each warp its 32-lane TMEM quarter), scale/add, store;
 //                       runs concurrently with the MMAs of the next tile (double-buffered accumulator)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -34,6 +36,7 @@ struct PackParams {
     // batch (blockIdx.y): element stride of x, byte stride of the tile buffers, element stride of scale/shift
     int64_t x_batch, tile_batch_bytes, vec_batch;
     int vec_k;                  // stride_k == 1, x and every row start 16-byte aligned: 128-bit source loads
+    int fp16;                   // 1: emit IEEE half (11-bit significand) into `hi` instead of bf16 (flash-attention V operand)
 };
 
 // One thread produces one 16-byte chunk (8 consecutive k of one row).  Threads of a warp walk the
@@ -67,9 +70,16 @@ __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
             for (int e = 0; e < 8; ++e)
                 v[e] = (row < p.rows && k0 + e < p.k) ? __ldg(p.x + row * p.stride_r + (k0 + e) * p.stride_k) : sh;
         }
+        const uint32_t off = tile_chunk_offset(r, c);
+        if (p.fp16) {
+            __align__(16) __half hh[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hh[e] = __float2half_rn((row < p.rows && k0 + e < p.k) ? (v[e] - sh) * sc : 0.f);
+            *reinterpret_cast<uint4*>(hi_tile + off) = *reinterpret_cast<const uint4*>(hh);
+            continue;
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) split_bf16((row < p.rows && k0 + e < p.k) ? (v[e] - sh) * sc : 0.f, h[e], l[e]);
-        const uint32_t off = tile_chunk_offset(r, c);
         *reinterpret_cast<uint4*>(hi_tile + off) = *reinterpret_cast<const uint4*>(h);
         if (lo_tile) *reinterpret_cast<uint4*>(lo_tile + off) = *reinterpret_cast<const uint4*>(l);
     }
@@ -299,12 +309,32 @@ int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r
     return pack_operand_batched(x, rows, k, stride_r, stride_k, row_scale, row_shift, hi, lo, 1, 0, 0, 0, stream);
 }
 
+int pack_operand_impl(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                      const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
+                      int64_t tile_batch_bytes, int64_t vec_batch, int fp16, cudaStream_t stream);
+
 // `batch` independent operands in one launch: sample i reads x + i*x_batch (elements), scale/shift + i*vec_batch,
 // and writes its tiles at hi/lo + i*tile_batch_bytes.
 int pack_operand_batched(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
                          const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
                          int64_t tile_batch_bytes, int64_t vec_batch, cudaStream_t stream) {
+    return pack_operand_impl(x, rows, k, stride_r, stride_k, row_scale, row_shift, hi, lo, batch, x_batch, tile_batch_bytes,
+                             vec_batch, 0, stream);
+}
+
+// same tile format with IEEE-half elements (values scaled by row_scale first; no lo part)
+int pack_operand_batched_f16(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                             const float* row_scale, void* out, int batch, int64_t x_batch, int64_t tile_batch_bytes,
+                             int64_t vec_batch, cudaStream_t stream) {
+    return pack_operand_impl(x, rows, k, stride_r, stride_k, row_scale, nullptr, out, nullptr, batch, x_batch, tile_batch_bytes,
+                             vec_batch, 1, stream);
+}
+
+int pack_operand_impl(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                      const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
+                      int64_t tile_batch_bytes, int64_t vec_batch, int fp16, cudaStream_t stream) {
     PackParams p{};
+    p.fp16 = fp16;
     p.x_batch = x_batch; p.tile_batch_bytes = tile_batch_bytes; p.vec_batch = vec_batch;
     p.vec_k = (stride_k == 1 && stride_r % 4 == 0 && x_batch % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? 1 : 0;
     p.x = x; p.rows = rows; p.k = k; p.stride_r = stride_r; p.stride_k = stride_k; p.row_scale = row_scale;

@@ -28,6 +28,12 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
                         const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
                         int64_t b_batch_bytes, int64_t out_batch, cudaStream_t stream);
 int channel_norms(const float* x, int64_t c, int64_t l, float* sq, float* nrm, float* inv, cudaStream_t st);
+// flash.cu: single-kernel attention for C = 512 (S and P never leave the SM)
+bool flash_attn_supported(int64_t c, int64_t lc, int64_t ls);
+size_t flash_attn_workspace_bytes(int64_t lc, int64_t ls, int64_t samples);
+int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t lc, int64_t ls,
+                   int passes, void* workspace, size_t workspace_bytes, cudaStream_t st);
+extern int64_t g_attn_flash;
 
 namespace {
 
@@ -515,6 +521,10 @@ extern "C" int rpst_sanet_attn_fwd(const float* f, const float* g, const float* 
     RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* w = static_cast<char*>(workspace);
+    // C = 512 without a materialised attention map: one flash-style kernel (the per-sample workspace of the
+    // three-kernel path below always covers what it needs: packed Q, K, V only)
+    if (!attn_out && g_attn_flash && flash_attn_supported(c, lc, ls) && flash_attn_workspace_bytes(lc, ls, 1) <= workspace_bytes)
+        return flash_attn_fwd(f, g, h, out, b, lc, ls, passes, workspace, workspace_bytes, st);
     const int64_t kb_max = group_size(b, workspace_bytes, per_sample);
     for (int64_t i = 0; i < b; i += kb_max) {
         const int kb = (int)(b - i < kb_max ? b - i : kb_max);
