@@ -29,3 +29,28 @@ def test_reference_arm_other_ranks_print_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_both_arms_name_the_same_workload():
+    """`same_config` was false because the two arms spelled `config.workload` differently."""
+    sys.path.insert(0, ROOT)
+    import bench
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"workload": WORKLOAD') == 2          # one per arm, both the module constant
+    assert bench.WORKLOAD.startswith("configs[1]")
+    assert bench.algorithmic_bytes(32) == 57982058496       # SURVEY §8d: 54 GiB per 32-image step
+
+
+def test_stub_rp_network_cpu_leg_runs():
+    """The CPU arm of the `e2e_images` leg: stub RP encoder/decoder + the reference's AdaIN op sequence."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench_configs as BC
+    torch.manual_seed(0)
+    net = BC.StubRPNet().eval()
+    c, s = torch.rand(1, 3, 24, 24), torch.rand(1, 3, 24, 24)
+    with torch.no_grad():
+        feats = net.encode_rp_intermediate(c)
+        assert [f.shape[1] for f in feats] == [16, 32, 64, 128, 256] and all(f.shape[2:] == (24, 24) for f in feats)
+        out = BC.stylize_images(net, c, s, oracle=True)
+    assert out.shape == (1, 3, 24, 24) and torch.isfinite(out).all()
