@@ -70,6 +70,7 @@ struct FlashParams {
     int lc, ls;
     int qtiles, ktiles;                     // lc / 128, ls / 256
     int items;                              // b * qtiles
+    unsigned long long* prof;               // optional [32] cycle counters of pair 0 (tuning knob "attn_flash_prof")
 };
 
 template <bool X3>
@@ -172,22 +173,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
             uint32_t use = 0, g0 = 0;
             int n = 0;
             uint32_t last_slot = 0;
+            const bool prof = p.prof != nullptr && pair == 0;
+            long long c_full = 0, c_peer = 0, c_sempty = 0, c_pfull = 0, c_q = 0;
+            const long long c_begin = clock64();
             auto wait_slot = [&]() -> uint32_t {
                 const uint32_t slot = use % NS, ph = (use / NS) & 1u;
+                long long t0 = 0, t1 = 0;
+                if (prof) t0 = clock64();
                 mbar_wait(&full[slot], ph);
+                if (prof) t1 = clock64();
                 mbar_wait_cluster(&peer_full[slot], ph);
+                if (prof) { c_full += t1 - t0; c_peer += clock64() - t1; }
                 tcgen05_fence_after();
                 ++use;
                 last_slot = slot;
                 return ring_addr + slot * kTileBytes;
             };
             for (int item = pair; item < p.items; item += npairs, ++n) {
+                long long tq = prof ? clock64() : 0;
                 mbar_wait(&q_full, (uint32_t)n & 1u);
                 mbar_wait_cluster(&peer_q_full, (uint32_t)n & 1u);
+                if (prof) c_q += clock64() - tq;
                 tcgen05_fence_after();
                 auto issue_qk = [&](int t) {
                     const uint32_t g = g0 + t, buf = g & 1u;
+                    long long ts = prof ? clock64() : 0;
                     mbar_wait_cluster(&s_empty[buf], ((g >> 1) & 1u) ^ 1u);
+                    if (prof) c_sempty += clock64() - ts;
                     tcgen05_fence_after();
                     const uint32_t d = tmem_base + kFlOCols + buf * kFlSCols;
                     for (int kb = 0; kb < kFlQKBlocks; ++kb) {
@@ -213,7 +225,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                 };
                 auto issue_pv = [&](int t) {
                     const uint32_t g = g0 + t;
+                    long long tp = prof ? clock64() : 0;
                     mbar_wait_cluster(&p_full, g & 1u);
+                    if (prof) c_pfull += clock64() - tp;
                     tcgen05_fence_after();
                     for (int kbv = 0; kbv < kFlPVBlocks; ++kbv) {
                         for (int dc = 0; dc < 2; ++dc) {
@@ -237,6 +251,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                 }
                 issue_pv(T - 1);
                 g0 += T;
+            }
+            if (prof) {
+                p.prof[0] = (unsigned long long)(clock64() - c_begin);
+                p.prof[1] = (unsigned long long)c_full; p.prof[2] = (unsigned long long)c_peer;
+                p.prof[3] = (unsigned long long)c_sempty; p.prof[4] = (unsigned long long)c_pfull;
+                p.prof[5] = (unsigned long long)c_q; p.prof[6] = (unsigned long long)g0;
             }
         } else if (lane == 0) {
             // ------------------------------------------------------------------ relay (peer CTA): my half has landed
@@ -264,12 +284,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
         unsigned char* p_row = p_smem + row * 128;
         const uint32_t sw = (uint32_t)(row & 7);
         uint32_t g = 0;
+        const bool prof = p.prof != nullptr && pair == 0 && rank == 0 && warp == 2 && lane == 0;
+        long long c_sfull = 0, c_p1 = 0, c_bar = 0, c_odone = 0, c_resc = 0, c_p2 = 0, c_epi = 0;
+        const long long c_begin = clock64();
         for (int item = pair; item < p.items; item += npairs) {
             const int sample = item / p.qtiles, qt = item % p.qtiles;
             float m_ref = -INFINITY, l = 0.f;
             for (int t = 0; t < T; ++t, ++g) {
                 const uint32_t buf = g & 1u;
+                long long k0 = prof ? clock64() : 0;
                 mbar_wait(&s_full[buf], (g >> 1) & 1u);
+                long long k1 = prof ? clock64() : 0;
                 tcgen05_fence_after();
                 const uint32_t s_addr = lane_addr + kFlOCols + buf * kFlSCols;
                 float v[32];
@@ -281,9 +306,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
                 }
+                long long k2 = prof ? clock64() : 0;
                 xch[g & 1u][tl] = mx;
                 named_bar_sync(1, 128);
                 mx = fmaxf(mx, xch[g & 1u][tl ^ 64]) * kLog2e;
+                long long k3 = prof ? clock64() : 0;
                 float scale = 1.f;
                 bool need = false;
                 if (t == 0) {
@@ -298,6 +325,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                     mbar_wait(&o_done, (g - 1) & 1u);
                     tcgen05_fence_after();
                 }
+                long long k4 = prof ? clock64() : 0;
                 if (__any_sync(0xffffffffu, need)) {
                     l *= scale;
 #pragma unroll 1
@@ -309,6 +337,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                         tmem_st_32x32(lane_addr + c0, r);
                     }
                 }
+                long long k5 = prof ? clock64() : 0;
                 // pass 2: P = exp2(s log2e - m_ref), row sum, 16-bit P into the swizzled A-operand tile
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
@@ -351,7 +380,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                         mbar_arrive_cluster(p_full_remote);
                     }
                 }
+                if (prof) {
+                    const long long k6 = clock64();
+                    c_sfull += k1 - k0; c_p1 += k2 - k1; c_bar += k3 - k2; c_odone += k4 - k3; c_resc += k5 - k4; c_p2 += k6 - k5;
+                }
             }
+            const long long e0 = prof ? clock64() : 0;
             // ---- epilogue of the work item: O / l -> out[sample, d, i]
             mbar_wait(&o_done, (g - 1) & 1u);
             tcgen05_fence_after();
@@ -373,6 +407,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                 }
             }
             named_bar_sync(1, 128);                 // xch[0] is rewritten by the next item's first tile only after this
+            if (prof) c_epi += clock64() - e0;
+        }
+        if (prof) {
+            p.prof[8] = (unsigned long long)(clock64() - c_begin);
+            p.prof[9] = (unsigned long long)c_sfull; p.prof[10] = (unsigned long long)c_p1; p.prof[11] = (unsigned long long)c_bar;
+            p.prof[12] = (unsigned long long)c_odone; p.prof[13] = (unsigned long long)c_resc; p.prof[14] = (unsigned long long)c_p2;
+            p.prof[15] = (unsigned long long)c_epi;
         }
     }
     tcgen05_fence_before();
@@ -429,6 +470,8 @@ FlashLayout flash_layout(int64_t lc, int64_t ls, int64_t max_samples) {
 }
 
 }  // namespace
+
+int64_t g_attn_flash_prof = 0;   // device pointer to 32 x uint64 cycle counters (0 = off); bring-up / tuning only
 
 bool flash_attn_supported(int64_t c, int64_t lc, int64_t ls) {
     return c == kFlD && lc > 0 && ls > 0 && lc % 128 == 0 && ls % kFlKeys == 0;
@@ -498,6 +541,7 @@ int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, i
         p.lc = (int)lc; p.ls = (int)ls;
         p.qtiles = (int)(lc / 128); p.ktiles = (int)(ls / kFlKeys);
         p.items = kb * p.qtiles;
+        p.prof = reinterpret_cast<unsigned long long*>(g_attn_flash_prof);
         int pairs = sm_count() / 2;
         if (pairs > p.items) pairs = p.items;
         if (x3) flash_attn_kernel<true><<<2 * pairs, kFlThreads, FlashCfg<true>::smem, st>>>(p);
