@@ -182,7 +182,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
                 if (prof) t0 = clock64();
                 mbar_wait(&full[slot], ph);
                 if (prof) t1 = clock64();
-                mbar_wait_cluster(&peer_full[slot], ph);
+                mbar_wait(&peer_full[slot], ph);       // relayed TMA-completion event (async proxy on both ends)
                 if (prof) { c_full += t1 - t0; c_peer += clock64() - t1; }
                 tcgen05_fence_after();
                 ++use;
@@ -192,7 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
             for (int item = pair; item < p.items; item += npairs, ++n) {
                 long long tq = prof ? clock64() : 0;
                 mbar_wait(&q_full, (uint32_t)n & 1u);
-                mbar_wait_cluster(&peer_q_full, (uint32_t)n & 1u);
+                mbar_wait(&peer_q_full, (uint32_t)n & 1u);
                 if (prof) c_q += clock64() - tq;
                 tcgen05_fence_after();
                 auto issue_qk = [&](int t) {
@@ -261,15 +261,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlThreads, 1) flash
         } else if (lane == 0) {
             // ------------------------------------------------------------------ relay (peer CTA): my half has landed
             const uint32_t uses_per_item = (uint32_t)T * (kFlQKBlocks * Cfg::parts + 2 * kFlPVBlocks);
+            const uint32_t peer_full_remote = mapa_u32(smem_u32(&peer_full[0]), 0);
+            const uint32_t peer_q_remote = mapa_u32(smem_u32(&peer_q_full), 0);
             uint32_t use = 0;
             int n = 0;
             for (int item = pair; item < p.items; item += npairs, ++n) {
                 mbar_wait(&q_full, (uint32_t)n & 1u);
-                mbar_arrive_cluster(mapa_u32(smem_u32(&peer_q_full), 0));
+                mbar_arrive_cluster_relaxed(peer_q_remote);
                 for (uint32_t u = 0; u < uses_per_item; ++u, ++use) {
                     const uint32_t slot = use % NS;
                     mbar_wait(&full[slot], (use / NS) & 1u);
-                    mbar_arrive_cluster(mapa_u32(smem_u32(&peer_full[slot]), 0));
+                    mbar_arrive_cluster_relaxed(peer_full_remote + slot * (uint32_t)sizeof(uint64_t));
                 }
             }
         }
