@@ -6,19 +6,24 @@
 // W starts as A (+diag) and pairs of COLUMNS are rotated until mutually orthogonal; then column j of W
 // is lambda_j v_j (A symmetric PSD), so f(A) = V f(L) V^T = W diag(f(l_j)/l_j^2) W^T needs no separate
 // eigenvector accumulation.  One matrix = one thread-block CLUSTER: the n x n fp64 matrix lives in the
-// cluster's distributed shared memory, 32 columns (two blocks of 16) per CTA, a warp per column pair.
+// cluster's distributed shared memory, two blocks of BC columns per CTA (BC = 32: 64 columns, 1024 threads, a
+// whole SM per CTA — a 256 x 256 matrix is a 4-CTA cluster, so the 16 matrices of BASELINE config #3 are all
+// co-resident; BC = 16 for order 512 where 64 columns would not fit shared memory), a warp per column pair.
 // Block round-robin ordering: within a round a CTA orthogonalises its two column blocks against each
-// other (16 steps x 16 disjoint pairs; plus the pairs inside each block once per sweep); between rounds
+// other (BC steps x BC disjoint pairs; plus the pairs inside each block once per sweep); between rounds
 // the blocks move to their next owners through DSMEM (circle-method tournament, two cluster barriers).
+// In the cross steps a warp keeps ITS X column in registers for all BC steps (only the Y columns travel through
+// shared memory): the steps are shared-memory-bandwidth bound (2 x 2 KiB read + written per pair and step).
 // All CTAs of a cluster see the same convergence value, so the sweep loop exits uniformly.
 #include "common.cuh"
 
 namespace rpst {
 namespace {
 
-constexpr int kBlockCols = 16;                 // columns per block
-constexpr int kCtaCols = 2 * kBlockCols;       // columns per CTA
-constexpr int kEigThreads = 32 * kBlockCols;   // one warp per pair, 16 pairs per step
+// columns per block (BC).  BC = 32 (one whole SM per CTA, 4-CTA clusters at order 256) when many matrices must be
+// co-resident; BC = 16 (twice the SMs per matrix) for small batches: a step's cost grows with the pairs per SM
+// (measured: order 256, one matrix 3.0 ms with BC = 16 vs 5.3 ms with BC = 32; 16 matrices 5.6 vs 5.4 ms).
+constexpr bool eig_wide_ok(int np) { return np >= 64 && np <= 256; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -43,6 +48,10 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// gmax is the largest |cos| between two columns seen BEFORE they were rotated in this sweep; Jacobi converges
+// quadratically, so a sweep that saw 1e-8 leaves ~1e-16.  (1e-12 here cost one extra verification sweep in 11.)
+constexpr double kEigConverged = 1e-8;
 
 struct EigParams {
     const double* a;      // [batch, n, n] symmetric
@@ -101,8 +110,43 @@ __device__ __forceinline__ double rotate_pair(double* x, double* y, int lane) {
     return rel;
 }
 
-template <int ROWS>   // padded order np = 32*ROWS, cluster of ROWS CTAs
-__global__ void __launch_bounds__(kEigThreads, 2) jacobi_cluster_kernel(EigParams p) {
+// same rotation with the x column held in registers by the calling warp (xv is updated in place)
+template <int ROWS>
+__device__ __forceinline__ double rotate_pair_xreg(double (&xv)[ROWS], double* y, int lane) {
+    double yv[ROWS];
+    double aa = 0.0, bb = 0.0, gg = 0.0;
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        yv[i] = y[i * 32 + lane];
+        aa = fma(xv[i], xv[i], aa);
+        bb = fma(yv[i], yv[i], bb);
+        gg = fma(xv[i], yv[i], gg);
+    }
+    aa = warp_sum_f64(aa);
+    bb = warp_sum_f64(bb);
+    gg = warp_sum_f64(gg);
+    const float aaf = (float)aa, bbf = (float)bb, ggf = (float)gg;
+    const float prod = aaf * bbf;
+    if (!(prod > 0.f)) return 0.0;
+    const float relf = fabsf(ggf) * rsqrtf(prod);
+    if (relf <= 1e-15f) return (double)relf;
+    const float zeta = (float)(bb - aa) / (2.f * ggf);
+    const float tf = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+    const double t = (double)tf;
+    const double c = rsqrt(fma(t, t, 1.0));
+    const double s = c * t;
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        const double xo = xv[i];
+        xv[i] = c * xo - s * yv[i];
+        y[i * 32 + lane] = s * xo + c * yv[i];
+    }
+    return (double)relf;
+}
+
+template <int ROWS, int BC>   // padded order np = 32*ROWS, BC columns per block, cluster of np / (2 BC) CTAs
+__global__ void __launch_bounds__(32 * BC, (BC == 16 && ROWS < 16) ? 2 : 1) jacobi_cluster_kernel(EigParams p) {
+    constexpr int kBlockCols = BC, kCtaCols = 2 * BC, kEigThreads = 32 * BC;
     extern __shared__ __align__(16) unsigned char eig_smem[];
     double* cols = reinterpret_cast<double*>(eig_smem);            // [32][np]
     double* conv = cols + (size_t)kCtaCols * p.np;                 // [2]: per-sweep local maxima (double buffered)
@@ -136,8 +180,8 @@ __global__ void __launch_bounds__(kEigThreads, 2) jacobi_cluster_kernel(EigParam
         double wmax = 0.0;
         for (int r = 0; r < m - 1; ++r) {
             if (r == 0) {
-                // pairs inside each block (once per sweep): warps 0-7 block X, 8-15 block Y
-                const int half = warp >> 3, k = warp & 7;
+                // pairs inside each block (once per sweep): the lower half of the warps takes block X, the upper block Y
+                const int half = warp / (kBlockCols / 2), k = warp % (kBlockCols / 2);
                 double* base = cols + (size_t)half * kBlockCols * np;
                 for (int t = 0; t < kBlockCols - 1; ++t) {
                     const int c0 = block_at(k, t, kBlockCols), c1 = block_at(kBlockCols - 1 - k, t, kBlockCols);
@@ -145,11 +189,19 @@ __global__ void __launch_bounds__(kEigThreads, 2) jacobi_cluster_kernel(EigParam
                     __syncthreads();
                 }
             }
-            // cross pairs: X_i with Y_(i+s)
-            for (int s = 0; s < kBlockCols; ++s) {
-                const int j = (warp + s) & (kBlockCols - 1);
-                wmax = fmax(wmax, rotate_pair<ROWS>(cols + (size_t)warp * np, cols + (size_t)(kBlockCols + j) * np, lane));
-                __syncthreads();
+            // cross pairs: X_i with Y_(i+s); X_i stays in this warp's registers for the whole round
+            {
+                double xv[ROWS];
+                double* xcol = cols + (size_t)warp * np;
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) xv[i] = xcol[i * 32 + lane];
+                for (int s = 0; s < kBlockCols; ++s) {
+                    const int j = (warp + s) & (kBlockCols - 1);
+                    wmax = fmax(wmax, rotate_pair_xreg<ROWS>(xv, cols + (size_t)(kBlockCols + j) * np, lane));
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) xcol[i * 32 + lane] = xv[i];
             }
             const bool last_round = r == m - 2;
             if (last_round) {
@@ -188,7 +240,7 @@ __global__ void __launch_bounds__(kEigThreads, 2) jacobi_cluster_kernel(EigParam
                 for (int i = 0; i < ROWS; ++i)
                     cols[(size_t)slot * kBlockCols * np + i * kEigThreads + threadIdx.x] = stage[slot][i];
             __syncthreads();
-            if (last_round && gmax < 1e-12) { ++sweep; goto done; }   // uniform across the cluster
+            if (last_round && gmax < kEigConverged) { ++sweep; goto done; }   // uniform across the cluster
         }
     }
 done:
@@ -283,12 +335,14 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
     double* w = static_cast<double*>(ws);
     double* lam = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)batch * np * np * sizeof(double), 256));
     EigParams p{};
-    p.a = a; p.diag_add = diag_add; p.n = n; p.np = np; p.ctas = np / kCtaCols; p.max_sweeps = 20;
+    const bool wide = eig_wide_ok(np) && batch * (np / 32) > 96;     // more 32-column CTAs than fit one per SM with slack
+    const int bc = wide ? 32 : 16, cta_cols = 2 * bc;
+    p.a = a; p.diag_add = diag_add; p.n = n; p.np = np; p.ctas = np / cta_cols; p.max_sweeps = 20;
     p.w = w; p.lam = lam; p.sweeps = sweeps;
-    const size_t smem = (size_t)kCtaCols * np * sizeof(double) + 2 * sizeof(double);
+    const size_t smem = (size_t)cta_cols * np * sizeof(double) + 2 * sizeof(double);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(batch * p.ctas));
-    cfg.blockDim = dim3(kEigThreads);
+    cfg.blockDim = dim3(32 * bc);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -298,27 +352,30 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define RPST_EIG_CASE(R)                                                                                           \
-    case R: {                                                                                                      \
+#define RPST_EIG_CASE(R, BC)                                                                                       \
+    case R + 100 * (BC == 32): {                                                                                   \
         static PerDeviceFlag configured_on;                                                                        \
         bool& configured = configured_on.get();                                                                    \
         if (!configured) {                                                                                         \
-            RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+            RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem));                                                            \
-            if (R > 8)                                                                                             \
-                RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R>,                                           \
+            if (32 * R / (2 * BC) > 8)                                                                             \
+                RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R, BC>,                                       \
                                                cudaFuncAttributeNonPortableClusterSizeAllowed, 1));                \
             configured = true;                                                                                     \
         }                                                                                                          \
-        RPST_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<R>, p));                                          \
+        RPST_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<R, BC>, p));                                      \
         break;                                                                                                     \
     }
-    switch (np / 32) {
-        RPST_EIG_CASE(1)
-        RPST_EIG_CASE(2)
-        RPST_EIG_CASE(4)
-        RPST_EIG_CASE(8)
-        RPST_EIG_CASE(16)
+    switch (np / 32 + 100 * (bc == 32)) {
+        RPST_EIG_CASE(1, 16)
+        RPST_EIG_CASE(2, 16)
+        RPST_EIG_CASE(4, 16)
+        RPST_EIG_CASE(8, 16)
+        RPST_EIG_CASE(16, 16)
+        RPST_EIG_CASE(2, 32)
+        RPST_EIG_CASE(4, 32)
+        RPST_EIG_CASE(8, 32)
         default:
             set_error("sym_eig: unsupported padded order %d", np);
             return RPST_ERR_UNSUPPORTED;

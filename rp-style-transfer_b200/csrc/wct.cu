@@ -28,6 +28,12 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
 int eig_matfn(const double* w, const double* lam, int64_t batch, int n, double power, double cut, double* out,
               cudaStream_t stream);
 int dgemm_small(const double* a, const double* b, double* c, int64_t batch, int n, cudaStream_t stream);
+// cov.cu: one kernel from fp32 features to the centred covariance (conversion + centring inside the SYRK)
+bool cov_fused_supported(const float* x, int64_t c, int64_t hw);
+size_t cov_fused_workspace_bytes(int64_t c);
+int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
+              cudaStream_t st);
+extern int64_t g_wct_fused_cov;
 
 namespace {
 
@@ -67,7 +73,7 @@ __global__ void transform_finalize_kernel(const double* __restrict__ t, const fl
 
 struct WctLayout {
     size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, eig, mats[6], t32, bias,
-        t_hi, t_lo, x_hi, x_lo, total;
+        t_hi, t_lo, x_hi, x_lo, fused, total;
     int splits;
 };
 
@@ -104,6 +110,7 @@ WctLayout wct_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     l.t_lo = take(packed_operand_bytes(c, c));
     l.x_hi = take(packed_operand_bytes(hw_c, c));
     l.x_lo = take(packed_operand_bytes(hw_c, c));
+    l.fused = take(c <= 256 ? cov_fused_workspace_bytes(c) : 0);
     l.total = o;
     return l;
 }
@@ -139,6 +146,17 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
     float* mean_c = reinterpret_cast<float*>(w + l.mean_c);
     float* mean_s = reinterpret_cast<float*>(w + l.mean_s);
     int rc;
+    double* cov_c = reinterpret_cast<double*>(w + l.cov_c);
+    double* cov_s = reinterpret_cast<double*>(w + l.cov_s);
+    const bool fused = g_wct_fused_cov && cov_fused_supported(content, c, hw_c) && cov_fused_supported(style, c, hw_s) &&
+                       (c * hw_c) % 4 == 0 && (c * hw_s) % 4 == 0;
+    if (fused) {
+        // 1+2. means and centred covariances from ONE pass over each tensor (cov.cu)
+        for (int64_t i = 0; i < n; ++i) {
+            if ((rc = cov_fused(content + i * c * hw_c, c, hw_c, passes, 1.0, cov_c + i * c * c, mean_c + i * c, w + l.fused, st))) return rc;
+            if ((rc = cov_fused(style + i * c * hw_s, c, hw_s, passes, 0.0, cov_s + i * c * c, mean_s + i * c, w + l.fused, st))) return rc;
+        }
+    } else {
     // 1. channel means (network/wct_rp.py:85,92)
     rc = rpst_stats_nchw(content, n * c, hw_c, 0.f, mean_c, nullptr, w + l.stats, l.mean_c - l.stats, stream);
     if (rc) return rc;
@@ -148,8 +166,6 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
     void* ct_hi = w + l.cov_tiles_hi;
     void* ct_lo = w + l.cov_tiles_lo;
     float* partial = reinterpret_cast<float*>(w + l.partial);
-    double* cov_c = reinterpret_cast<double*>(w + l.cov_c);
-    double* cov_s = reinterpret_cast<double*>(w + l.cov_s);
     const int cc = (int)(c * c);
     for (int64_t i = 0; i < n; ++i) {
         for (int which = 0; which < 2; ++which) {
@@ -166,6 +182,7 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
                                                                which ? 0.0 : 1.0, (which ? cov_s : cov_c) + i * c * c);
             RPST_CUDA(cudaGetLastError());
         }
+    }
     }
     // 3. transform matrices, batched over samples (all fp64)
     double* m[6];

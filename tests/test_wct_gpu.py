@@ -90,3 +90,37 @@ def test_wct_full_plane_properties(rpst):
     assert R.rel_l2(cov_o, want_cov_o) < 1e-3
     # T (C_c) T^T == C_s + 1e-4-regularised root product: defining identity of the closed form
     assert R.rel_l2(tr @ cov_c @ tr.t(), torch.cov(xs)) < 5e-3
+
+
+# ---- round 2: fused convert + centre + SYRK covariance kernel (csrc/cov.cu) -------------------
+@pytest.mark.parametrize("n,c,h,w", [(1, 256, 64, 64), (2, 200, 20, 17 * 4), (1, 64, 9, 8), (1, 128, 33, 4), (2, 16, 8, 8)])
+def test_fused_covariance_matches_packed_path_and_oracle(rpst, n, c, h, w):
+    """The transform matrix T depends on the two covariances only: fused kernel (shifted operands + rank-1
+    correction, SYRK symmetry, ragged last k-tile, padded channel rows) vs the pack + GEMM path vs the fp64 oracle."""
+    ct = torch.relu(torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(11)) + 0.5)
+    st = torch.relu(torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(12)) * 2 + 1)
+    mix = torch.randn(c, c, generator=torch.Generator().manual_seed(13)) / c ** 0.5
+    ct = torch.einsum("oc,nchw->nohw", mix, ct)
+    st = torch.einsum("oc,nchw->nohw", mix.t(), st)
+    try:
+        rpst.set_tuning("wct_fused_cov", 0)
+        out0, t0 = rpst.wct_fuse(ct.cuda(), st.cuda(), return_transform=True)
+    finally:
+        rpst.set_tuning("wct_fused_cov", 1)
+    out1, t1 = rpst.wct_fuse(ct.cuda(), st.cuda(), return_transform=True)
+    want = R.wct_fuse(ct, st)
+    assert R.rel_l2(out1, want) < 1e-3, R.rel_l2(out1, want)
+    assert R.rel_l2(out0, want) < 1e-3
+    assert R.rel_l2(t1, t0) < 2e-4, R.rel_l2(t1, t0)
+    assert R.rel_l2(out1.mean(dim=(2, 3)), st.mean(dim=(2, 3))) < 1e-3
+
+
+def test_fused_covariance_with_mean_far_from_zero(rpst):
+    """|mean| >> std: the sub-sampled shift must keep the rank-1 centring correction free of cancellation."""
+    n, c, h, w = 1, 64, 64, 64
+    g = torch.Generator().manual_seed(21)
+    ct = torch.randn(n, c, h, w, generator=g) * 0.05 + 40.0 + torch.arange(c).view(1, c, 1, 1) * 3.0
+    st = torch.randn(n, c, h, w, generator=g) * 0.2 - 25.0
+    want = R.wct_fuse(ct, st)
+    got = rpst.wct_fuse(ct.cuda(), st.cuda())
+    assert R.rel_l2(got, want) < 1e-3, R.rel_l2(got, want)
