@@ -3,7 +3,8 @@
 //
 // One kernel reads the fp32 features ONCE and feeds the tensor cores directly: no packed-operand round trip
 // (the separate pack pass read 268 MB and wrote 222 MB per operand before the GEMM read them again).
-//   warps 1..8  converters: 128-bit global loads of a [C x 64 positions] k-tile, subtract a per-channel SHIFT,
+//   warps 1..16 converters in two groups that alternate k-tiles (one group's global loads are in flight while the
+//               other converts): 128-bit loads of a [C x 64 positions] k-tile, subtract a per-channel SHIFT,
 //               split into bf16 hi + lo, store into the K-major SWIZZLE_128B operand tile in shared memory
 //               (A and B of the SYRK are the same tile), and keep fp32 row sums of the shifted values
 //   warp 0      one thread issues tcgen05.mma: X X^T over this CTA's slice of H*W (split-K over all SMs) into TMEM;
@@ -20,7 +21,9 @@
 namespace rpst {
 namespace {
 
-constexpr int kCovConvWarps = 8;
+constexpr int kCovGroupWarps = 8;                            // converter warps per group: warp w owns rows [32 w, 32 w + 32)
+constexpr int kCovGroups = 2;
+constexpr int kCovConvWarps = kCovGroupWarps * kCovGroups;
 constexpr int kCovThreads = 32 * (1 + kCovConvWarps);
 constexpr int kCovMaxC = 256;
 constexpr uint32_t kCovPartBytes = 2 * kTileBytes;          // [256 rows x 64 positions] bf16 = 32 KiB
@@ -29,12 +32,19 @@ struct CovParams {
     const float* x;          // [c, hw] one sample, row stride hw
     const float* shift;      // [cp] per-channel shift (rows >= c: 0)
     float* partial;          // [grid, cp, cp] per-CTA partial Gram (blocks on/above the diagonal only)
-    float* rowsum;           // [grid, cp] per-CTA sums of (x - shift)
+    float* rowsum;           // [grid * 2, cp] per-CTA and converter-group sums of (x - shift)
     int64_t hw;
     int c, cp;               // channels, padded to 128 / 256
     int k_tiles;             // ceil(hw / 64)
     int passes;              // 1: bf16, 3: bf16x3
 };
+
+// {lo, hi} -> packed bf16x2 with round-to-nearest-even: lo in bits 0..15 (the element at the lower address)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 template <int PARTS>   // 1: hi only, 2: hi + lo
 __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) {
@@ -44,23 +54,23 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) 
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t full[NST], empty[NST], acc_full;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_shift[kCovMaxC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = p.cp / 128;
-    // this CTA's slice of the k-tiles
-    const int per = (p.k_tiles + gridDim.x - 1) / gridDim.x;
-    const int kt0 = blockIdx.x * per;
-    const int kt1 = min(p.k_tiles, kt0 + per);
-    const int nkt = max(0, kt1 - kt0);
+    // k-tiles are dealt round-robin: at any moment the co-running CTAs read ADJACENT 256-byte pieces of every channel
+    // row (contiguous ranges per CTA scattered 256-byte accesses over DRAM pages: 3.0 TB/s)
+    const int nkt = blockIdx.x < p.k_tiles ? (p.k_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(&full[s], kCovConvWarps);
+            mbar_init(&full[s], kCovGroupWarps);
             mbar_init(&empty[s], 1);
         }
         mbar_init(&acc_full, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_shift[r] = r < p.cp ? __ldg(p.shift + r) : 0.f;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -99,35 +109,26 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) 
             umma_commit(&acc_full);
         }
     } else {
-        // ------------------------------------------------------------------ converters: warp cw owns rows [32 cw, 32 cw + 32)
-        const int cw = warp - 1;
+        // ------------------------------------------------------------------ converters: group grp takes k-tiles grp, grp+2, ...
+        const int grp = (warp - 1) / kCovGroupWarps;
+        const int cw = (warp - 1) % kCovGroupWarps;
         const int sub = lane >> 4;                 // which of the two rows of a load
         const int p4 = (lane & 15) * 4;            // first of this lane's 4 positions inside the k-tile
-        float sh[16], acc[16];
+        float acc[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int row = cw * 32 + 2 * i + sub;
-            sh[i] = row < p.cp ? __ldg(p.shift + row) : 0.f;
-            acc[i] = 0.f;
-        }
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
         const bool rows_used = cw * 32 < p.cp;     // C <= 128: the upper converter warps only keep the handshake going
-        for (int it = 0; it < nkt; ++it) {
-            const int kt = kt0 + it;
-            const int64_t pos = (int64_t)kt * kTileK + p4;
+        for (int it = grp; it < nkt; it += kCovGroups) {
+            const int64_t pos = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileK + p4;
             float4 v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int row = cw * 32 + 2 * i + sub;
-                if (rows_used && row < p.c && pos + 4 <= p.hw) {
+                if (rows_used && row < p.c && pos < p.hw) {               // hw % 4 == 0: a float4 is inside or outside
                     v[i] = __ldcs(reinterpret_cast<const float4*>(p.x + (int64_t)row * p.hw + pos));
-                } else if (rows_used && row < p.c && pos < p.hw) {       // ragged last k-tile (hw % 64 != 0, hw % 4 == 0 never lands here)
-                    const float* src = p.x + (int64_t)row * p.hw + pos;
-                    v[i].x = src[0];
-                    v[i].y = pos + 1 < p.hw ? src[1] : sh[i];
-                    v[i].z = pos + 2 < p.hw ? src[2] : sh[i];
-                    v[i].w = sh[i];
                 } else {
-                    v[i] = make_float4(sh[i], sh[i], sh[i], sh[i]);      // padding: (x - shift) = 0
+                    const float sh = s_shift[row];
+                    v[i] = make_float4(sh, sh, sh, sh);                   // padding: (x - shift) = 0
                 }
             }
             const int s = it % NST;
@@ -138,19 +139,17 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int row = cw * 32 + 2 * i + sub;
-                    const float a = v[i].x - sh[i], b = v[i].y - sh[i], c2 = v[i].z - sh[i], d = v[i].w - sh[i];
+                    const float sh = s_shift[row];
+                    const float a = v[i].x - sh, b = v[i].y - sh, c2 = v[i].z - sh, d = v[i].w - sh;
                     acc[i] += (a + b) + (c2 + d);
-                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_bf16(a, h0, l0); split_bf16(b, h1, l1); split_bf16(c2, h2, l2); split_bf16(d, h3, l3);
+                    // two elements per instruction: hi = bf16x2(a, b); the bf16 -> fp32 widening is a shift / mask
+                    const uint32_t h01 = pack_bf16x2(a, b), h23 = pack_bf16x2(c2, d);
                     const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((p4 >> 3) ^ (row & 7)) << 4) + ((lane & 1) << 3));
-                    __nv_bfloat162 a01 = __halves2bfloat162(h0, h1), a23 = __halves2bfloat162(h2, h3);
-                    uint2 w;
-                    w.x = *reinterpret_cast<uint32_t*>(&a01); w.y = *reinterpret_cast<uint32_t*>(&a23);
-                    *reinterpret_cast<uint2*>(hi + off) = w;
+                    *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
                     if (PARTS == 2) {
-                        __nv_bfloat162 b01 = __halves2bfloat162(l0, l1), b23 = __halves2bfloat162(l2, l3);
-                        w.x = *reinterpret_cast<uint32_t*>(&b01); w.y = *reinterpret_cast<uint32_t*>(&b23);
-                        *reinterpret_cast<uint2*>(lo + off) = w;
+                        const uint32_t l01 = pack_bf16x2(a - __uint_as_float(h01 << 16), b - __uint_as_float(h01 & 0xffff0000u));
+                        const uint32_t l23 = pack_bf16x2(c2 - __uint_as_float(h23 << 16), d - __uint_as_float(h23 & 0xffff0000u));
+                        *reinterpret_cast<uint2*>(lo + off) = make_uint2(l01, l23);
                     }
                 }
             }
@@ -166,11 +165,11 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) 
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
                 const int row = cw * 32 + 2 * i + sub;
-                if ((lane & 15) == 0 && row < p.cp) p.rowsum[(size_t)blockIdx.x * p.cp + row] = a;
+                if ((lane & 15) == 0 && row < p.cp) p.rowsum[((size_t)blockIdx.x * kCovGroups + grp) * p.cp + row] = a;
             }
         }
         // ------------------------------------------------------------------ epilogue (warps 1..4 = TMEM quarters 1,2,3,0)
-        if (warp <= 4) {
+        if (warp <= 4) {                                         // first four warps of group 0
             const int q = warp & 3;
             const int r = q * 32 + lane;
             float* out = p.partial + (size_t)blockIdx.x * p.cp * p.cp;
@@ -209,45 +208,96 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) 
     }
 }
 
-// sub-sampled per-channel mean (up to 32 segments of 64 positions spread over the plane): the centring shift
-__global__ void __launch_bounds__(128) cov_shift_kernel(const float* __restrict__ x, int c, int cp, int64_t hw,
+// sub-sampled per-channel mean (up to 32 segments of 64 positions spread over the plane): the centring shift.
+// One warp per channel, every load independent.
+__global__ void __launch_bounds__(256) cov_shift_kernel(const float* __restrict__ x, int c, int cp, int64_t hw,
                                                         float* __restrict__ shift) {
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= cp) return;
     if (row >= c) {
         if (lane == 0) shift[row] = 0.f;
         return;
     }
-    const int64_t segs = hw / 64 > 32 ? 32 : (hw / 64 > 0 ? hw / 64 : 1);
-    const int64_t seg_len = hw / 64 > 0 ? 64 : hw;
-    const int64_t stride = hw / segs;
+    const int segs = (int)(hw / 64 > 32 ? 32 : hw / 64);      // hw >= 64
+    const int64_t stride = (hw / segs) & ~(int64_t)3;          // >= 64, keeps the 8-byte loads aligned
+    const float* xr = x + (int64_t)row * hw + 2 * lane;
     float a = 0.f;
-    for (int64_t i = lane; i < segs * seg_len; i += 32) a += x[(int64_t)row * hw + (i / seg_len) * stride + (i % seg_len)];
+#pragma unroll 8
+    for (int sgi = 0; sgi < segs; ++sgi) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(xr + sgi * stride));   // hw % 4 == 0 keeps this 8-byte aligned
+        a += v.x + v.y;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) shift[row] = a / (float)(segs * seg_len);
+    if (lane == 0) shift[row] = a / (float)(segs * 64);
 }
 
-// fixed-order fp64 reduction of the per-CTA partials + rank-1 centring correction; also the exact means
-__global__ void __launch_bounds__(256) cov_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ rowsum,
-                                                           const float* __restrict__ shift, int parts, int c, int cp, double hw,
-                                                           double diag_add, double* __restrict__ cov, float* __restrict__ mean) {
-    __shared__ double s_sum[kCovMaxC];
-    for (int r = threadIdx.x; r < cp; r += blockDim.x) {
-        double a = 0.0;
-        for (int z = 0; z < parts; ++z) a += (double)rowsum[(size_t)z * cp + r];
-        s_sum[r] = a;
+// S[r] = sum over CTAs and converter groups of the partial row sums (fp64, fixed order); exact means.
+// Thread (e, r): entry slice e of 8, row r; the 8 slice sums are folded in index order through shared memory.
+__global__ void __launch_bounds__(256) cov_rowsum_kernel(const float* __restrict__ rowsum, const float* __restrict__ shift,
+                                                         int entries, int c, int cp, double hw, double* __restrict__ s_sum,
+                                                         float* __restrict__ mean) {
+    __shared__ double red[8][32];
+    const int rl = threadIdx.x & 31, e = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + rl;
+    const int per = (entries + 7) / 8;
+    const int z0 = e * per, z1 = min(entries, z0 + per);
+    double a = 0.0;
+    if (r < cp) {
+        for (int z = z0; z < z1; z += 8) {             // 8 independent loads in flight, added in index order
+            float t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = z + k < z1 ? __ldg(rowsum + (size_t)(z + k) * cp + r) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a += (double)t[k];
+        }
     }
+    red[e][rl] = a;
     __syncthreads();
-    const int i = blockIdx.x;                       // one row of the covariance per block
-    if (mean && threadIdx.x == 0) mean[i] = (float)((double)shift[i] + s_sum[i] / hw);
-    for (int j = threadIdx.x; j < c; j += blockDim.x) {
-        // block (1,0) was not computed: take the mirrored entry
-        const bool lower = i >= 128 && j < 128;
-        const size_t idx = lower ? (size_t)j * cp + i : (size_t)i * cp + j;
-        double g = 0.0;
-        for (int z = 0; z < parts; ++z) g += (double)partial[(size_t)z * cp * cp + idx];
-        cov[(size_t)i * c + j] = (g - s_sum[i] * s_sum[j] / hw) / (hw - 1.0) + (i == j ? diag_add : 0.0);
+    if (e == 0 && r < cp) {
+        double t = red[0][rl];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += red[k][rl];
+        s_sum[r] = t;
+        if (mean && r < c) mean[r] = (float)((double)shift[r] + t / hw);
+    }
+}
+
+// Fixed-order fp64 reduction of the per-CTA partial Grams + rank-1 centring correction.  A block owns 64 groups of
+// four consecutive columns of one row; its 4 thread rows split the partials and are folded in index order.
+__global__ void __launch_bounds__(256) cov_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ s_sum,
+                                                           int parts, int c, int cp, double hw, double diag_add,
+                                                           double* __restrict__ cov) {
+    __shared__ double red[4][64][4];
+    const int i = blockIdx.x;                                   // covariance row (computed blocks only: see below)
+    const int jg = threadIdx.x & 63, zs = threadIdx.x >> 6;
+    const int j0 = (i >= 128 ? 128 : 0) + 4 * jg + 256 * blockIdx.y;   // rows >= 128 start at column 128 (SYRK blocks)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const bool live = j0 < cp;
+    if (live) {
+        const float* src = partial + (size_t)i * cp + j0;
+        const int per = (parts + 3) / 4;
+        const int z0 = zs * per, z1 = min(parts, z0 + per);
+#pragma unroll 4
+        for (int z = z0; z < z1; ++z) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)z * cp * cp));
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+    }
+    red[zs][jg][0] = a0; red[zs][jg][1] = a1; red[zs][jg][2] = a2; red[zs][jg][3] = a3;
+    __syncthreads();
+    if (zs == 0 && live) {
+        const double si = s_sum[i];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            if (i < c && j < c) {
+                const double g = ((red[0][jg][e] + red[1][jg][e]) + red[2][jg][e]) + red[3][jg][e];
+                const double v = (g - si * s_sum[j] / hw) / (hw - 1.0);
+                cov[(size_t)i * c + j] = v + (i == j ? diag_add : 0.0);
+                if (i < 128 && j >= 128) cov[(size_t)j * c + i] = v;    // block (1,0) is the mirror of block (0,1)
+            }
+        }
     }
 }
 
@@ -260,7 +310,8 @@ bool cov_fused_supported(const float* x, int64_t c, int64_t hw) {
 size_t cov_fused_workspace_bytes(int64_t c) {
     const size_t cp = c <= 128 ? 128 : 256;
     const size_t g = (size_t)sm_count();
-    return align_up(g * cp * cp * sizeof(float), 256) + align_up(g * cp * sizeof(float), 256) + align_up(cp * sizeof(float), 256);
+    return align_up(g * cp * cp * sizeof(float), 256) + align_up(g * kCovGroups * cp * sizeof(float), 256) +
+           align_up(cp * sizeof(float), 256) + align_up(cp * sizeof(double), 256);
 }
 
 // cov [c,c] fp64 = centred covariance of x [c,hw] (+ diag_add on the diagonal); mean [c] fp32 exact channel means
@@ -271,16 +322,15 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
     char* w = static_cast<char*>(workspace);
     float* partial = reinterpret_cast<float*>(w);
     float* rowsum = reinterpret_cast<float*>(w + align_up((size_t)g * cp * cp * sizeof(float), 256));
-    float* shift = reinterpret_cast<float*>(reinterpret_cast<char*>(rowsum) + align_up((size_t)g * cp * sizeof(float), 256));
-    cov_shift_kernel<<<(cp + 3) / 4, 128, 0, st>>>(x, (int)c, cp, hw, shift);
+    float* shift = reinterpret_cast<float*>(reinterpret_cast<char*>(rowsum) + align_up((size_t)g * kCovGroups * cp * sizeof(float), 256));
+    double* s_sum = reinterpret_cast<double*>(reinterpret_cast<char*>(shift) + align_up((size_t)cp * sizeof(float), 256));
+    cov_shift_kernel<<<(cp + 7) / 8, 256, 0, st>>>(x, (int)c, cp, hw, shift);
     RPST_CUDA(cudaGetLastError());
     CovParams p{};
     p.x = x; p.shift = shift; p.partial = partial; p.rowsum = rowsum; p.hw = hw; p.c = (int)c; p.cp = cp;
     p.k_tiles = (int)((hw + kTileK - 1) / kTileK);
     p.passes = passes;
-    int grid = g < p.k_tiles ? g : p.k_tiles;
-    const int per = (p.k_tiles + grid - 1) / grid;
-    grid = (p.k_tiles + per - 1) / per;             // no CTA without work
+    const int grid = g < p.k_tiles ? g : p.k_tiles;
     static PerDeviceFlag configured_on;
     bool& configured = configured_on.get();
     constexpr size_t smem = 1024 + 3 * 2 * kCovPartBytes;   // 193 KiB for both instantiations
@@ -292,7 +342,9 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
     if (passes == 3) cov_fused_kernel<2><<<grid, kCovThreads, smem, st>>>(p);
     else cov_fused_kernel<1><<<grid, kCovThreads, smem, st>>>(p);
     RPST_CUDA(cudaGetLastError());
-    cov_finalize_kernel<<<(unsigned)c, 256, 0, st>>>(partial, rowsum, shift, grid, (int)c, cp, (double)hw, diag_add, cov, mean);
+    cov_rowsum_kernel<<<(cp + 31) / 32, 256, 0, st>>>(rowsum, shift, grid * kCovGroups, (int)c, cp, (double)hw, s_sum, mean);
+    RPST_CUDA(cudaGetLastError());
+    cov_finalize_kernel<<<dim3((unsigned)cp, 1), 256, 0, st>>>(partial, s_sum, grid, (int)c, cp, (double)hw, diag_add, cov);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }

@@ -34,6 +34,11 @@ size_t cov_fused_workspace_bytes(int64_t c);
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
               cudaStream_t st);
 extern int64_t g_wct_fused_cov;
+// wct_apply.cu: out = T (x - mu_c) + mu_s with the transposed bf16 operand built on the fly
+bool wct_apply_fused_supported(int64_t c, int64_t hw);
+int wct_apply_fused(const float* x, const float* mu_c, const float* mu_s, const void* t_hi, const void* t_lo, float* out,
+                    int64_t c, int64_t hw, int passes, cudaStream_t st);
+extern int64_t g_wct_fused_apply;
 
 namespace {
 
@@ -218,6 +223,12 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
         RPST_CUDA(cudaGetLastError());
         rc = pack_operand_shift(t32, c, c, c, 1, nullptr, nullptr, w + l.t_hi, w + l.t_lo, st);
         if (rc) return rc;
+        if (g_wct_fused_apply && wct_apply_fused_supported(c, hw_c)) {
+            rc = wct_apply_fused(content + i * c * hw_c, mean_c + i * c, mean_s + i * c, w + l.t_hi, w + l.t_lo,
+                                 out + i * c * hw_c, c, hw_c, passes, st);
+            if (rc) return rc;
+            continue;
+        }
         rc = pack_operand_shift(content + i * c * hw_c, hw_c, c, 1, hw_c, nullptr, nullptr, w + l.x_hi,
                                 passes == 3 ? w + l.x_lo : nullptr, st);
         if (rc) return rc;

@@ -104,14 +104,19 @@ def test_fused_covariance_matches_packed_path_and_oracle(rpst, n, c, h, w):
     st = torch.einsum("oc,nchw->nohw", mix.t(), st)
     try:
         rpst.set_tuning("wct_fused_cov", 0)
+        rpst.set_tuning("wct_fused_apply", 0)
         out0, t0 = rpst.wct_fuse(ct.cuda(), st.cuda(), return_transform=True)
     finally:
         rpst.set_tuning("wct_fused_cov", 1)
+        rpst.set_tuning("wct_fused_apply", 1)
     out1, t1 = rpst.wct_fuse(ct.cuda(), st.cuda(), return_transform=True)
     want = R.wct_fuse(ct, st)
     assert R.rel_l2(out1, want) < 1e-3, R.rel_l2(out1, want)
     assert R.rel_l2(out0, want) < 1e-3
     assert R.rel_l2(t1, t0) < 2e-4, R.rel_l2(t1, t0)
+    assert R.rel_l2(out1, out0) < 2e-4, R.rel_l2(out1, out0)      # fused apply (wct_apply.cu) vs pack + GEMM
+    out16 = rpst.wct_fuse(ct.cuda(), st.cuda(), precision="bf16")
+    assert R.rel_l2(out16, want) < 1e-2
     assert R.rel_l2(out1.mean(dim=(2, 3)), st.mean(dim=(2, 3))) < 1e-3
 
 
@@ -121,6 +126,16 @@ def test_fused_covariance_with_mean_far_from_zero(rpst):
     g = torch.Generator().manual_seed(21)
     ct = torch.randn(n, c, h, w, generator=g) * 0.05 + 40.0 + torch.arange(c).view(1, c, 1, 1) * 3.0
     st = torch.randn(n, c, h, w, generator=g) * 0.2 - 25.0
+    want = R.wct_fuse(ct, st)
+    got = rpst.wct_fuse(ct.cuda(), st.cuda())
+    assert R.rel_l2(got, want) < 1e-3, R.rel_l2(got, want)
+
+
+@pytest.mark.parametrize("c,h,w", [(64, 7, 9), (200, 31, 5), (256, 33, 31), (3, 5, 5)])
+def test_fused_apply_ragged_shapes(rpst, c, h, w):
+    """odd H*W (scalar loads, ragged last position tile) and channel counts that are not tile multiples"""
+    ct = torch.relu(torch.randn(1, c, h, w, generator=torch.Generator().manual_seed(31)) + 0.5)
+    st = torch.relu(torch.randn(1, c, h + 2, w + 1, generator=torch.Generator().manual_seed(32)) * 2 + 1)
     want = R.wct_fuse(ct, st)
     got = rpst.wct_fuse(ct.cuda(), st.cuda())
     assert R.rel_l2(got, want) < 1e-3, R.rel_l2(got, want)
