@@ -9,7 +9,7 @@ from .functional import (adain_blend, adain_concat, adain_mapped, adaptive_insta
 
 from . import losses
 from .losses import calc_content_loss, calc_style_loss
-from .modules import SELayer
+from .modules import CCAMDec, SELayer, ccam_attention
 from .mrf import MRFLoss, cal_affinity_map, cal_dist, mrf_match, packed_gemm
 from .wct import matrix_inv_sqrt, matrix_sqrt, wct_fuse, whiten_and_color
 from .sanet import (AdaptiveSANet, AdaptiveTransform, AEALReluModule, AEAModule, SANet, Transform, attention_core,

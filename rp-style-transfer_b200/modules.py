@@ -59,3 +59,37 @@ class SELayer(nn.Module):
         y = self.fc(mean.view(b, c)).view(b, c, 1, 1)
         self.attention_map = y
         return F.plane_affine(x, y)
+
+
+class CCAMDec(nn.Module):
+    """network/adain_rp.py:347-385 (the channel Gram `X Y^T` over H*W is the same dense
+    contraction as the WCT covariance).  Both products run on the tcgen05 GEMM block (bf16x3, fp32-grade); the C x K
+    softmax in between is O(C*K).  As in the reference, `scale` is a plain zero tensor (`nn.Parameter(...).cuda()` does
+    not register), so the shipped module returns its input unchanged; with `scale == 0` the products are skipped."""
+
+    def __init__(self):
+        super().__init__()
+        self.softmax = nn.Softmax(dim=-1)
+        self.scale = torch.zeros(1)
+
+    def forward(self, x, y):
+        x, y = x.detach(), y.detach()
+        scale = float(self.scale)
+        if scale == 0.0:
+            return x + 0.0
+        return x + scale * ccam_attention(x, y)
+
+
+def ccam_attention(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """softmax(rowmax(X Y^T) - X Y^T) Y for x [B,C,H,W], y [B,K,H,W] (network/adain_rp.py:370-381)."""
+    from .mrf import packed_gemm
+    x, y = F._prep(x, "x"), F._prep(y, "y")
+    b, c = x.shape[:2]
+    k = y.shape[1]
+    outs = []
+    for i in range(b):
+        xr, yr = x[i].reshape(c, -1), y[i].reshape(k, -1)
+        energy = packed_gemm(xr, yr)                                     # [C,K]: Gram over H*W
+        att = torch.softmax(energy.max(dim=-1, keepdim=True)[0] - energy, dim=-1)
+        outs.append(packed_gemm(att, yr.t()).reshape(x.shape[1:]))      # [C,K] x [K,N]
+    return torch.stack(outs)

@@ -138,3 +138,15 @@ def test_cal_dist_is_differentiable(rpst):
     dist = (a64 * a64).sum(0)[:, None] + (b64 * b64).sum(0)[None, :] - 2.0 * a64.t() @ b64   # network/base.py:349-360
     ra, rb = torch.autograd.grad(dist, (a64, b64), w.double())
     assert R.rel_l2(ga, ra) < 1e-4 and R.rel_l2(gb, rb) < 1e-4
+
+
+def test_ccam_gram_attention_vs_oracle(rpst):
+    """CCAM's channel Gram + attention on the tcgen05 GEMM block (network/adain_rp.py:358-385)."""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 32, 24, 20, generator=g) * 0.05
+    y = torch.randn(2, 32, 24, 20, generator=g) * 0.05
+    m = rpst.CCAMDec()
+    assert torch.equal(m(x.cuda(), y.cuda()).cpu(), x)                     # as shipped: scale == 0 -> identity
+    m.scale = torch.tensor([0.7])
+    want = R.ccam(x, y, scale=0.7, dtype=torch.float64)
+    assert R.rel_l2(m(x.cuda(), y.cuda()), want) < 1e-4
