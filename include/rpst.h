@@ -48,7 +48,12 @@ RPST_API const char* rpst_last_error(void);
  *   "adain_ctas_per_sm" persistent CTAs per SM for the register-staged pipelined kernel
  *   "adain_path"       0: TMA-staged kernel when planes are 16-byte aligned (default), 1: register-staged
  *   "seg_lag_bytes"    segment AdaIN: bytes of content between a plane's statistics and its apply
- *   "adain_stages"     TMA shared-memory stages = consumer warp groups per CTA (2..7, 32 KiB each) */
+ *   "adain_stages"     TMA shared-memory stages = consumer warp groups per CTA (2..7, 32 KiB each)
+ *   "watchdog_ms"      every in-kernel spin wait traps after this many ms instead of hanging the device (default 4000);
+ *                      0 disables the watchdog (debuggers, MPS time-slicing, compute-sanitizer); applies to all devices
+ *   "attn_flash"       1 (default): C = 512 attention runs as one flash-style kernel when the shape allows; 0: GEMM -> rows -> GEMM
+ *   "wct_fused_cov" / "wct_fused_apply"   1 (default): fused convert+centre+SYRK covariance / fused colouring apply (C <= 256)
+ *   "attn_flash_prof"  device pointer to 32 x uint64 cycle counters filled by the flash kernel's pair 0 (0 = off) */
 RPST_API int rpst_set_tuning(const char* name, int64_t value);
 RPST_API int64_t rpst_get_tuning(const char* name);
 
@@ -89,12 +94,6 @@ RPST_API int rpst_adain_fwd_mapped(const float* content, const float* style, con
                           int64_t n, int64_t c, int64_t hw, int64_t out_batch_stride, float eps,
                           const int32_t* content_map, const int32_t* style_map, void* workspace,
                           size_t workspace_bytes, void* stream);
-
-/* Test hook (no data touched): the ticket schedule the TMA-staged AdaIN kernel walks for a call shape.
- * info[5] (host) = {tickets, statistics items per plane, apply items per plane, lag, merge lead};
- * tickets (device, [max_tickets,3] int32, may be NULL) = (kind, plane, chunk), kind 0 statistics / 1 apply / 2 merge. */
-RPST_API int rpst_debug_adain_schedule(int64_t planes, int64_t hw, int has_style, int has_prev, int stats_only,
-                              int32_t* tickets, int64_t max_tickets, int64_t* info, void* stream);
 
 /* Backward of rpst_adain_fwd w.r.t. content and style (autograd gives this to the reference for
  * free; gradients reach the shared RP encoder through both arguments, SURVEY.md §7 hard part 7).
@@ -154,12 +153,6 @@ RPST_API int rpst_seg_adain_fwd(const float* content, const float* style, const 
                        const uint8_t* s_labels, const float* prev, float* out, int64_t n, int64_t c,
                        int64_t hw_c, int64_t hw_s, float eps, int32_t* label_info, void* workspace,
                        size_t workspace_bytes, void* stream);
-
-/* Test hook: ticket schedule of the segment kernel (see rpst_debug_adain_schedule).  info[5] = {tickets, content
- * statistics items, style statistics items, apply items per plane, lag}; kind 0 content statistics, 1 style
- * statistics, 2 apply, 3 merge. */
-RPST_API int rpst_debug_seg_schedule(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s, int has_prev, int32_t* tickets,
-                            int64_t max_tickets, int64_t* info, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a12 cal_dist(A, B)                                                  network/base.py:349-360

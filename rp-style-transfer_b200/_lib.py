@@ -31,7 +31,6 @@ SIGNATURES = {
     "rpst_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_adain_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
     "rpst_adain_fwd_mapped": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, P, c_size_t, P]),
-    "rpst_debug_adain_schedule": (c_int, [c_int64, c_int64, c_int, c_int, c_int, P, c_int64, P, P]),
     "rpst_adain_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_adain_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, P, c_size_t, P]),
     "rpst_plane_affine": (c_int, [P, P, P, P, c_int64, c_int64, P]),
@@ -40,7 +39,6 @@ SIGNATURES = {
     "rpst_plane_affine2": (c_int, [P, P, P, P, P, P, c_int64, c_int64, P]),
     "rpst_pair_loss_bwd": (c_int, [P, P, P, P, c_int, c_int, P, c_int64, c_int64, P]),
     "rpst_seg_adain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
-    "rpst_debug_seg_schedule": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, P, c_int64, P, P]),
     "rpst_pairwise_sqdist_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "rpst_pairwise_sqdist": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, c_size_t, P]),
     "rpst_mrf_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
@@ -69,6 +67,15 @@ SIGNATURES = {
 }
 
 
+# white-box test hooks (include/rpst_debug.h): only in librpst_debug.so, never in the product library
+DEBUG_LIB_PATH = os.path.join(PKG, "librpst_debug.so")
+DEBUG_SIGNATURES = {
+    "rpst_debug_adain_schedule": (c_int, [c_int64, c_int64, c_int, c_int, c_int, P, c_int64, P, P]),
+    "rpst_debug_seg_schedule": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, P, c_int64, P, P]),
+    "rpst_last_error": (c_char_p, []),
+}
+
+
 class RpstError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"librpst error {code}: {message}")
@@ -94,6 +101,24 @@ def lib() -> ctypes.CDLL:
         fn.argtypes = args
     _lib = handle
     return handle
+
+
+_debug_lib = None
+
+
+def debug_lib() -> ctypes.CDLL:
+    """librpst_debug.so (tests only): the product sources compiled with -DRPST_DEBUG_EXPORTS."""
+    global _debug_lib
+    if _debug_lib is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        handle = ctypes.CDLL(DEBUG_LIB_PATH)
+        for name, (res, args) in DEBUG_SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _debug_lib = handle
+    return _debug_lib
 
 
 def check(code: int) -> None:

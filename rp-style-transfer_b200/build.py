@@ -11,6 +11,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "librpst.so")
+DEBUG_LIB = os.path.join(PKG, "librpst_debug.so")    # same sources + -DRPST_DEBUG_EXPORTS: white-box test hooks only
+DEBUG_SOURCES = ("adain.cu", "seg.cu")               # translation units that carry a debug export
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,7 +35,7 @@ def sources():
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(DEBUG_LIB):
         return True
     t = os.path.getmtime(LIB)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
@@ -48,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs, procs = [], []
+    dbg_objs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
@@ -55,6 +58,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        if os.path.basename(src) in DEBUG_SOURCES:
+            dobj = obj[:-2] + ".dbg.o"
+            dbg_objs.append(dobj)
+            procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, "-DRPST_DEBUG_EXPORTS", "-c", src, "-o", dobj],
+                                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        else:
+            dbg_objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
@@ -71,6 +81,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
     os.replace(LIB + ".tmp", LIB)
+    r = subprocess.run([nvcc, "-shared", "-o", DEBUG_LIB + ".tmp", *dbg_objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link of librpst_debug.so failed")
+    os.replace(DEBUG_LIB + ".tmp", DEBUG_LIB)
     return LIB
 
 

@@ -289,7 +289,7 @@ __device__ __forceinline__ float4 merge_plane_coef_small(const AdainParams& p, i
             do {
                 __nanosleep(40);
                 v[u] = ld_slot(slots + k);
-                if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                if (watchdog_expired(t0)) __trap();
             } while (!slot_valid(v[u]));
         }
     }
@@ -348,7 +348,7 @@ __device__ __forceinline__ float4 merge_plane_coef(const AdainParams& p, int64_t
         do {
             __nanosleep(40);
             v0 = ld_slot(slots);
-            if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+            if (watchdog_expired(t0)) __trap();
         } while (!slot_valid(v0));
     }
     const float kc = v0.x, ks = v0.z;
@@ -360,7 +360,7 @@ __device__ __forceinline__ float4 merge_plane_coef(const AdainParams& p, int64_t
             do {
                 __nanosleep(40);
                 v = ld_slot(slots + k);
-                if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                if (watchdog_expired(t0)) __trap();
             } while (!slot_valid(v));
         }
         const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
@@ -660,7 +660,7 @@ __device__ __noinline__ void merge_plane_coef_group(const AdainParams& p, int64_
                     do {
                         __nanosleep(40);
                         v[u] = ld_slot(slots + k);
-                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                        if (watchdog_expired(t0)) __trap();
                     } while (!slot_valid(v[u]));
                 }
                 const int64_t rem = p.hw - (int64_t)k * p.slot_elems;
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(64 + STAGES * kTmaGroupThreads, 1) adain_tma_k
                     do {
                         __nanosleep(40);
                         cf = ld_slot(&p.coef[plane]);
-                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                        if (watchdog_expired(t0)) __trap();
                     } while (!slot_valid(cf));
                 }
                 cf.x = __shfl_sync(0xffffffffu, cf.x, 0);
@@ -1596,6 +1596,7 @@ int adain_fwd_impl(const float* content, const float* style, const float* prev, 
 }
 }  // namespace
 
+#ifdef RPST_DEBUG_EXPORTS   // white-box test hooks: only in librpst_debug.so (tests/test_schedule_gpu.py), never in the product library
 // Test hook: the ticket schedule the TMA kernel would walk for this call shape.  info = {tickets, stats items
 // per plane, apply items per plane, lag, merge lead}; tickets [max_tickets,3] receives (kind, plane, chunk) with
 // kind 0 statistics, 1 apply, 2 merge.  Used by tests/test_schedule_gpu.py to check the schedule's invariants
@@ -1619,6 +1620,7 @@ extern "C" int rpst_debug_adain_schedule(int64_t planes, int64_t hw, int has_sty
     }
     return RPST_OK;
 }
+#endif  // RPST_DEBUG_EXPORTS
 
 extern "C" size_t rpst_adain_bwd_workspace_bytes(int64_t n, int64_t c, int64_t hw) {
     if (n <= 0 || c <= 0 || hw <= 0) return 256;
@@ -1667,3 +1669,5 @@ extern "C" int rpst_plane_affine(const float* x, const float* scale, const float
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
+
+RPST_WATCHDOG_SETTER(adain)

@@ -37,15 +37,27 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Watchdog: a wait that lasts longer than this is a protocol bug; trap (the launch fails with an
-// error) instead of hanging the device.
-constexpr uint64_t kWatchdogNs = 4000000000ull;
+// Watchdog: a wait that lasts longer than this is a protocol bug; trap (the launch fails with an error) instead of
+// hanging the device.  Opt-out / adjustable: rpst_set_tuning("watchdog_ms", 0) disables it (debuggers, MPS
+// time-slicing and compute-sanitizer stretch waits legitimately).  The limit is a per-translation-unit device
+// variable (no relocatable device code in this library); RPST_WATCHDOG_SETTER registers the TU's setter with api.cu.
+static __device__ unsigned long long g_watchdog_ns = 4000000000ull;
+__device__ __forceinline__ bool watchdog_expired(uint64_t t0) {
+    const unsigned long long limit = g_watchdog_ns;
+    return limit != 0 && global_timer_ns() - t0 > limit;
+}
+#define RPST_WATCHDOG_SETTER(tag)                                                                            \
+    namespace rpst {                                                                                         \
+    int set_watchdog_##tag(unsigned long long ns) {                                                          \
+        return cudaMemcpyToSymbol(g_watchdog_ns, &ns, sizeof(ns)) == cudaSuccess ? 0 : -2;                   \
+    }                                                                                                        \
+    }
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = global_timer_ns();
     while (!mbar_try_wait(bar, parity)) {
-        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+        if (watchdog_expired(t0)) __trap();
     }
 }
 

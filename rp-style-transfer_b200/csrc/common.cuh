@@ -7,6 +7,9 @@
 #include <string.h>
 
 #include "../../include/rpst.h"
+#ifdef RPST_DEBUG_EXPORTS
+#include "../../include/rpst_debug.h"
+#endif
 
 namespace rpst {
 

@@ -350,3 +350,5 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
 }
 
 }  // namespace rpst
+
+RPST_WATCHDOG_SETTER(cov)

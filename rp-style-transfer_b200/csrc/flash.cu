@@ -554,3 +554,5 @@ int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, i
 }
 
 }  // namespace rpst
+
+RPST_WATCHDOG_SETTER(flash)

@@ -449,3 +449,5 @@ extern "C" int rpst_gemm_packed(const void* a_hi, const void* a_lo, const void* 
     return gemm_packed(a_hi, a_lo, b_hi, b_lo, out, m, n, k, ldo, passes, alpha, row_add, col_add,
                        static_cast<cudaStream_t>(stream));
 }
+
+RPST_WATCHDOG_SETTER(gemm)

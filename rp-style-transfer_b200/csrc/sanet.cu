@@ -818,3 +818,5 @@ extern "C" int rpst_cosine_affinity(const float* content, const float* style, fl
     }
     return RPST_OK;
 }
+
+RPST_WATCHDOG_SETTER(sanet)

@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                                     do {   // straggling statistics item
                                         __nanosleep(64);
                                         v[u] = ld_slot1(sp);
-                                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                                        if (watchdog_expired(t0)) __trap();
                                     } while (!slot1_valid(v[u]));
                                 }
                                 s4[which * 2 + 0] += (double)v[u].x;
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     const uint64_t t0 = global_timer_ns();
                     while (ld_acquire(&p.ready[plane]) == 0) {
                         __nanosleep(64);
-                        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+                        if (watchdog_expired(t0)) __trap();
                     }
                 }
                 named_bar_sync(1 + group, kSegGroupThreads);
@@ -1047,6 +1047,7 @@ __global__ void seg_schedule_dump_kernel(SegTmaParams p, int32_t* out) {
 
 using namespace rpst;
 
+#ifdef RPST_DEBUG_EXPORTS   // white-box test hooks: only in librpst_debug.so (tests/test_schedule_gpu.py), never in the product library
 // Test hook, see rpst_debug_adain_schedule: kind 0 content statistics, 1 style statistics, 2 apply, 3 merge;
 // info = {tickets, content items, style items, apply items, lag}.
 extern "C" int rpst_debug_seg_schedule(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s, int has_prev, int32_t* tickets,
@@ -1065,6 +1066,7 @@ extern "C" int rpst_debug_seg_schedule(int64_t n, int64_t c, int64_t hw_c, int64
     }
     return RPST_OK;
 }
+#endif  // RPST_DEBUG_EXPORTS
 
 extern "C" size_t rpst_seg_adain_workspace_bytes(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     if (n <= 0 || c <= 0) return 256;
@@ -1190,3 +1192,5 @@ extern "C" int rpst_seg_adain_fwd(const float* content, const float* style, cons
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
+
+RPST_WATCHDOG_SETTER(seg)

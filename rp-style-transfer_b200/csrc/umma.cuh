@@ -143,7 +143,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     if (mbar_try_wait_cluster(bar, parity)) return;
     const uint64_t t0 = global_timer_ns();
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (global_timer_ns() - t0 > kWatchdogNs) __trap();
+        if (watchdog_expired(t0)) __trap();
     }
 }
 __device__ __forceinline__ void umma2_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

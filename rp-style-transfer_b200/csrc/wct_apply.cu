@@ -275,3 +275,5 @@ int wct_apply_fused(const float* x, const float* mu_c, const float* mu_s, const 
 }
 
 }  // namespace rpst
+
+RPST_WATCHDOG_SETTER(wct_apply)

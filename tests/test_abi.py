@@ -58,6 +58,24 @@ def test_ctypes_table_mirrors_header():
                 assert re.match(rf"^{re.escape(k)}\s+\w+$", decl), (name, decl, k)
 
 
+def test_debug_hooks_are_not_in_the_product_library():
+    """`rpst_debug_*` must not be exported from librpst.so; they live in librpst_debug.so
+    (include/rpst_debug.h), which the schedule tests load."""
+    import rpst
+    out = subprocess.run(["nm", "-D", "--defined-only", rpst._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "rpst_debug" not in out
+    dbg = subprocess.run(["nm", "-D", "--defined-only", rpst._lib.DEBUG_LIB_PATH], capture_output=True, text=True).stdout
+    assert set(rpst._lib.DEBUG_SIGNATURES) <= set(re.findall(r"\b(rpst_\w+)\b", dbg))
+    assert rpst._lib.debug_lib().rpst_debug_adain_schedule is not None
+
+
+def test_watchdog_knob_round_trips_without_gpu():
+    import rpst
+    assert rpst.get_tuning("watchdog_ms") == 4000
+    rpst.set_tuning("watchdog_ms", 0)          # opt out (no device here: only the host-side value changes)
+    rpst.set_tuning("watchdog_ms", 4000)
+
+
 def test_version_and_tuning(lib):
     import rpst
     assert rpst.version() == 100
@@ -106,5 +124,5 @@ def test_library_is_sm_100a_with_tcgen05_and_tma_sass():
     archs = set(re.findall(r"\.(sm_\w+)\.cubin", elf))
     assert archs == {"sm_100a"}, archs
     sass = subprocess.run([cuobjdump, "-sass", rpst._lib.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "SYNCS"):
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS"):
         assert mnemonic in sass, mnemonic

@@ -13,12 +13,12 @@ pytestmark = pytest.mark.gpu
 
 def dump(planes, hw, has_style, has_prev, stats_only):
     import rpst
-    L = rpst._lib.lib()
+    D = rpst._lib.debug_lib()     # white-box hooks live in librpst_debug.so, not in the product library
     info = (ctypes.c_int64 * 5)()
-    rpst._lib.check(L.rpst_debug_adain_schedule(planes, hw, has_style, has_prev, stats_only, None, 0, info, None))
+    rpst._lib.check(D.rpst_debug_adain_schedule(planes, hw, has_style, has_prev, stats_only, None, 0, info, None))
     total = int(info[0])
     buf = torch.empty(total, 3, dtype=torch.int32, device="cuda")
-    rpst._lib.check(L.rpst_debug_adain_schedule(planes, hw, has_style, has_prev, stats_only, buf.data_ptr(), total, info,
+    rpst._lib.check(D.rpst_debug_adain_schedule(planes, hw, has_style, has_prev, stats_only, buf.data_ptr(), total, info,
                                                 torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return buf.cpu().numpy(), [int(v) for v in info]
@@ -58,12 +58,12 @@ def test_schedule_invariants(planes, hw, has_style, has_prev, stats_only):
 
 def dump_seg(n, c, hw_c, hw_s, has_prev):
     import rpst
-    L = rpst._lib.lib()
+    D = rpst._lib.debug_lib()     # white-box hooks live in librpst_debug.so, not in the product library
     info = (ctypes.c_int64 * 5)()
-    rpst._lib.check(L.rpst_debug_seg_schedule(n, c, hw_c, hw_s, has_prev, None, 0, info, None))
+    rpst._lib.check(D.rpst_debug_seg_schedule(n, c, hw_c, hw_s, has_prev, None, 0, info, None))
     total = int(info[0])
     buf = torch.empty(total, 3, dtype=torch.int32, device="cuda")
-    rpst._lib.check(L.rpst_debug_seg_schedule(n, c, hw_c, hw_s, has_prev, buf.data_ptr(), total, info,
+    rpst._lib.check(D.rpst_debug_seg_schedule(n, c, hw_c, hw_s, has_prev, buf.data_ptr(), total, info,
                                               torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return buf.cpu().numpy(), [int(v) for v in info]
