@@ -288,6 +288,32 @@ RPST_API int rpst_gemm_packed(const void* a_hi, const void* a_lo, const void* b_
                      int64_t m, int64_t n, int64_t k, int64_t ldo, int passes, float alpha,
                      const float* row_add, const float* col_add, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f2 / f4  Pointwise (1x1) convolution with fused prologue / epilogue (csrc/pwconv.cu):
+ *     y[b,o,n] = act( sum_c W[o,c] * ((x[b,c,n] - sub[b,c]) * mul[b,c]) + bias[o] ) (+ residual[b,o,n])
+ *   - SANet projections with `mean_variance_norm` folded into the operand conversion (sub = mean, mul = 1/std) and
+ *     Q / K emitted as packed attention operands                         network/sanet.py:82-99
+ *   - RP-encoder 1x1 conv + LeakyReLU with the AdaIN statistics from the epilogue        network/base.py:170-198
+ *   x [b,cin,hw] fp32; w_hi / w_lo: the [cout,cin] weight packed with rpst_pack_operand(w, cout, cin, cin, 1, ...);
+ *   bias [cout], sub / mul [b,cin], residual [b,cout,hw] may be NULL; act 0 none, 1 LeakyReLU(slope);
+ *   out fp32 [b,cout,hw] and / or out_hi, out_lo: packed [hw x cout] operand tiles per sample (rows = positions; sample
+ *   stride align_up(rpst_packed_operand_bytes(hw, cout), 256); needs hw % 128 == 0, cout % 64 == 0);
+ *   stats_partial (rpst_conv1x1_stats_bytes) receives per-warp (sum, sum of squares) of y; rpst_conv1x1_stats_finalize
+ *   turns them into mean / sqrt(unbiased var + eps) [b,cout] — calc_mean_std of y without reading y again.
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_conv1x1_stats_bytes(int64_t b, int64_t cout, int64_t hw);
+RPST_API int rpst_conv1x1(const float* x, const void* w_hi, const void* w_lo, const float* bias, const float* sub,
+                 const float* mul, const float* residual, float* out, void* out_hi, void* out_lo,
+                 float* stats_partial, int64_t b, int64_t cin, int64_t cout, int64_t hw, int act, float slope,
+                 int passes, void* stream);
+RPST_API int rpst_conv1x1_stats_finalize(const float* stats_partial, int64_t b, int64_t cout, int64_t hw, float eps,
+                                float* mean, float* std, void* stream);
+/* Attention core (rpst_sanet_attn_fwd) with Q / K already packed by rpst_conv1x1 (C = 512, Lc % 128 == 0, Ls % 256 == 0). */
+RPST_API size_t rpst_sanet_attn_packed_workspace_bytes(int64_t b, int64_t lc, int64_t ls);
+RPST_API int rpst_sanet_attn_fwd_packed(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const float* h,
+                               float* out, int64_t b, int64_t c, int64_t lc, int64_t ls, int passes, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ from .sanet import (AdaptiveSANet, AdaptiveTransform, AEALReluModule, AEAModule,
                     cal_affinity_matrix)
 from .segment import adaptive_instance_normalization_with_segment, do_mask_stylized, load_label_map, seg_adain_batch
 
+from .conv import adain_from_stats, conv1x1
 from .decode import multiscale_transform
 from .install import install, uninstall
 

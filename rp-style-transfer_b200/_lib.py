@@ -63,6 +63,11 @@ SIGNATURES = {
     "rpst_sanet_adaptive_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "rpst_sanet_attn_adaptive_fwd": (c_int, [P, P, P, P, P, c_int64, P, P, P, P, c_int, c_float, c_float, c_float,
                                              P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
+    "rpst_conv1x1_stats_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_conv1x1": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_int, P]),
+    "rpst_conv1x1_stats_finalize": (c_int, [P, c_int64, c_int64, c_int64, c_float, P, P, P]),
+    "rpst_sanet_attn_packed_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "rpst_sanet_attn_fwd_packed": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P, c_size_t, P]),
     "rpst_seg_adain_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_float, P, P, c_size_t, P]),
 }
 

@@ -38,7 +38,7 @@ int set_watchdog_flash(unsigned long long ns);
 int set_watchdog_gemm(unsigned long long ns);
 int set_watchdog_sanet(unsigned long long ns);
 int set_watchdog_seg(unsigned long long ns);
-int set_watchdog_wct_apply(unsigned long long ns);
+int set_watchdog_pwconv(unsigned long long ns);
 
 static int64_t g_watchdog_ms = 4000;
 
@@ -58,7 +58,7 @@ static int apply_watchdog(int64_t ms) {
         rc |= set_watchdog_gemm(ns);
         rc |= set_watchdog_sanet(ns);
         rc |= set_watchdog_seg(ns);
-        rc |= set_watchdog_wct_apply(ns);
+        rc |= set_watchdog_pwconv(ns);
     }
     cudaSetDevice(cur);
     if (rc) {

@@ -485,9 +485,16 @@ size_t flash_attn_workspace_bytes(int64_t lc, int64_t ls, int64_t samples) {
 }
 
 // softmax(F^T G) applied to H for `b` samples, F [b,512,lc], G/H [b,512,ls] -> out [b,512,lc]; samples are processed
-// in groups of as many as the workspace holds (one persistent launch per group).
-int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t lc, int64_t ls,
-                   int passes, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// in groups of as many as the workspace holds (one persistent launch per group).  With `q_pre` / `k_pre` the Q / K
+// operand tiles come from the caller (pwconv.cu emits them from the 1x1 projections' epilogue: hi at q_pre, lo at
+// q_pre + q_pre_lo_offset, sample stride q_pre_batch) and f / g are not read.
+struct FlashPrepacked {
+    const char* q_hi; const char* q_lo; const char* k_hi; const char* k_lo;
+    int64_t q_batch, k_batch;
+};
+
+int flash_attn_run(const float* f, const float* g, const float* h, const FlashPrepacked* pre, float* out, int64_t b, int64_t lc,
+                   int64_t ls, int passes, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const bool x3 = passes == 3;
     int64_t kb_max = b;
     while (kb_max > 1 && flash_attn_workspace_bytes(lc, ls, kb_max) > workspace_bytes) --kb_max;
@@ -511,15 +518,17 @@ int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, i
         char* k_hi = q_lo + (size_t)kb_max * l.q_b;
         char* k_lo = k_hi + (size_t)kb_max * l.k_b;
         char* vt = k_lo + (size_t)kb_max * l.k_b;
-        const float* fi = f + i * kFlD * lc;
-        const float* gi = g + i * kFlD * ls;
         const float* hi_ = h + i * kFlD * ls;
         int rc;
-        // Q = F^T and K = G^T: rows = positions (unit stride in the source), K = channels
-        if ((rc = pack_operand_batched(fi, lc, kFlD, 1, lc, nullptr, nullptr, q_hi, x3 ? q_lo : nullptr, kb, kFlD * lc,
-                                       (int64_t)l.q_b, 0, st))) return rc;
-        if ((rc = pack_operand_batched(gi, ls, kFlD, 1, ls, nullptr, nullptr, k_hi, x3 ? k_lo : nullptr, kb, kFlD * ls,
-                                       (int64_t)l.k_b, 0, st))) return rc;
+        if (!pre) {
+            const float* fi = f + i * kFlD * lc;
+            const float* gi = g + i * kFlD * ls;
+            // Q = F^T and K = G^T: rows = positions (unit stride in the source), K = channels
+            if ((rc = pack_operand_batched(fi, lc, kFlD, 1, lc, nullptr, nullptr, q_hi, x3 ? q_lo : nullptr, kb, kFlD * lc,
+                                           (int64_t)l.q_b, 0, st))) return rc;
+            if ((rc = pack_operand_batched(gi, ls, kFlD, 1, ls, nullptr, nullptr, k_hi, x3 ? k_lo : nullptr, kb, kFlD * ls,
+                                           (int64_t)l.k_b, 0, st))) return rc;
+        }
         float* unscale = nullptr;
         if (x3) {
             // V as IEEE half, pre-scaled by a per-sample power of two (exact) so that it cannot overflow
@@ -536,8 +545,16 @@ int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, i
             if ((rc = pack_operand_batched(hi_, kFlD, ls, ls, 1, nullptr, nullptr, vt, nullptr, kb, kFlD * ls, (int64_t)l.v_b, 0, st))) return rc;
         }
         FlashParams p{};
-        p.q_hi = q_hi; p.q_lo = q_lo; p.k_hi = k_hi; p.k_lo = k_lo; p.v = vt;
-        p.q_batch = (int64_t)l.q_b; p.k_batch = (int64_t)l.k_b; p.v_batch = (int64_t)l.v_b;
+        if (pre) {
+            p.q_hi = pre->q_hi + i * pre->q_batch; p.q_lo = pre->q_lo ? pre->q_lo + i * pre->q_batch : nullptr;
+            p.k_hi = pre->k_hi + i * pre->k_batch; p.k_lo = pre->k_lo ? pre->k_lo + i * pre->k_batch : nullptr;
+            p.q_batch = pre->q_batch; p.k_batch = pre->k_batch;
+        } else {
+            p.q_hi = q_hi; p.q_lo = q_lo; p.k_hi = k_hi; p.k_lo = k_lo;
+            p.q_batch = (int64_t)l.q_b; p.k_batch = (int64_t)l.k_b;
+        }
+        p.v = vt;
+        p.v_batch = (int64_t)l.v_b;
         p.v_unscale = unscale;
         p.out = out + i * kFlD * lc;
         p.lc = (int)lc; p.ls = (int)ls;
@@ -553,6 +570,37 @@ int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, i
     return RPST_OK;
 }
 
+int flash_attn_fwd(const float* f, const float* g, const float* h, float* out, int64_t b, int64_t lc, int64_t ls,
+                   int passes, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    return flash_attn_run(f, g, h, nullptr, out, b, lc, ls, passes, workspace, workspace_bytes, st);
+}
+
 }  // namespace rpst
+
+using namespace rpst;
+
+/* Attention core with Q / K already packed (rpst_conv1x1 with out_hi / out_lo): q tiles [b][lc x 512], k tiles
+ * [b][ls x 512], sample strides = align_up(packed_operand_bytes(l, 512), 256); h fp32 [b,512,ls] -> out [b,512,lc]. */
+extern "C" size_t rpst_sanet_attn_packed_workspace_bytes(int64_t b, int64_t lc, int64_t ls) {
+    if (b <= 0 || lc <= 0 || ls <= 0) return 256;
+    return flash_attn_workspace_bytes(lc, ls, b);
+}
+
+extern "C" int rpst_sanet_attn_fwd_packed(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo, const float* h,
+                                          float* out, int64_t b, int64_t c, int64_t lc, int64_t ls, int passes, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    RPST_CHECK_ARG(b >= 0, "sanet_packed: negative batch");
+    if (b == 0) return RPST_OK;
+    RPST_CHECK_ARG(flash_attn_supported(c, lc, ls), "sanet_packed: needs C = 512, Lc %% 128 == 0, Ls %% 256 == 0");
+    RPST_CHECK_ARG(q_hi && k_hi && h && out && workspace, "sanet_packed: null pointer");
+    RPST_CHECK_ARG(passes == 1 || (passes == 3 && q_lo && k_lo), "sanet_packed: passes must be 1, or 3 with the lo tiles");
+    RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sanet_packed: workspace must be 256-byte aligned");
+    FlashPrepacked pre{};
+    pre.q_hi = static_cast<const char*>(q_hi); pre.q_lo = static_cast<const char*>(q_lo);
+    pre.k_hi = static_cast<const char*>(k_hi); pre.k_lo = static_cast<const char*>(k_lo);
+    pre.q_batch = (int64_t)align_up(packed_operand_bytes(lc, 512), 256);
+    pre.k_batch = (int64_t)align_up(packed_operand_bytes(ls, 512), 256);
+    return flash_attn_run(nullptr, nullptr, h, &pre, out, b, lc, ls, passes, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 
 RPST_WATCHDOG_SETTER(flash)

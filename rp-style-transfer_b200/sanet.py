@@ -254,8 +254,14 @@ class SANet(nn.Module):
         self.sm = nn.Softmax(dim=-1)
         self.out_conv = nn.Conv2d(in_planes, in_planes, (1, 1))
         self.precision = "fp32"
+        self.fused = True      # inference at in_planes = 512: projections + normalisation + residual on the tcgen05 block
 
     def forward(self, content, style):
+        from .conv import sanet_forward_fused, sanet_fused_supported
+        needs_grad = torch.is_grad_enabled() and (content.requires_grad or style.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        if getattr(self, "fused", True) and not needs_grad and sanet_fused_supported(content, style):
+            return sanet_forward_fused(self, content, style)
         F = self.f(mean_variance_norm(content))
         G = self.g(mean_variance_norm(style))
         H = self.h(style)
