@@ -165,6 +165,24 @@ def config4(dev, peaks, cpu=True, batch=16):
                        "frac_bf16": total_flops / (total_ms["bf16"] / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
                        "tensor_pipe": tp or None,
                        "note": "algorithmic flops 4 L^2 C per sample; fp32-grade issues 3 bf16 passes on the logits + 1 half pass on P.V"}
+    # the whole SANet(512) module at relu4_1 (instance normalisation + four 1x1 projections + attention + residual):
+    # projections on the tcgen05 block with the normalisation folded in (rpst.conv) vs cuDNN convolutions around the core
+    try:
+        torch.manual_seed(0)
+        m = rpst.SANet(512).to(dev)
+        c, s = R.synth_features((4, 512, 128, 128), cfg=4, device=dev)
+        mod = {}
+        with torch.no_grad():
+            for prec in ("fp32", "bf16"):
+                m.precision = prec
+                m.fused = True
+                mod[f"fused_{prec}_ms_per_sample"] = dev_time_ms(lambda: m(c, s), 3, 1) / 4
+                m.fused = False
+                mod[f"cudnn_projections_{prec}_ms_per_sample"] = dev_time_ms(lambda: m(c, s), 3, 1) / 4
+        out["module_L16384"] = mod
+        del m, c, s
+    except Exception as e:
+        out["module_L16384"] = {"error": repr(e)[:200]}
     out["l2"] = "operands of one call: 3 x 512 MiB (L=16384) / 3 x 128 MiB (L=4096), beyond L2"
     torch.cuda.empty_cache()
     if cpu:

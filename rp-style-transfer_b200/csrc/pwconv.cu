@@ -49,7 +49,7 @@ struct PwParams {
     char* out_hi;            // packed tiles, rows = positions, K = output channels (the attention kernel's Q / K format) or null
     char* out_lo;
     int64_t tile_batch;      // bytes between samples of the packed output
-    float* stats;            // [b, tiles * 4, cout, 2] partial (sum, sum of squares) of the stored values or null
+    float* stats;            // [b, grid * 4, cout, 2] per-CTA-and-warp partial (sum, sum of squares) of the stored values (zeroed by the host) or null
     float slope;             // LeakyReLU slope when act == 1
     int act;
     int64_t hw;
@@ -60,6 +60,7 @@ struct PwParams {
     int batch;
     int vec_ok;              // x 16-byte aligned and hw % 4 == 0: 128-bit loads
     int parts;
+    int stat_ctas;           // CTA slots per sample in `stats` (= SM count >= grid)
 };
 
 // A tile of one k-block: [8 K-atoms (8 channels each)][2 MN-atoms (64 positions each)][8 channel rows][128 B]
@@ -97,7 +98,11 @@ __device__ __forceinline__ PwItem pw_item(const PwParams& p, int item) {
     return it;
 }
 
-template <int PARTS>
+// VEC: hw % 4 == 0, x 16-byte aligned, cin % 8 == 0 (128-bit loads, no ragged-edge code in the hot loop);
+// EPI: 0 fp32 output only, 1 packed operand tiles (+ optional fp32), 2 fp32 output + epilogue statistics.
+// Separate instantiations keep each kernel's code small: the warp roles run different code at the same time and
+// a 64 KiB kernel thrashed the instruction cache (12 % of the stalls were "no instruction").
+template <int PARTS, bool VEC, int EPI>
 __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
     // stage: A hi [128 pos x 64 ch] 16 KiB (+ lo 16 KiB), B hi [256 out x 64 ch] 32 KiB (+ lo 32 KiB)
     constexpr uint32_t kA = kTileBytes, kB = 2 * kTileBytes;
@@ -107,6 +112,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t full_a[NST], full_b[NST], empty[NST], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float stat_tile[EPI == 2 ? 4 * 32 * 33 : 1];
+    __shared__ float stat_acc[EPI == 2 ? 4 * kPwMaxC * 2 : 1];   // running per-warp column sums of the current sample
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.batch * p.tiles * p.col_tiles;
 
@@ -187,8 +194,24 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
         const int q = warp & 3;
         const int r = q * 32 + lane;                       // row of the position tile
         int ti = 0;
+        float* acc = stat_acc + (warp - 2) * (kPwMaxC * 2);
+        int acc_sample = -1;
+        auto flush_stats = [&](int sample) {               // this warp's sums of `sample` -> global partial, then clear
+            if (EPI != 2 || !p.stats || sample < 0) return;
+            float* dst = p.stats + (((int64_t)sample * p.stat_ctas + blockIdx.x) * 4 + (warp - 2)) * p.cout * 2;
+            for (int o = lane; o < p.cout; o += 32) {
+                dst[2 * o] = acc[2 * o];
+                dst[2 * o + 1] = acc[2 * o + 1];
+            }
+        };
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
             const PwItem w = pw_item(p, item);
+            if (EPI == 2 && p.stats && w.sample != acc_sample) {
+                flush_stats(acc_sample);
+                for (int o = lane; o < 2 * kPwMaxC; o += 32) acc[o] = 0.f;
+                __syncwarp();
+                acc_sample = w.sample;
+            }
             const int buf = ti & 1;
             mbar_wait(&acc_full[buf], (ti >> 1) & 1);
             tcgen05_fence_after();
@@ -200,21 +223,44 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
             for (int c0 = 0; c0 < w.ncol; c0 += 32) {
                 const int o0 = 256 * w.ct + c0;            // first output channel of this chunk
                 tmem_ld_32x32(tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (o0 + 32 <= p.cout) {
+                    // whole chunk inside the channel range: uniform branches hoisted out of the 32-element loops (the
+                    // per-element predicated form cost ~30 instructions per value and made the epilogue the bottleneck)
+                    if (bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float y = v[j] + ((bias && o0 + j < p.cout) ? __ldg(bias + o0 + j) : 0.f);
-                    if (p.act == 1) y = y >= 0.f ? y : p.slope * y;
-                    if (p.residual && inside && o0 + j < p.cout)
-                        y += __ldcs(p.residual + ((int64_t)w.sample * p.cout + o0 + j) * p.hw + n);
-                    v[j] = (inside && o0 + j < p.cout) ? y : 0.f;
-                }
-                if (p.out && inside) {
-                    float* dst = p.out + ((int64_t)w.sample * p.cout + o0) * p.hw + n;
+                        for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + o0 + j);
+                    }
+                    if (p.act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (o0 + j < p.cout) __stcs(dst + (int64_t)j * p.hw, v[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : p.slope * v[j];
+                    }
+                    if (inside) {
+                        if (p.residual) {
+                            const float* res = p.residual + ((int64_t)w.sample * p.cout + o0) * p.hw + n;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __ldcs(res + (int64_t)j * p.hw);
+                        }
+                        if (p.out) {
+                            float* dst = p.out + ((int64_t)w.sample * p.cout + o0) * p.hw + n;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) __stcs(dst + (int64_t)j * p.hw, v[j]);
+                        }
+                    } else if (EPI != 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const bool ok = inside && o0 + j < p.cout;
+                        float y = v[j] + ((bias && o0 + j < p.cout) ? __ldg(bias + o0 + j) : 0.f);
+                        if (p.act == 1) y = y >= 0.f ? y : p.slope * y;
+                        if (p.residual && ok) y += __ldcs(p.residual + ((int64_t)w.sample * p.cout + o0 + j) * p.hw + n);
+                        v[j] = ok ? y : 0.f;
+                        if (p.out && ok) __stcs(p.out + ((int64_t)w.sample * p.cout + o0 + j) * p.hw + n, y);
+                    }
                 }
-                if (p.out_hi) {
+                if (EPI == 1 && p.out_hi) {
                     // packed tile (position tile t, 64-channel block o0 / 64): this thread's row, four 16-byte chunks
                     const int kbo = o0 >> 6, ko_tiles = p.coutp >> 6;
                     char* base = p.out_hi + (int64_t)w.sample * p.tile_batch + ((int64_t)w.t * ko_tiles + kbo) * kTileBytes +
@@ -235,29 +281,25 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
                         if (base_lo) *reinterpret_cast<uint4*>(base_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
                     }
                 }
-                if (p.stats) {
-                    // per-channel (sum, sum of squares) over this warp's 32 positions: butterfly reduce-scatter, after
-                    // which lane j holds the totals of column j (31 shuffles per quantity instead of 5 x 32)
-                    float s1[32], s2[32];
+                if (EPI == 2 && p.stats) {
+                    // per-channel (sum, sum of squares) over this warp's 32 positions: transpose the 32 x 32 chunk through
+                    // a padded shared-memory tile (32 stores + 32 conflict-free loads per thread; the shuffle butterfly
+                    // cost ~6k cycles per chunk), lane j then owns column j
+                    float* tile = stat_tile + (warp - 2) * (32 * 33);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+                    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-                    for (int w2 = 16; w2 >= 1; w2 >>= 1) {
-                        const bool upper = (lane & w2) != 0;
-#pragma unroll
-                        for (int j = 0; j < w2; ++j) {
-                            // keep the half of the columns that matches this lane's bit, send the other half
-                            const float keep1 = upper ? s1[j + w2] : s1[j], send1 = upper ? s1[j] : s1[j + w2];
-                            const float keep2 = upper ? s2[j + w2] : s2[j], send2 = upper ? s2[j] : s2[j + w2];
-                            s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, w2);
-                            s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w2);
-                        }
+                    for (int r2 = 0; r2 < 32; ++r2) {
+                        const float y = tile[r2 * 33 + lane];
+                        t1 += y;
+                        t2 = fmaf(y, y, t2);
                     }
-                    // lane's column index: bits were consumed from the top: column = lane (bit-reversal free by construction)
-                    if (o0 + lane < p.cout) {
-                        float* dst = p.stats + ((((int64_t)w.sample * p.tiles + w.t) * 4 + q) * p.cout + o0 + lane) * 2;
-                        dst[0] = s1[0];
-                        dst[1] = s2[0];
+                    __syncwarp();
+                    if (o0 + lane < p.cout) {              // lane owns column o0 + lane: plain read-modify-write, fixed order
+                        acc[2 * (o0 + lane)] += t1;
+                        acc[2 * (o0 + lane) + 1] += t2;
                     }
                 }
             }
@@ -265,54 +307,87 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        __syncwarp();
+        flush_stats(acc_sample);
     } else {
         // ------------------------------------------------------------------ converters: (x - sub) * mul as bf16 hi / lo, MN-major tile
         const int cw = warp - 6;                           // warp cw converts channels [8 cw, 8 cw + 8) of every k-block
         // lane -> positions 4 lane .. 4 lane + 3 of the tile: MN-atom lane / 16, 16-byte chunk (lane % 16) / 2, half lane & 1
         const uint32_t lane_off = (uint32_t)(lane >> 4) * kPwLBO + ((uint32_t)lane & 1u) * 8u;
         const uint32_t chunk = ((uint32_t)lane & 15u) >> 1;
-        // Work units u = (item, k-block) in issue order; three register buffers rotate so that the loads of units u+1 and
-        // u+2 are in flight while unit u is converted (load-latency bound: 8 loads per thread in flight gave 1.7 TB/s).
-        const int my_items = (int)blockIdx.x < items ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const uint32_t units = (uint32_t)my_items * (uint32_t)p.kb;
-        auto load_unit = [&](float4 (&v)[8], uint32_t u) {
-            if (u >= units) return;
-            const PwItem w = pw_item(p, (int)blockIdx.x + (int)(u / p.kb) * (int)gridDim.x);
-            const int kb = (int)(u % p.kb);
+        // Work units (item, k-block) in issue order; three register buffers rotate so that the loads of two units are in
+        // flight while a third is converted (load-latency bound: 8 loads per thread in flight gave 1.7 TB/s).  Two cursors
+        // (load / convert) walk the unit sequence incrementally: no divisions in the loop.
+        struct Cursor {
+            int item, kb;
+            const float* xrow;     // x + (sample * cin + cw * 8) * hw + n  (k-block 0, channel row 0 of this warp)
+            int soff;              // sample * cin + cw * 8: index of this warp's first channel in sub / mul
+            int64_t n;             // first position of this lane (generic path)
+            bool vec, live;
+        };
+        const int64_t kb_stride = 64 * p.hw;
+        auto decode = [&](Cursor& c) {
+            c.live = c.item < items;
+            if (!c.live) return;
+            const PwItem w = pw_item(p, c.item);
             const int64_t n = (int64_t)w.t * 128 + 4 * lane;
-            const bool vec = p.vec_ok && n + 4 <= p.hw;               // aligned 128-bit loads; otherwise per-element
-            const float* xs = p.x + (int64_t)w.sample * p.cin * p.hw;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = kb * 64 + cw * 8 + j;
-                if (c < p.cin && vec) {
-                    v[j] = __ldcs(reinterpret_cast<const float4*>(xs + (int64_t)c * p.hw + n));
-                } else if (c < p.cin) {
-                    const float* src = xs + (int64_t)c * p.hw + n;
-                    const float pad = p.sub ? __ldg(p.sub + (int64_t)w.sample * p.cin + c) : 0.f;   // (pad - sub) * mul = 0
-                    v[j].x = n + 0 < p.hw ? src[0] : pad;
-                    v[j].y = n + 1 < p.hw ? src[1] : pad;
-                    v[j].z = n + 2 < p.hw ? src[2] : pad;
-                    v[j].w = n + 3 < p.hw ? src[3] : pad;
-                } else {
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            c.vec = p.vec_ok && n + 4 <= p.hw;
+            c.n = n;
+            c.xrow = p.x + ((int64_t)w.sample * p.cin + cw * 8) * p.hw + n;
+            c.soff = w.sample * p.cin + cw * 8;
+        };
+        auto advance = [&](Cursor& c) {
+            if (++c.kb == p.kb) {
+                c.kb = 0;
+                c.item += (int)gridDim.x;
+                decode(c);
             }
         };
-        auto conv_unit = [&](float4 (&v)[8], uint32_t u) {
-            if (u >= units) return;
-            const PwItem w = pw_item(p, (int)blockIdx.x + (int)(u / p.kb) * (int)gridDim.x);
-            const int kb = (int)(u % p.kb);
-            const int s = u % NST;
+        auto load_unit = [&](float4 (&v)[8], Cursor& c) {
+            if (!c.live) return;
+            const int c0 = c.kb * 64 + cw * 8;
+            const float* src0 = c.xrow + (int64_t)c.kb * kb_stride;
+            if (VEC) {
+                if (c.vec && c0 < p.cin) {                  // cin % 8 == 0: a warp's 8 channels are all inside or all padding
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __ldcs(reinterpret_cast<const float4*>(src0 + (int64_t)j * p.hw));
+                } else {                                    // beyond the last position / channel: the rows are discarded or multiply zero weights
+                    const float pad = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = make_float4(pad, pad, pad, pad);
+                }
+            } else {
+                const int64_t n = c.n;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (c0 + j < p.cin) {
+                        const float* src = src0 + (int64_t)j * p.hw;
+                        const float pad = p.sub ? __ldg(p.sub + c.soff + c.kb * 64 + j) : 0.f;     // (pad - sub) * mul = 0
+                        v[j].x = n + 0 < p.hw ? src[0] : pad;
+                        v[j].y = n + 1 < p.hw ? src[1] : pad;
+                        v[j].z = n + 2 < p.hw ? src[2] : pad;
+                        v[j].w = n + 3 < p.hw ? src[3] : pad;
+                    } else {
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            advance(c);
+        };
+        uint32_t u = 0;
+        auto conv_unit = [&](float4 (&v)[8], Cursor& c) {
+            if (!c.live) return;
+            const int c0 = c.kb * 64 + cw * 8;
+            const int sidx = c.soff + c.kb * 64;
+            const uint32_t s = u & (NST - 1);
             mbar_wait(&empty[s], ((u / NST) & 1u) ^ 1u);
             unsigned char* a_hi = smem + (size_t)s * kStage + (size_t)cw * kPwSBO + lane_off;
             unsigned char* a_lo = a_hi + kA;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {              // channel row j of this warp's 8-channel atom
-                const int c = kb * 64 + cw * 8 + j;
-                const bool live = c < p.cin;
-                const float sb = (p.sub && live) ? __ldg(p.sub + (int64_t)w.sample * p.cin + c) : 0.f;
-                const float ml = (p.mul && live) ? __ldg(p.mul + (int64_t)w.sample * p.cin + c) : 1.f;
+                const bool ok = c0 + j < p.cin;
+                const float sb = (p.sub && ok) ? __ldg(p.sub + sidx + j) : 0.f;
+                const float ml = (p.mul && ok) ? __ldg(p.mul + sidx + j) : 1.f;
                 const float a = (v[j].x - sb) * ml, b = (v[j].y - sb) * ml, c2 = (v[j].z - sb) * ml, d = (v[j].w - sb) * ml;
                 const uint32_t off = (uint32_t)j * 128u + ((chunk ^ (uint32_t)j) << 4);
                 const uint32_t h01 = pw_pack_bf16x2(a, b), h23 = pw_pack_bf16x2(c2, d);
@@ -326,17 +401,24 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_a[s]);
+            ++u;
+            advance(c);
         };
+        Cursor ld, cv;
+        ld.item = cv.item = (int)blockIdx.x;
+        ld.kb = cv.kb = 0;
+        decode(ld);
+        cv = ld;
         float4 v0[8], v1[8], v2[8];
-        load_unit(v0, 0);
-        load_unit(v1, 1);
-        for (uint32_t u = 0; u < units; u += 3) {
-            load_unit(v2, u + 2);
-            conv_unit(v0, u);
-            load_unit(v0, u + 3);
-            conv_unit(v1, u + 1);
-            load_unit(v1, u + 4);
-            conv_unit(v2, u + 2);
+        load_unit(v0, ld);
+        load_unit(v1, ld);
+        while (cv.live) {
+            load_unit(v2, ld);
+            conv_unit(v0, cv);
+            load_unit(v0, ld);
+            conv_unit(v1, cv);
+            load_unit(v1, ld);
+            conv_unit(v2, cv);
         }
     }
     tcgen05_fence_before();
@@ -395,28 +477,44 @@ int pw_conv(const PwArgs& a, cudaStream_t st) {
     p.col_tiles = (p.coutp + 255) / 256;
     p.tiles = (int)((a.hw + 127) / 128);
     p.batch = (int)a.b;
+    p.stat_ctas = sm_count();
     p.vec_ok = (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) ? 1 : 0;
     const int64_t items = (int64_t)p.batch * p.tiles * p.col_tiles;
     if (items == 0) return RPST_OK;
     RPST_CHECK_ARG(items < (1ll << 30), "conv1x1: too many work items");
-    constexpr size_t smem = 1024 + 2 * 2 * (kTileBytes + 2 * kTileBytes);   // 193 KiB for both instantiations
-    static PerDeviceFlag configured_on;
-    bool& configured = configured_on.get();
-    if (!configured) {
-        RPST_CUDA(cudaFuncSetAttribute(pw_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RPST_CUDA(cudaFuncSetAttribute(pw_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    constexpr size_t smem = 1024 + 2 * 2 * (kTileBytes + 2 * kTileBytes);   // 193 KiB for every instantiation
+    const bool vec = p.vec_ok && a.cin % 8 == 0;
+    const int epi = p.out_hi ? 1 : (p.stats ? 2 : 0);
+    RPST_CHECK_ARG(!(p.out_hi && p.stats), "conv1x1: packed output and epilogue statistics are separate modes");
     int grid = sm_count();
     if (grid > items) grid = (int)items;
-    if (a.passes == 3) pw_conv_kernel<2><<<grid, kPwThreads, smem, st>>>(p);
-    else pw_conv_kernel<1><<<grid, kPwThreads, smem, st>>>(p);
+    static PerDeviceFlag configured_on[12];
+#define RPST_PW_CASE(PARTS, VEC, EPI)                                                                                     \
+    {                                                                                                                     \
+        bool& configured = configured_on[((PARTS) - 1) * 6 + (VEC) * 3 + (EPI)].get();                                    \
+        if (!configured) {                                                                                                \
+            RPST_CUDA(cudaFuncSetAttribute(pw_conv_kernel<PARTS, VEC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           (int)smem));                                                                   \
+            configured = true;                                                                                            \
+        }                                                                                                                 \
+        pw_conv_kernel<PARTS, VEC, EPI><<<grid, kPwThreads, smem, st>>>(p);                                               \
+    }
+#define RPST_PW_EPI(PARTS, VEC)                                                    \
+    if (epi == 0) RPST_PW_CASE(PARTS, VEC, 0) else if (epi == 1) RPST_PW_CASE(PARTS, VEC, 1) else RPST_PW_CASE(PARTS, VEC, 2)
+    if (a.passes == 3) {
+        if (vec) { RPST_PW_EPI(2, true) } else { RPST_PW_EPI(2, false) }
+    } else {
+        if (vec) { RPST_PW_EPI(1, true) } else { RPST_PW_EPI(1, false) }
+    }
+#undef RPST_PW_EPI
+#undef RPST_PW_CASE
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
 
-// ---- WCT colouring (wct.cu): out = T (x - mu_c) + mu_s with T given as packed tiles (rows = output channels)
-bool wct_apply_fused_supported(int64_t c, int64_t hw) { return c >= 1 && c <= 256 && hw >= 1; }
+// ---- WCT colouring (wct.cu): out = T (x - mu_c) + mu_s with T given as packed tiles (rows = output channels).
+// (A dedicated copy of this kernel without the general epilogue measured 1.80 vs 1.83 ms per sample end to end: dropped.)
+bool wct_apply_fused_supported(int64_t c, int64_t hw) { return c >= 1 && c <= kPwMaxC && hw >= 1; }
 
 int wct_apply_fused(const float* x, const float* mu_c, const float* mu_s, const void* t_hi, const void* t_lo, float* out,
                     int64_t c, int64_t hw, int passes, cudaStream_t st) {
@@ -430,9 +528,12 @@ int wct_apply_fused(const float* x, const float* mu_c, const float* mu_s, const 
 
 using namespace rpst;
 
+// per sample: one (sum, sum of squares) pair per channel, CTA and epilogue warp
+static int pw_stat_entries() { return sm_count() * 4; }
+
 extern "C" size_t rpst_conv1x1_stats_bytes(int64_t b, int64_t cout, int64_t hw) {
     if (b <= 0 || cout <= 0 || hw <= 0) return 256;
-    return align_up((size_t)b * ((hw + 127) / 128) * 4 * cout * 2 * sizeof(float), 256);
+    return align_up((size_t)b * pw_stat_entries() * cout * 2 * sizeof(float), 256);
 }
 
 extern "C" int rpst_conv1x1(const float* x, const void* w_hi, const void* w_lo, const float* bias, const float* sub,
@@ -455,6 +556,8 @@ extern "C" int rpst_conv1x1(const float* x, const void* w_hi, const void* w_lo, 
     a.tile_batch = (int64_t)align_up(packed_operand_bytes(hw, cout), 256);
     a.stats = stats_partial; a.act = act; a.slope = slope;
     a.b = b; a.cin = cin; a.cout = cout; a.hw = hw; a.passes = passes;
+    if (stats_partial)      // CTAs that never touch a sample leave their entries at zero
+        RPST_CUDA(cudaMemsetAsync(stats_partial, 0, rpst_conv1x1_stats_bytes(b, cout, hw), static_cast<cudaStream_t>(stream)));
     return pw_conv(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -463,7 +566,7 @@ extern "C" int rpst_conv1x1_stats_finalize(const float* stats_partial, int64_t b
     RPST_CHECK_ARG(b >= 0 && cout >= 0 && hw >= 0, "conv1x1_stats: negative size");
     if (b == 0 || cout == 0) return RPST_OK;
     RPST_CHECK_ARG(stats_partial && mean && std, "conv1x1_stats: null pointer");
-    const int entries = (int)((hw + 127) / 128) * 4;
+    const int entries = pw_stat_entries();
     pw_stats_finalize_kernel<<<dim3((unsigned)((cout + 127) / 128), (unsigned)b), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         stats_partial, entries, (int)cout, (double)hw, (double)eps, mean, std);
     RPST_CUDA(cudaGetLastError());
