@@ -110,20 +110,20 @@ __device__ __forceinline__ double rotate_pair(double* x, double* y, int lane) {
     return rel;
 }
 
-// same rotation with the x column held in registers by the calling warp (xv is updated in place)
+// Cross-pair step with TRACKED squared norms: aa (this warp's X column, a register) and bb (the Y column, from shared
+// memory) are updated analytically after the rotation (|x'|^2 = aa - t g, |y'|^2 = bb + t g: Rutishauser), so a step
+// needs ONE dot product and one warp reduction instead of three.  The norms are recomputed from the data at the start
+// of every round, so rounding drift is bounded by one round; they only steer the rotation ANGLE (c^2 + s^2 = 1 holds
+// exactly), and Jacobi is self-correcting in the angle.
 template <int ROWS>
-__device__ __forceinline__ double rotate_pair_xreg(double (&xv)[ROWS], double* y, int lane) {
+__device__ __forceinline__ double rotate_pair_tracked(double (&xv)[ROWS], double* y, double& aa, double& bb, int lane) {
     double yv[ROWS];
-    double aa = 0.0, bb = 0.0, gg = 0.0;
+    double gg = 0.0;
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
         yv[i] = y[i * 32 + lane];
-        aa = fma(xv[i], xv[i], aa);
-        bb = fma(yv[i], yv[i], bb);
         gg = fma(xv[i], yv[i], gg);
     }
-    aa = warp_sum_f64(aa);
-    bb = warp_sum_f64(bb);
     gg = warp_sum_f64(gg);
     const float aaf = (float)aa, bbf = (float)bb, ggf = (float)gg;
     const float prod = aaf * bbf;
@@ -141,6 +141,8 @@ __device__ __forceinline__ double rotate_pair_xreg(double (&xv)[ROWS], double* y
         xv[i] = c * xo - s * yv[i];
         y[i * 32 + lane] = s * xo + c * yv[i];
     }
+    aa = fma(-t, gg, aa);
+    bb = fma(t, gg, bb);
     return (double)relf;
 }
 
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(32 * BC, (BC == 16 && ROWS < 16) ? 2 : 1) jaco
     double* cols = reinterpret_cast<double*>(eig_smem);            // [32][np]
     double* conv = cols + (size_t)kCtaCols * p.np;                 // [2]: per-sweep local maxima (double buffered)
     __shared__ double warp_max[kBlockCols];
+    __shared__ double ynorm[kBlockCols];                           // tracked squared norms of the Y block's columns
 
     const int B = p.ctas, m = 2 * B;
     const int rank = (int)cluster_ctarank();
@@ -193,11 +196,24 @@ __global__ void __launch_bounds__(32 * BC, (BC == 16 && ROWS < 16) ? 2 : 1) jaco
             {
                 double xv[ROWS];
                 double* xcol = cols + (size_t)warp * np;
+                double* ycol = cols + (size_t)(kBlockCols + warp) * np;
+                double aa = 0.0, yy = 0.0;
 #pragma unroll
-                for (int i = 0; i < ROWS; ++i) xv[i] = xcol[i * 32 + lane];
+                for (int i = 0; i < ROWS; ++i) {
+                    xv[i] = xcol[i * 32 + lane];
+                    const double yw = ycol[i * 32 + lane];
+                    aa = fma(xv[i], xv[i], aa);
+                    yy = fma(yw, yw, yy);
+                }
+                aa = warp_sum_f64(aa);
+                yy = warp_sum_f64(yy);
+                if (lane == 0) ynorm[warp] = yy;
+                __syncthreads();
                 for (int s = 0; s < kBlockCols; ++s) {
                     const int j = (warp + s) & (kBlockCols - 1);
-                    wmax = fmax(wmax, rotate_pair_xreg<ROWS>(xv, cols + (size_t)(kBlockCols + j) * np, lane));
+                    double bb = ynorm[j];
+                    wmax = fmax(wmax, rotate_pair_tracked<ROWS>(xv, cols + (size_t)(kBlockCols + j) * np, aa, bb, lane));
+                    if (lane == 0) ynorm[j] = bb;
                     __syncthreads();
                 }
 #pragma unroll
