@@ -61,6 +61,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// The same wait for threads that poll next to working warps: optional back-off, and the watchdog (a slow
+// %globaltimer read) is looked at every 1024 polls only.
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity, unsigned sleep_ns = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    unsigned polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if ((++polls & 1023u) == 0) {
+            if (t0 == 0) t0 = global_timer_ns();
+            else if (watchdog_expired(t0)) __trap();
+        }
+    }
+}
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map needed for contiguous data).
 // dst/src 16-byte aligned, bytes a multiple of 16; completion is signalled on `bar` (complete_tx).
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,

@@ -490,6 +490,29 @@ constexpr int kSegCacheBytes = (kSegCoefBytes + kLabels * 4 + kLabels + 2 * kMax
 constexpr int kSegMergeThreads = 64;   // two dedicated merge warps per CTA (one thread per dense label)
 constexpr int kSegMailbox = 8;
 
+// Open runs of a warp -> per-label totals tab[d] for dense label d (atomic-free, fixed order; needs <= 32 usable
+// labels).  Lanes holding the same label form a group (match.any); its lowest lane adds the others in lane order
+// (one shuffle pair per step, as many steps as the largest group has members) and stores the group's total.
+// A third of the instructions of the scan it replaces (every lane reading all 32 staged runs).
+__device__ __forceinline__ void seg_warp_totals(float2* tab, int lane, int cur, float a1, float a2) {
+    const int key = cur >= 0 ? cur : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int steps = (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
+    float s1 = a1, s2 = a2;
+    unsigned rem = peers & (peers - 1u);   // the group without its lowest lane
+    const bool leader = (peers & ((1u << lane) - 1u)) == 0u;
+    for (int k = 1; k < steps; ++k) {
+        const int src = rem ? __ffs(rem) - 1 : lane;
+        const float x1 = __shfl_sync(0xffffffffu, a1, src), x2 = __shfl_sync(0xffffffffu, a2, src);
+        if (rem) { s1 += x1; s2 += x2; }
+        rem &= rem - 1u;
+    }
+    tab[lane] = make_float2(0.f, 0.f);
+    __syncwarp();
+    if (leader && key >= 0) tab[key] = make_float2(s1, s2);
+    __syncwarp();
+}
+
 template <int G>
 __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 1) seg_tma_kernel(SegTmaParams p) {
     constexpr int S = G * kSegDepth;   // stages; group g owns stages g*kSegDepth .. +kSegDepth-1
@@ -553,7 +576,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                 for (int i = 0; i < nvalid; ++i) {
                     if (dec[i].kind == 3) {
                         const int ms = (int)(mseq % kSegMailbox);
-                        mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
+                        mbar_wait_quiet(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
                         mbox[ms] = dec[i].plane;
                         mbar_arrive(&mfull[ms]);
                         ++mseq;
@@ -569,7 +592,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     const unsigned my_seq = seq + (unsigned)my_pos;
                     const unsigned k = my_seq / G;
                     const int stage = (int)(my_seq % G) * kSegDepth + (int)(k % kSegDepth);
-                    mbar_wait(&empty[stage], ((k / kSegDepth) & 1u) ^ 1u);
+                    mbar_wait_quiet(&empty[stage], ((k / kSegDepth) & 1u) ^ 1u);
                     SegDesc* d = &desc[stage];
                     d->plane = plane; d->kind = kind; d->chunk = chunk;
                     const bool is_style = kind == 1;
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     d->nvec = nvec;
                     const uint32_t bytes = (uint32_t)nvec * 16u;
                     unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
-                    const int64_t sample = plane / p.channels;
+                    const int64_t sample = (int)plane / (int)p.channels;
                     const float* src = (is_style ? p.style : p.content) + plane * hw + e0;
                     const uint8_t* lab = (is_style ? p.s_lab : p.c_lab) + sample * hw + e0;
                     const bool has_prev = kind == 2 && p.prev != nullptr;
@@ -600,12 +623,12 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
                     for (int g = 0; g < G; ++g, ++seq) {   // one stop descriptor per consumer group
                         const unsigned k = seq / G;
                         const int stage = (int)(seq % G) * kSegDepth + (int)(k % kSegDepth);
-                        mbar_wait(&empty[stage], ((k / kSegDepth) & 1u) ^ 1u);
+                        mbar_wait_quiet(&empty[stage], ((k / kSegDepth) & 1u) ^ 1u);
                         desc[stage].kind = -1;
                         mbar_arrive(&full[stage]);
                     }
                     const int ms = (int)(mseq % kSegMailbox);
-                    mbar_wait(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
+                    mbar_wait_quiet(&mempty[ms], ((mseq / kSegMailbox) & 1u) ^ 1u);
                     mbox[ms] = -1;
                     mbar_arrive(&mfull[ms]);
                 }
@@ -626,7 +649,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
         const int t = threadIdx.x - (32 + G * kSegGroupThreads);
         for (unsigned mseq = 0;; ++mseq) {
             const int ms = (int)(mseq % kSegMailbox);
-            mbar_wait(&mfull[ms], (mseq / kSegMailbox) & 1u);
+            mbar_wait_quiet(&mfull[ms], (mseq / kSegMailbox) & 1u, 64);
             const int64_t plane = mbox[ms];
             __syncwarp();
             if (lane == 0) mbar_arrive(&mempty[ms]);
@@ -722,7 +745,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
     for (unsigned seq = group;; seq += G) {
         const unsigned k = seq / G;
         const int stage = group * kSegDepth + (int)(k % kSegDepth);
-        mbar_wait(&full[stage], (k / kSegDepth) & 1u);
+        mbar_wait_quiet(&full[stage], (k / kSegDepth) & 1u);
         const SegDesc* d = &desc[stage];
         const int kind = d->kind;
         if (kind < 0) break;
@@ -731,7 +754,7 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
         // vectors per warp: a full item gives each warp 512 (16 per lane), a half item (apply with prev) 256
         const int warp_vecs = (kind == 2 ? p.apply_elems : kSegItemElems) / 4 / kSegGroupWarps;
         const int wvec = min(max(d->nvec - gw * warp_vecs, 0), warp_vecs);
-        const int64_t sample = plane / p.channels;
+        const int64_t sample = (int)plane / (int)p.channels;   // planes < 2^31 (checked by the host): 32-bit division
         unsigned char* st = stages + (size_t)stage * STAGE_BYTES;
         const float4* a4 = reinterpret_cast<const float4*>(st) + gw * warp_vecs;
         const float4* b4 = reinterpret_cast<const float4*>(st + kSegHalfElems * 4) + gw * warp_vecs;
@@ -820,21 +843,9 @@ __global__ void __launch_bounds__(32 + G * kSegGroupThreads + kSegMergeThreads, 
             const bool staged = p.flush_mode == 2 && dcount <= 32;
             float* wt = c_wtot + (sparity * kSegGroupWarps + gw) * 64;
             if (staged) {
-                // Atomic-free and deterministic: every lane stages its open run (dense id, S1, S2); lane d then
-                // gathers label d over the 32 staged runs in lane order (broadcast reads) and stores the warp's
-                // total for that label; the publishing thread below adds the four warps in warp order.
-                float4* stg = c_stage + gw * 32;
-                stg[lane] = make_float4(__int_as_float(cur), a1, a2, 0.f);
-                __syncwarp();
-                float t1 = 0.f, t2 = 0.f;
-#pragma unroll 8
-                for (int j = 0; j < 32; ++j) {
-                    const float4 r = stg[j];
-                    if (__float_as_int(r.x) == lane) { t1 += r.y; t2 += r.z; }
-                }
-                wt[lane * 2 + 0] = t1;
-                wt[lane * 2 + 1] = t2;
-                __syncwarp();
+                // atomic-free and deterministic: the warp's totals per dense label (lane-ordered sums); the
+                // publishing thread below adds the four warps in warp order
+                seg_warp_totals(reinterpret_cast<float2*>(wt), lane, cur, a1, a2);
             } else if (p.flush_mode != 1) {
                 if (cur >= 0) {
                     atomicAdd(&acc[cur * 2 + 0], a1);
