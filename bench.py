@@ -3,7 +3,7 @@
 (BASELINE.json configs[1]: `run_deeper_multiscale_rp_adain`, batch 32 per GPU, levels
 C = 16,32,64,128,256 at full 512x512 resolution).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode infer|train] [--scaling weak|strong]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong] [--no-sustained] [--no-extra]
 
 A step = one pass of the hot path over one batch: AdaIN on the deepest level + `prev + AdaIN` on the
 four shallower ones (network/adain_rp.py:286-302 with the decoder convolutions factored out), five
