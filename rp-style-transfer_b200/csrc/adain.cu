@@ -27,6 +27,7 @@ namespace {
 struct Tuning {
     int64_t lag_bytes = 32ll << 20;
     int64_t big_lag_bytes = 128ll << 20;  // planes >= 4 MiB
+    int64_t mvn_lag_bytes = 44ll << 20;   // style == NULL (mean_variance_norm): see plan_schedule
     int64_t hints = 1;
     int64_t ctas_per_sm = 4;
     int64_t path = 0;    // 0: TMA-staged kernel when alignment allows, 1: register-staged kernel
@@ -1334,7 +1335,11 @@ int64_t plan_schedule(AdainParams& p, bool use_tma) {
     // planes of >= 4 MiB: the statistics -> merge -> apply chain (>= 3 dependent global round trips of ~4.5 us
     // each under load) no longer fits the ~32 MiB L2 window, and a short lag stalls the apply items instead;
     // measured at 1x256x1024x2048: 32 MiB 3.03 TB/s, 64 MiB 4.92, 128 MiB 5.22 (tools/big_plane_sweep.py)
-    const int64_t lag_bytes = plane_bytes >= (4ll << 20) ? g_tuning.big_lag_bytes : g_tuning.lag_bytes;
+    // mean_variance_norm (no style stream): the statistics items drain 1.5x faster in bytes, so the same chain latency
+    // spans more planes; 8x256x512x512: 32 MiB 4.2 TB/s, 40 MiB 5.07, 44 MiB 5.18, 48 MiB 4.99 (L2 misses set in), 56 MiB 4.75
+    // (tools/mvn_sweep.py)
+    const bool mvn = p.style == nullptr && !p.stats_only;
+    const int64_t lag_bytes = plane_bytes >= (4ll << 20) ? g_tuning.big_lag_bytes : mvn ? g_tuning.mvn_lag_bytes : g_tuning.lag_bytes;
     int64_t lag = (lag_bytes + plane_bytes - 1) / plane_bytes;
     if (lag < 3) lag = 3;
     p.lag = (int)(lag < p.planes ? lag : p.planes);
@@ -1491,6 +1496,7 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     int64_t* slot = nullptr;
     if (!strcmp(name, "adain_lag_bytes")) slot = &g_tuning.lag_bytes;
     else if (!strcmp(name, "adain_big_lag_bytes")) slot = &g_tuning.big_lag_bytes;
+    else if (!strcmp(name, "adain_mvn_lag_bytes")) slot = &g_tuning.mvn_lag_bytes;
     else if (!strcmp(name, "adain_hints")) slot = &g_tuning.hints;
     else if (!strcmp(name, "adain_ctas_per_sm")) slot = &g_tuning.ctas_per_sm;
     else if (!strcmp(name, "adain_path")) slot = &g_tuning.path;

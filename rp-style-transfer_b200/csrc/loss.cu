@@ -70,87 +70,6 @@ struct PairParams {
     unsigned* ticket;     // zeroed before the launch
 };
 
-template <int VEC>
-__global__ void __launch_bounds__(kLossThreads) pair_moments_kernel(PairParams p) {
-    constexpr int CHUNK = kLossThreads * kLossVecs * VEC;
-    __shared__ PairM s_warp[kLossThreads / 32];
-    const uint64_t pol = policy_evict_first();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int64_t plane = item / p.cpp;
-        const int chunk = (int)(item % p.cpp);
-        const int64_t e0 = (int64_t)chunk * CHUNK;
-        const int64_t rem = p.hw - e0;
-        const int nvec = (int)((rem < CHUNK ? rem : CHUNK) / VEC);
-        const float* xb = p.x + plane * p.hw + e0;
-        const float* yb = p.y + plane * p.hw + e0;
-        float xv[kLossVecs][VEC], yv[kLossVecs][VEC];
-#pragma unroll
-        for (int j = 0; j < kLossVecs; ++j) {
-            const int idx = j * kLossThreads + threadIdx.x;
-            if (idx < nvec) {
-                load_vec<VEC>(xv[j], xb + (int64_t)idx * VEC, pol, true);
-            } else {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) xv[j][e] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kLossVecs; ++j) {
-            const int idx = j * kLossThreads + threadIdx.x;
-            if (idx < nvec) {
-                load_vec<VEC>(yv[j], yb + (int64_t)idx * VEC, pol, true);
-            } else {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) yv[j][e] = 0.f;
-            }
-        }
-        // exact two-pass moments of this thread's registers
-        float sx = 0.f, sy = 0.f;
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < kLossVecs; ++j) {
-            if (j * kLossThreads + (int)threadIdx.x < nvec) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { sx += xv[j][e]; sy += yv[j][e]; }
-                cnt += VEC;
-            }
-        }
-        PairM m = {(float)cnt, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (cnt > 0) {
-            m.mx = sx / m.n;
-            m.my = sy / m.n;
-#pragma unroll
-            for (int j = 0; j < kLossVecs; ++j) {
-                if (j * kLossThreads + (int)threadIdx.x < nvec) {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const float dx = xv[j][e] - m.mx, dy = yv[j][e] - m.my;
-                        m.m2x = fmaf(dx, dx, m.m2x);
-                        m.m2y = fmaf(dy, dy, m.m2y);
-                        m.cxy = fmaf(dx, dy, m.cxy);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = pair_merge(m, pair_shfl_xor(m, o));
-        if (lane == 0) s_warp[warp] = m;
-        __syncthreads();
-        if (warp == 0) {
-            PairM t = lane < kLossThreads / 32 ? s_warp[lane] : PairM{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) t = pair_merge(t, pair_shfl_xor(t, o));
-            if (lane == 0) {
-                float4* dst = reinterpret_cast<float4*>(p.part + item);
-                dst[0] = make_float4(t.n, t.mx, t.m2x, t.my);
-                dst[1] = make_float4(t.m2y, t.cxy, 0.f, 0.f);
-            }
-        }
-        __syncthreads();
-    }
-}
-
 struct PairD {
     double n, mx, m2x, my, m2y, cxy;
 };
@@ -179,6 +98,162 @@ __device__ __forceinline__ PairD pair_shfl_xor(const PairD& m, int o) {
     return r;
 }
 
+// per-plane loss terms from the merged moments (fp64: the content term cancels when x ~ y)
+__device__ __forceinline__ void pair_terms(const PairParams& p, const PairD& m, int64_t plane, bool write_stats, double& style_term,
+                                           double& content_term) {
+    const double denom = (double)p.hw - 1.0;  // HW==1 -> 0/0 = NaN like torch.var
+    const double vx = m.m2x / denom + (double)p.eps, vy = m.m2y / denom + (double)p.eps;
+    const double sdx = sqrt(vx), sdy = sqrt(vy);
+    const double dm = m.mx - m.my, ds = sdx - sdy;
+    style_term = dm * dm + ds * ds;
+    content_term = m.m2x / vx + m.m2y / vy - 2.0 * m.cxy / (sdx * sdy);
+    if (write_stats && p.stats) {
+        float4* st = reinterpret_cast<float4*>(p.stats + plane * 8);
+        st[0] = make_float4((float)m.mx, (float)sdx, (float)m.my, (float)sdy);
+        st[1] = make_float4((float)m.m2x, (float)m.m2y, (float)m.cxy, 0.f);
+    }
+}
+
+// last block (ticket): fixed-order sum of the block partials -> the two losses
+__device__ __forceinline__ void pair_last_block_sum(const PairParams& p, unsigned blocks, double* s_a, double* s_b) {
+    double a = 0.0, b = 0.0;
+    for (unsigned i = threadIdx.x; i < blocks; i += 256) {
+        a += __ldcg(p.block_part + 2 * i);
+        b += __ldcg(p.block_part + 2 * i + 1);
+    }
+    s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { s_a[threadIdx.x] += s_a[threadIdx.x + s]; s_b[threadIdx.x] += s_b[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.losses[0] = (float)(s_a[0] / (double)p.planes);
+        p.losses[1] = (float)(s_b[0] / ((double)p.planes * (double)p.hw));
+    }
+}
+
+// VECS = vectors per thread and tensor: 8 for the general case; 4 for planes that fit half a chunk (64x64 VGG relu4_1
+// planes): half the registers, so five CTAs instead of three are resident per SM and hide the load latency that
+// bounds small planes (the chunk geometry, one record per plane, is the same).
+// FUSED (one chunk per plane and at most 256 planes per CTA): the CTA keeps its planes' records in shared memory and,
+// after its last item, finalizes them itself (one thread per plane, block partial, last-block ticket) — no second
+// kernel, which on 64x64 planes was a quarter of the time.
+template <int VEC, int VECS, bool FUSED>
+__global__ void __launch_bounds__(kLossThreads, VECS == kLossVecs ? 3 : 5) pair_moments_kernel(PairParams p) {
+    constexpr int CHUNK = kLossThreads * kLossVecs * VEC;
+    static_assert(kLossThreads == 256, "finalize helpers assume 256 threads");
+    __shared__ PairM s_warp[kLossThreads / 32];
+    __shared__ PairM s_rec[FUSED ? kLossThreads : 1];
+    int my_items = 0;
+    const uint64_t pol = policy_evict_first();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int64_t plane = item / p.cpp;
+        const int chunk = (int)(item % p.cpp);
+        const int64_t e0 = (int64_t)chunk * CHUNK;
+        const int64_t rem = p.hw - e0;
+        const int nvec = (int)((rem < CHUNK ? rem : CHUNK) / VEC);
+        const float* xb = p.x + plane * p.hw + e0;
+        const float* yb = p.y + plane * p.hw + e0;
+        float xv[VECS][VEC], yv[VECS][VEC];
+#pragma unroll
+        for (int j = 0; j < VECS; ++j) {
+            const int idx = j * kLossThreads + threadIdx.x;
+            if (idx < nvec) {
+                load_vec<VEC>(xv[j], xb + (int64_t)idx * VEC, pol, true);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) xv[j][e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VECS; ++j) {
+            const int idx = j * kLossThreads + threadIdx.x;
+            if (idx < nvec) {
+                load_vec<VEC>(yv[j], yb + (int64_t)idx * VEC, pol, true);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) yv[j][e] = 0.f;
+            }
+        }
+        // exact two-pass moments of this thread's registers
+        float sx = 0.f, sy = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < VECS; ++j) {
+            if (j * kLossThreads + (int)threadIdx.x < nvec) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { sx += xv[j][e]; sy += yv[j][e]; }
+                cnt += VEC;
+            }
+        }
+        PairM m = {(float)cnt, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (cnt > 0) {
+            m.mx = sx / m.n;
+            m.my = sy / m.n;
+#pragma unroll
+            for (int j = 0; j < VECS; ++j) {
+                if (j * kLossThreads + (int)threadIdx.x < nvec) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const float dx = xv[j][e] - m.mx, dy = yv[j][e] - m.my;
+                        m.m2x = fmaf(dx, dx, m.m2x);
+                        m.m2y = fmaf(dy, dy, m.m2y);
+                        m.cxy = fmaf(dx, dy, m.cxy);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = pair_merge(m, pair_shfl_xor(m, o));
+        if (lane == 0) s_warp[warp] = m;
+        __syncthreads();
+        if (warp == 0) {
+            PairM t = lane < kLossThreads / 32 ? s_warp[lane] : PairM{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) t = pair_merge(t, pair_shfl_xor(t, o));
+            if (lane == 0) {
+                if constexpr (FUSED) {
+                    s_rec[my_items] = t;
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(p.part + item);
+                    dst[0] = make_float4(t.n, t.mx, t.m2x, t.my);
+                    dst[1] = make_float4(t.m2y, t.cxy, 0.f, 0.f);
+                }
+            }
+        }
+        ++my_items;
+        __syncthreads();
+    }
+    if constexpr (FUSED) {
+        __shared__ double s_a[256], s_b[256];
+        __shared__ bool s_last;
+        double style_term = 0.0, content_term = 0.0;
+        if ((int)threadIdx.x < my_items) {
+            const PairM r = s_rec[threadIdx.x];
+            const PairD m = {(double)r.n, (double)r.mx, (double)r.m2x, (double)r.my, (double)r.m2y, (double)r.cxy};
+            pair_terms(p, m, (int64_t)blockIdx.x + (int64_t)threadIdx.x * gridDim.x, true, style_term, content_term);
+        }
+        s_a[threadIdx.x] = style_term; s_b[threadIdx.x] = content_term;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) { s_a[threadIdx.x] += s_a[threadIdx.x + s]; s_b[threadIdx.x] += s_b[threadIdx.x + s]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            p.block_part[2 * blockIdx.x] = s_a[0];
+            p.block_part[2 * blockIdx.x + 1] = s_b[0];
+            __threadfence();
+            s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        pair_last_block_sum(p, gridDim.x, s_a, s_b);
+    }
+}
+
 // one warp per plane; block partial sums -> last block (ticket) adds them in index order
 __global__ void __launch_bounds__(256) pair_finalize_kernel(PairParams p) {
     __shared__ double s_style[8], s_content[8];
@@ -196,17 +271,7 @@ __global__ void __launch_bounds__(256) pair_finalize_kernel(PairParams p) {
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = pair_merge(m, pair_shfl_xor(m, o));
-        const double denom = (double)p.hw - 1.0;  // HW==1 -> 0/0 = NaN like torch.var
-        const double vx = m.m2x / denom + (double)p.eps, vy = m.m2y / denom + (double)p.eps;
-        const double sdx = sqrt(vx), sdy = sqrt(vy);
-        const double dm = m.mx - m.my, ds = sdx - sdy;
-        style_term = dm * dm + ds * ds;
-        content_term = m.m2x / vx + m.m2y / vy - 2.0 * m.cxy / (sdx * sdy);
-        if (lane == 0 && p.stats) {
-            float4* st = reinterpret_cast<float4*>(p.stats + plane * 8);
-            st[0] = make_float4((float)m.mx, (float)sdx, (float)m.my, (float)sdy);
-            st[1] = make_float4((float)m.m2x, (float)m.m2y, (float)m.cxy, 0.f);
-        }
+        pair_terms(p, m, plane, lane == 0, style_term, content_term);
     }
     if (lane == 0) { s_style[warp] = style_term; s_content[warp] = content_term; }
     __syncthreads();
@@ -221,23 +286,8 @@ __global__ void __launch_bounds__(256) pair_finalize_kernel(PairParams p) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last block: fixed-order sum of the block partials (thread-strided, then a shared-memory tree)
     __shared__ double s_a[256], s_b[256];
-    double a = 0.0, b = 0.0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) {
-        a += __ldcg(p.block_part + 2 * i);
-        b += __ldcg(p.block_part + 2 * i + 1);
-    }
-    s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) { s_a[threadIdx.x] += s_a[threadIdx.x + s]; s_b[threadIdx.x] += s_b[threadIdx.x + s]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        p.losses[0] = (float)(s_a[0] / (double)p.planes);
-        p.losses[1] = (float)(s_b[0] / ((double)p.planes * (double)p.hw));
-    }
+    pair_last_block_sum(p, gridDim.x, s_a, s_b);
 }
 
 template <int VEC>
@@ -335,6 +385,7 @@ __global__ void __launch_bounds__(256) pair_loss_bwd_kernel(const float* __restr
     }
 }
 
+constexpr int64_t kFusedMaxGrid = 4096;   // CTAs of the fused moments+finalize launch (block partials reserved for them)
 struct PairLayout {
     size_t part_off, block_off, total;
     int cpp;
@@ -347,7 +398,7 @@ PairLayout pair_layout(int64_t planes, int64_t hw, int vec) {
     l.fin_blocks = (planes + 7) / 8;
     l.part_off = 256;
     l.block_off = align_up(l.part_off + (size_t)planes * l.cpp * sizeof(PairRec), 256);
-    l.total = align_up(l.block_off + (size_t)l.fin_blocks * 2 * sizeof(double), 256);
+    l.total = align_up(l.block_off + (size_t)(l.fin_blocks + kFusedMaxGrid) * 2 * sizeof(double), 256);
     return l;
 }
 
@@ -384,17 +435,33 @@ extern "C" int rpst_pair_stats(const float* x, const float* y, int64_t planes, i
     RPST_CHECK_ARG(l.fin_blocks < (1ll << 31), "pair_stats: too many planes");
     RPST_CUDA(cudaMemsetAsync(base, 0, 256, st));
     // persistent grid = exactly the co-resident CTAs (64 KiB of loads in flight each)
-    static int per_sm[2] = {0, 0};
-    if (per_sm[vec] == 0) {
+    const bool half = hw <= (int64_t)kLossThreads * (kLossVecs / 2) * (vec ? 4 : 1);   // the plane fits half a chunk
+    static int per_sm[2][2] = {{0, 0}, {0, 0}};
+    int& nbs = per_sm[vec ? 1 : 0][half ? 1 : 0];
+    if (nbs == 0) {
         int nb = 0;
-        if (vec) RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<4>, kLossThreads, 0));
-        else RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<1>, kLossThreads, 0));
-        per_sm[vec] = nb > 0 ? nb : 1;
+        if (vec && half) RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<4, kLossVecs / 2, true>, kLossThreads, 0));
+        else if (vec) RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<4, kLossVecs, true>, kLossThreads, 0));
+        else if (half) RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<1, kLossVecs / 2, true>, kLossThreads, 0));
+        else RPST_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_moments_kernel<1, kLossVecs, true>, kLossThreads, 0));
+        nbs = nb > 0 ? nb : 1;
     }
-    int64_t grid = (int64_t)sm_count() * per_sm[vec];
+    int64_t grid = (int64_t)sm_count() * nbs;
     if (grid > p.items) grid = p.items;
-    if (vec) pair_moments_kernel<4><<<(int)grid, kLossThreads, 0, st>>>(p);
-    else pair_moments_kernel<1><<<(int)grid, kLossThreads, 0, st>>>(p);
+    // one chunk per plane: the moments kernel finalizes its own planes (no second launch)
+    const bool fused = l.cpp == 1 && grid <= kFusedMaxGrid && p.items <= grid * (int64_t)kLossThreads;
+    if (fused) {
+        if (vec && half) pair_moments_kernel<4, kLossVecs / 2, true><<<(int)grid, kLossThreads, 0, st>>>(p);
+        else if (vec) pair_moments_kernel<4, kLossVecs, true><<<(int)grid, kLossThreads, 0, st>>>(p);
+        else if (half) pair_moments_kernel<1, kLossVecs / 2, true><<<(int)grid, kLossThreads, 0, st>>>(p);
+        else pair_moments_kernel<1, kLossVecs, true><<<(int)grid, kLossThreads, 0, st>>>(p);
+        RPST_CUDA(cudaGetLastError());
+        return RPST_OK;
+    }
+    if (vec && half) pair_moments_kernel<4, kLossVecs / 2, false><<<(int)grid, kLossThreads, 0, st>>>(p);
+    else if (vec) pair_moments_kernel<4, kLossVecs, false><<<(int)grid, kLossThreads, 0, st>>>(p);
+    else if (half) pair_moments_kernel<1, kLossVecs / 2, false><<<(int)grid, kLossThreads, 0, st>>>(p);
+    else pair_moments_kernel<1, kLossVecs, false><<<(int)grid, kLossThreads, 0, st>>>(p);
     RPST_CUDA(cudaGetLastError());
     pair_finalize_kernel<<<(unsigned)l.fin_blocks, 256, 0, st>>>(p);
     RPST_CUDA(cudaGetLastError());
