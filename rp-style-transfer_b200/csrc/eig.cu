@@ -59,6 +59,7 @@ struct EigParams {
     int n, np;            // logical / padded (multiple of 32) order
     int ctas;             // cluster size = np / 32
     int max_sweeps;
+    double tol;           // stop after a sweep whose largest |cos| between two columns (before rotating them) was below this
     double* w;            // [batch, np, np]: column j at w + j*np (lambda_j v_j)
     double* lam;          // [batch, np]
     int* sweeps;          // [batch] or null
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(32 * BC, (BC == 16 && ROWS < 16) ? 2 : 1) jaco
                 for (int i = 0; i < ROWS; ++i)
                     cols[(size_t)slot * kBlockCols * np + i * kEigThreads + threadIdx.x] = stage[slot][i];
             __syncthreads();
-            if (last_round && gmax < kEigConverged) { ++sweep; goto done; }   // uniform across the cluster
+            if (last_round && gmax < p.tol) { ++sweep; goto done; }   // uniform across the cluster
         }
     }
 done:
@@ -328,6 +329,8 @@ __global__ void __launch_bounds__(256) dgemm_small_kernel(const double* __restri
 }  // namespace
 
 // ---- internal host API -------------------------------------------------------------------------
+int64_t g_eig_wide = -1;   // tuning knob "eig_wide": -1 auto, 0 / 1 force 16- / 32-column blocks, -2 auto + print cluster occupancy
+
 int eig_padded_order(int n) {
     int np = 32;
     while (np < n) np *= 2;   // 32, 64, 128, 256, 512: cluster sizes 1, 2, 4, 8, 16
@@ -341,7 +344,7 @@ size_t eig_workspace_bytes(int64_t batch, int n) {
 
 // a [batch,n,n] -> W/lam in workspace
 int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* ws, size_t ws_bytes, double** w_out,
-                  double** lam_out, int* sweeps, cudaStream_t stream) {
+                  double** lam_out, int* sweeps, cudaStream_t stream, double tol) {
     RPST_CHECK_ARG(n >= 1 && n <= 512, "sym_eig: order must be in [1, 512] (got %d)", n);
     const int np = eig_padded_order(n);
     if (ws_bytes < eig_workspace_bytes(batch, n)) {
@@ -351,11 +354,18 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
     double* w = static_cast<double*>(ws);
     double* lam = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)batch * np * np * sizeof(double), 256));
     EigParams p{};
-    const bool wide = eig_wide_ok(np) && batch * (np / 32) > 96;     // more 32-column CTAs than fit one per SM with slack
+    // 16-column blocks (np/32 CTAs per matrix) until they need more than ~one CTA per SM; 15 eight-CTA clusters are
+    // co-resident at one CTA per SM (cudaOccupancyMaxActiveClusters), a 16th shares SMs: 16 x 256^2 4.43 ms against
+    // 4.77 with 32-column blocks (4 CTAs per matrix, 64 SMs); from 160 CTAs on the wide blocks win (32 x 256^2: 4.94 / 5.31)
+    bool wide = eig_wide_ok(np) && batch * (np / 32) > 160;
+    if (g_eig_wide >= 0 && eig_wide_ok(np)) wide = g_eig_wide == 1;
+    const bool spread = g_eig_wide == 2;   // 16-column blocks, shared memory padded so that one CTA fits per SM
     const int bc = wide ? 32 : 16, cta_cols = 2 * bc;
     p.a = a; p.diag_add = diag_add; p.n = n; p.np = np; p.ctas = np / cta_cols; p.max_sweeps = 20;
+    p.tol = tol > 0.0 ? tol : kEigConverged;
     p.w = w; p.lam = lam; p.sweeps = sweeps;
-    const size_t smem = (size_t)cta_cols * np * sizeof(double) + 2 * sizeof(double);
+    size_t smem = (size_t)cta_cols * np * sizeof(double) + 2 * sizeof(double);
+    if (spread && smem < (120u << 10)) smem = 120u << 10;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(batch * p.ctas));
     cfg.blockDim = dim3(32 * bc);
@@ -374,11 +384,16 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
         bool& configured = configured_on.get();                                                                    \
         if (!configured) {                                                                                         \
             RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)smem));                                                            \
+                                           (int)(smem > (120u << 10) ? smem : (120u << 10))));                     \
             if (32 * R / (2 * BC) > 8)                                                                             \
                 RPST_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<R, BC>,                                       \
                                                cudaFuncAttributeNonPortableClusterSizeAllowed, 1));                \
             configured = true;                                                                                     \
+        }                                                                                                          \
+        if (g_eig_wide == -2 || g_eig_wide == 2) {                                                                                    \
+            int nc = 0;                                                                                            \
+            RPST_CUDA(cudaOccupancyMaxActiveClusters(&nc, jacobi_cluster_kernel<R, BC>, &cfg));                    \
+            fprintf(stderr, "[rpst] jacobi<%d,%d>: cluster %d, max active clusters %d\n", R, BC, p.ctas, nc);      \
         }                                                                                                          \
         RPST_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<R, BC>, p));                                      \
         break;                                                                                                     \
@@ -436,7 +451,7 @@ extern "C" int rpst_sym_eig_fn(const double* a, int64_t batch, int64_t n, double
     RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sym_eig: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *w, *lam;
-    int rc = eig_decompose(a, batch, (int)n, diag_add, workspace, workspace_bytes, &w, &lam, sweeps, st);
+    int rc = eig_decompose(a, batch, (int)n, diag_add, workspace, workspace_bytes, &w, &lam, sweeps, st, 0.0);
     if (rc) return rc;
     // network/wct_rp.py:14-17 / 32-35: the spectrum is cut at the first value below 1e-5
     if (out_sqrt && (rc = eig_matfn(w, lam, batch, (int)n, 0.5, 1e-5, out_sqrt, st))) return rc;

@@ -24,10 +24,13 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
 int eig_padded_order(int n);
 size_t eig_workspace_bytes(int64_t batch, int n);
 int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* ws, size_t ws_bytes, double** w_out,
-                  double** lam_out, int* sweeps, cudaStream_t stream);
+                  double** lam_out, int* sweeps, cudaStream_t stream, double tol);
 int eig_matfn(const double* w, const double* lam, int64_t batch, int n, double power, double cut, double* out,
               cudaStream_t stream);
 int dgemm_small(const double* a, const double* b, double* c, int64_t batch, int n, cudaStream_t stream);
+// Jacobi stop for the WCT's own decompositions: a sweep that saw |cos| < 1e-5 leaves ~1e-10 (quadratic convergence),
+// far below the fp32-grade covariances that go in; the public rpst_sym_eig_fn keeps 1e-8 (-> 1e-16).  One sweep less.
+constexpr double kWctEigTol = 1e-5;
 // cov.cu: one kernel from fp32 features to the centred covariance (conversion + centring inside the SYRK)
 bool cov_fused_supported(const float* x, int64_t c, int64_t hw);
 size_t cov_fused_workspace_bytes(int64_t c);
@@ -195,7 +198,7 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
     double *ew, *el;
     const size_t eig_bytes = l.mats[0] - l.eig;
     double* T = m[5];
-    rc = eig_decompose(cov_c, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st);
+    rc = eig_decompose(cov_c, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol);
     if (rc) return rc;
     double* iroot = m[1];
     if ((rc = eig_matfn(ew, el, n, (int)c, -0.5, 1e-5, iroot, st))) return rc;
@@ -204,12 +207,12 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
         if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, root, st))) return rc;
         if ((rc = dgemm_small(root, cov_s, m[2], n, (int)c, st))) return rc;       // C^1/2 S
         if ((rc = dgemm_small(m[2], root, m[3], n, (int)c, st))) return rc;        // C^1/2 S C^1/2
-        if ((rc = eig_decompose(m[3], n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st))) return rc;
+        if ((rc = eig_decompose(m[3], n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol))) return rc;
         if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, m[4], st))) return rc;   // middle^(1/2)
         if ((rc = dgemm_small(iroot, m[4], m[2], n, (int)c, st))) return rc;
         if ((rc = dgemm_small(m[2], iroot, T, n, (int)c, st))) return rc;
     } else {
-        if ((rc = eig_decompose(cov_s, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st))) return rc;
+        if ((rc = eig_decompose(cov_s, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol))) return rc;
         if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, m[4], st))) return rc;   // S^(1/2)
         if ((rc = dgemm_small(m[4], iroot, T, n, (int)c, st))) return rc;
     }
