@@ -71,7 +71,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc, "-shared", "-o", LIB + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    # shared cudart: the static runtime would embed every runtime entry point (batch-memcpy names included) in the
+    # shipped binary; torch has libcudart.so.12 loaded already, the rpath covers a bare ctypes load
+    shared_rt = ["--cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    link = [nvcc, "-shared", "-o", LIB + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a", *shared_rt, "-lcuda"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         # libcuda may be absent on a GPU-less build box: the driver API is resolved at run time
@@ -81,7 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
     os.replace(LIB + ".tmp", LIB)
-    r = subprocess.run([nvcc, "-shared", "-o", DEBUG_LIB + ".tmp", *dbg_objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+    r = subprocess.run([nvcc, "-shared", "-o", DEBUG_LIB + ".tmp", *dbg_objs, "-gencode", "arch=compute_100a,code=sm_100a", *shared_rt],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout)

@@ -13,6 +13,7 @@
 //               cov = (G - S S^T / HW) / (HW - 1) (+ diag) and the exact means mu = shift + S / HW
 // The shift is a cheap sub-sampled mean: centring with ANY shift is exact after the rank-1 correction, and a shift
 // close to the mean keeps the correction small (no cancellation), so no full statistics pass is needed.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -208,6 +209,216 @@ __global__ void __launch_bounds__(kCovThreads, 1) cov_fused_kernel(CovParams p) 
     }
 }
 
+// ---- TMA-staged variant ----------------------------------------------------------------------------------------------
+// The register-staged kernel above is bound by the latency of its global loads (16 float4 in flight per converter
+// thread: 2.9 TB/s, ncu long_scoreboard 24 %).  Here a producer thread brings [128 channels x 64 positions] fp32 boxes
+// into a shared-memory ring with 2-D tensor-map TMA (cp.async.bulk.tensor.2d: 96-128 KiB in flight per SM, no
+// registers involved); the converter warps read the boxes with conflict-free 128-bit shared loads and build the same
+// bf16 hi/lo operand stages.  Out-of-range channels come back as zeros from the TMA unit (shift 0 there), out-of-range
+// positions are masked by the converters.
+//   warp 0       TMEM allocation; lane 0 = TMA producer
+//   warp 1       lane 0 = MMA issuer (same SYRK block schedule as above)
+//   warps 2..17  converters: warp w owns rows [8 w, 8 w + 8) of every box; warps 2..5 also run the epilogue
+constexpr int kCovBoxRows = 128;
+constexpr uint32_t kCovBoxBytes = kCovBoxRows * kTileK * sizeof(float);    // 32 KiB
+constexpr int kCovTmaConvWarps = 16;
+constexpr int kCovTmaThreads = 32 * (2 + kCovTmaConvWarps);
+
+template <int PARTS> struct CovTmaCfg {
+    static constexpr int fstages = PARTS == 2 ? 3 : 4;          // fp32 boxes
+    static constexpr int ostages = PARTS == 2 ? 2 : 3;          // operand stages (hi [+ lo], 256 rows)
+    static constexpr uint32_t ostage = kCovPartBytes * PARTS;
+    static constexpr size_t smem = 1024 + (size_t)fstages * kCovBoxBytes + (size_t)ostages * ostage;   // 225 KiB
+};
+
+__device__ __forceinline__ void tma_load_box_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int PARTS>
+__global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid_constant__ CUtensorMap tmap, CovParams p) {
+    using Cfg = CovTmaCfg<PARTS>;
+    constexpr int NF = Cfg::fstages, NO = Cfg::ostages;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* fring = smem;
+    unsigned char* oring = smem + (size_t)NF * kCovBoxBytes;
+    __shared__ uint64_t ffull[NF], fempty[NF], ofull[NO], oempty[NO], acc_full;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_shift[kCovMaxC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = p.cp / 128;
+    const int nkt = blockIdx.x < p.k_tiles ? (p.k_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NF; ++s) {
+            mbar_init(&ffull[s], 1);
+            mbar_init(&fempty[s], kCovTmaConvWarps);
+        }
+        for (int s = 0; s < NO; ++s) {
+            mbar_init(&ofull[s], kCovTmaConvWarps);
+            mbar_init(&oempty[s], 1);
+        }
+        mbar_init(&acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_shift[r] = r < p.cp ? __ldg(p.shift + r) : 0.f;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
+            uint32_t use = 0;
+            for (int it = 0; it < nkt; ++it) {
+                const int pos0 = (int)(((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileK);
+                for (int h = 0; h < m_tiles; ++h, ++use) {
+                    const uint32_t s = use % NF;
+                    mbar_wait(&fempty[s], ((use / NF) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&ffull[s], kCovBoxBytes);
+                    tma_load_box_2d(fring + (size_t)s * kCovBoxBytes, &tmap, pos0, h * kCovBoxRows, &ffull[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkt > 0) {
+            const uint32_t idesc0 = umma_idesc_bf16(128, p.cp);
+            const uint32_t idesc1 = umma_idesc_bf16(128, 128);
+            for (int it = 0; it < nkt; ++it) {
+                const int s = it % NO;
+                mbar_wait(&ofull[s], (uint32_t)(it / NO) & 1u);
+                tcgen05_fence_after();
+                const uint32_t hi = smem_u32(oring + (size_t)s * Cfg::ostage), lo = hi + kCovPartBytes;
+#pragma unroll
+                for (int k = 0; k < kTileK / kUmmaK; ++k) {
+                    const uint32_t ko = k * kUmmaK * 2;
+                    const bool acc = it > 0 || k > 0;
+                    umma_bf16_ss(tmem_base, umma_desc_k_sw128(hi + ko), umma_desc_k_sw128(hi + ko), idesc0, acc);
+                    if (PARTS == 2) {
+                        umma_bf16_ss(tmem_base, umma_desc_k_sw128(hi + ko), umma_desc_k_sw128(lo + ko), idesc0, true);
+                        umma_bf16_ss(tmem_base, umma_desc_k_sw128(lo + ko), umma_desc_k_sw128(hi + ko), idesc0, true);
+                    }
+                    if (m_tiles == 2) {
+                        const uint32_t h1 = hi + kTileBytes + ko, l1 = lo + kTileBytes + ko;
+                        umma_bf16_ss(tmem_base + 256, umma_desc_k_sw128(h1), umma_desc_k_sw128(h1), idesc1, acc);
+                        if (PARTS == 2) {
+                            umma_bf16_ss(tmem_base + 256, umma_desc_k_sw128(h1), umma_desc_k_sw128(l1), idesc1, true);
+                            umma_bf16_ss(tmem_base + 256, umma_desc_k_sw128(l1), umma_desc_k_sw128(h1), idesc1, true);
+                        }
+                    }
+                }
+                umma_commit(&oempty[s]);
+            }
+            umma_commit(&acc_full);
+        }
+    } else {
+        const int cw = warp - 2;
+        const int sub = lane >> 4;                 // which of the two rows of a shared-memory load
+        const int p4 = (lane & 15) * 4;            // first of this lane's 4 positions inside the k-tile
+        float acc[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
+        uint32_t use = 0;
+        for (int it = 0; it < nkt; ++it) {
+            const int64_t pos = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileK + p4;
+            const bool valid = pos < p.hw;                                   // hw % 4 == 0: a float4 is inside or outside
+            const int os = it % NO;
+            unsigned char* hi = oring + (size_t)os * Cfg::ostage;
+            unsigned char* lo = hi + kCovPartBytes;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h < m_tiles) {
+                    const uint32_t fs = use % NF;
+                    mbar_wait(&ffull[fs], (use / NF) & 1u);
+                    ++use;
+                    const unsigned char* box = fring + (size_t)fs * kCovBoxBytes;
+                    float4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        v[i] = *reinterpret_cast<const float4*>(box + (size_t)(cw * 8 + 2 * i + sub) * (kTileK * 4) + p4 * 4);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fempty[fs]);                 // the box may be overwritten
+                    if (h == 0) mbar_wait(&oempty[os], ((uint32_t)(it / NO) & 1u) ^ 1u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = h * kCovBoxRows + cw * 8 + 2 * i + sub;
+                        const float sh = s_shift[row];
+                        const float a = valid ? v[i].x - sh : 0.f, b = valid ? v[i].y - sh : 0.f;
+                        const float c2 = valid ? v[i].z - sh : 0.f, d = valid ? v[i].w - sh : 0.f;
+                        acc[h][i] += (a + b) + (c2 + d);
+                        const uint32_t h01 = pack_bf16x2(a, b), h23 = pack_bf16x2(c2, d);
+                        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((p4 >> 3) ^ (row & 7)) << 4) + ((lane & 1) << 3));
+                        *reinterpret_cast<uint2*>(hi + off) = make_uint2(h01, h23);
+                        if (PARTS == 2) {
+                            const uint32_t l01 = pack_bf16x2(a - __uint_as_float(h01 << 16), b - __uint_as_float(h01 & 0xffff0000u));
+                            const uint32_t l23 = pack_bf16x2(c2 - __uint_as_float(h23 << 16), d - __uint_as_float(h23 & 0xffff0000u));
+                            *reinterpret_cast<uint2*>(lo + off) = make_uint2(l01, l23);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ofull[os]);
+        }
+        // row sums of the shifted values: the 16 lanes sharing a row add up, fixed order
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = acc[h][i];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                const int row = h * kCovBoxRows + cw * 8 + 2 * i + sub;
+                if ((lane & 15) == 0 && row < p.cp) p.rowsum[(size_t)blockIdx.x * p.cp + row] = a;
+            }
+        }
+        if (warp <= 5) {                                         // epilogue: warps 2..5 = TMEM quarters 2,3,0,1
+            const int q = warp & 3;
+            const int r = q * 32 + lane;
+            float* out = p.partial + (size_t)blockIdx.x * p.cp * p.cp;
+            if (nkt > 0) {
+                mbar_wait(&acc_full, 0);
+                tcgen05_fence_after();
+            }
+            float vals[32];
+            for (int c0 = 0; c0 < p.cp; c0 += 32) {              // M-tile 0: rows 0..127, all columns
+                if (nkt > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, vals);
+                else
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) vals[j] = 0.f;
+                float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.cp + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+            }
+            if (m_tiles == 2) {
+                for (int c0 = 0; c0 < 128; c0 += 32) {           // M-tile 1: rows 128..255, columns 128..255
+                    if (nkt > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, vals);
+                    else
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) vals[j] = 0.f;
+                    float4* dst = reinterpret_cast<float4*>(out + (size_t)(128 + r) * p.cp + 128 + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // sub-sampled per-channel mean (up to 32 segments of 64 positions spread over the plane): the centring shift.
 // One warp per channel, every load independent.
 __global__ void __launch_bounds__(256) cov_shift_kernel(const float* __restrict__ x, int c, int cp, int64_t hw,
@@ -314,6 +525,26 @@ size_t cov_fused_workspace_bytes(int64_t c) {
            align_up(cp * sizeof(float), 256) + align_up(cp * sizeof(double), 256);
 }
 
+int64_t g_wct_cov_tma = 1;   // tuning knob "wct_cov_tma": 1 = TMA-staged kernel, 0 = register-staged kernel
+
+namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry-point query: librpst.so does not link libcuda
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+}  // namespace
+
 // cov [c,c] fp64 = centred covariance of x [c,hw] (+ diag_add on the diagonal); mean [c] fp32 exact channel means
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
               cudaStream_t st) {
@@ -337,12 +568,35 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
     if (!configured) {
         RPST_CUDA(cudaFuncSetAttribute(cov_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RPST_CUDA(cudaFuncSetAttribute(cov_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(cov_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CovTmaCfg<1>::smem));
+        RPST_CUDA(cudaFuncSetAttribute(cov_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CovTmaCfg<2>::smem));
         configured = true;
     }
-    if (passes == 3) cov_fused_kernel<2><<<grid, kCovThreads, smem, st>>>(p);
-    else cov_fused_kernel<1><<<grid, kCovThreads, smem, st>>>(p);
+    int entries = grid * kCovGroups;
+    EncodeTiledFn encode = g_wct_cov_tma && hw < (1ll << 31) - 64 ? encode_tiled_fn() : nullptr;
+    if (encode) {
+        // x as a 2-D tensor [c rows, hw positions]; boxes of 128 rows x 64 positions (256-byte row pieces)
+        CUtensorMap tmap;
+        const cuuint64_t gdim[2] = {(cuuint64_t)hw, (cuuint64_t)c};
+        const cuuint64_t gstride[1] = {(cuuint64_t)hw * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kCovBoxRows};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("wct covariance: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return RPST_ERR_CUDA;
+        }
+        entries = grid;
+        if (passes == 3) cov_tma_kernel<2><<<grid, kCovTmaThreads, CovTmaCfg<2>::smem, st>>>(tmap, p);
+        else cov_tma_kernel<1><<<grid, kCovTmaThreads, CovTmaCfg<1>::smem, st>>>(tmap, p);
+    } else {
+        if (passes == 3) cov_fused_kernel<2><<<grid, kCovThreads, smem, st>>>(p);
+        else cov_fused_kernel<1><<<grid, kCovThreads, smem, st>>>(p);
+    }
     RPST_CUDA(cudaGetLastError());
-    cov_rowsum_kernel<<<(cp + 31) / 32, 256, 0, st>>>(rowsum, shift, grid * kCovGroups, (int)c, cp, (double)hw, s_sum, mean);
+    cov_rowsum_kernel<<<(cp + 31) / 32, 256, 0, st>>>(rowsum, shift, entries, (int)c, cp, (double)hw, s_sum, mean);
     RPST_CUDA(cudaGetLastError());
     cov_finalize_kernel<<<dim3((unsigned)cp, 1), 256, 0, st>>>(partial, s_sum, grid, (int)c, cp, (double)hw, diag_add, cov);
     RPST_CUDA(cudaGetLastError());
