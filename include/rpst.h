@@ -195,6 +195,18 @@ RPST_API int rpst_sym_eig_fn(const double* a, int64_t batch, int64_t n, double d
                     double* out_inv_sqrt, double* eigenvalues, int32_t* sweeps, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* The same two functions for matrices that are positive DEFINITE after the shift, by a scaled coupled
+ * Newton-Schulz iteration (fp64 products on every SM; what rpst_wct_fuse uses for C > 64): every
+ * eigenvalue of a + diag_add I must be >= lmin > 0 (the WCT's covariances + 1e-4 I: lmin = 1e-4), where the
+ * reference's 1e-5 cut never fires and V diag(s^(+-1/2)) V^T is the principal root.  No host
+ * synchronisation: flags[b] = 1 marks a matrix whose iteration was NOT accepted (||Z Y - I||_F > 1e-7:
+ * indefinite input, eigenvalues far below lmin) — its outputs must not be used; run rpst_sym_eig_fn
+ * for it.  flags [batch] int32 (required).
+ * ------------------------------------------------------------------------------------------ */
+RPST_API size_t rpst_spd_roots_workspace_bytes(int64_t batch, int64_t n);
+RPST_API int rpst_spd_roots(const double* a, int64_t batch, int64_t n, double diag_add, double lmin, double* out_sqrt,
+                   double* out_inv_sqrt, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a6  WCTRPNet.whiten_and_color(cF, sF, method='closed-form')          network/wct_rp.py:82-114
  * a7  WCTRPNet.fuse(content_feats, style_feats)                        network/wct_rp.py:157-166

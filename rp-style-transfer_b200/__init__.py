@@ -11,7 +11,7 @@ from . import losses
 from .losses import calc_content_loss, calc_style_loss
 from .modules import CCAMDec, SELayer, ccam_attention
 from .mrf import MRFLoss, cal_affinity_map, cal_dist, mrf_match, packed_gemm
-from .wct import matrix_inv_sqrt, matrix_sqrt, wct_fuse, whiten_and_color
+from .wct import matrix_inv_sqrt, matrix_sqrt, spd_roots, wct_fuse, whiten_and_color
 from .sanet import (AdaptiveSANet, AdaptiveTransform, AEALReluModule, AEAModule, SANet, Transform, attention_core,
                     cal_affinity_matrix)
 from .segment import adaptive_instance_normalization_with_segment, do_mask_stylized, load_label_map, seg_adain_batch

@@ -48,6 +48,8 @@ SIGNATURES = {
     "rpst_gemm_packed": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_float, P, P, P]),
     "rpst_sym_eig_fn_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "rpst_sym_eig_fn": (c_int, [P, c_int64, c_int64, c_double, P, P, P, P, P, c_size_t, P]),
+    "rpst_spd_roots_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "rpst_spd_roots": (c_int, [P, c_int64, c_int64, c_double, c_double, P, P, P, P, c_size_t, P]),
     "rpst_wct_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "rpst_wct_fuse": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, c_size_t, P]),
     "rpst_sanet_attn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

@@ -72,6 +72,8 @@ static int apply_watchdog(int64_t ms) {
 
 extern "C" int rpst_version(void) { return RPST_VERSION; }
 
+namespace rpst { int64_t ns_flagged_total(); }
+
 extern "C" const char* rpst_last_error(void) { return rpst::g_err; }
 
 extern "C" int rpst_set_tuning(const char* name, int64_t value) {
@@ -84,6 +86,7 @@ extern "C" int rpst_set_tuning(const char* name, int64_t value) {
 extern "C" int64_t rpst_get_tuning(const char* name) {
     int64_t v = -1;
     if (name && !strcmp(name, "watchdog_ms")) return rpst::g_watchdog_ms;
+    if (name && !strcmp(name, "wct_ns_flagged")) return rpst::ns_flagged_total();   // read-only counter (synchronises)
     if (name && rpst::set_adain_tuning(name, 0, false, &v)) return v;
     return -1;
 }

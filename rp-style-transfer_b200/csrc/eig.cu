@@ -63,6 +63,7 @@ struct EigParams {
     double* w;            // [batch, np, np]: column j at w + j*np (lambda_j v_j)
     double* lam;          // [batch, np]
     int* sweeps;          // [batch] or null
+    const int* only;      // [batch] or null: matrices whose entry is 0 are skipped (every CTA of their cluster returns at once)
 };
 
 // circle-method tournament over m blocks: position -> block in round r and its inverse
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(32 * BC, (BC == 16 && ROWS < 16) ? 2 : 1) jaco
     constexpr int np = 32 * ROWS;
     const int n = p.n;
     const double* A = p.a + (size_t)batch * n * n;
+    if (p.only && p.only[batch] == 0) return;      // uniform across the cluster: nobody reaches a cluster barrier
 
     // round-0 arrangement: slot 0 = block `rank`, slot 1 = block m-1-rank (block b = columns 16b..16b+15).
     // Column j of the symmetric input = row j; the padding extends A with an identity block.
@@ -282,9 +284,11 @@ done:
 // out[b] (n x n, row-major, ld n) = sum_j g(lam_j) w_j w_j^T restricted to the first n rows,
 // g = lam^(power) / lam^2, dropped where lam < cut (network/wct_rp.py:14-17: spectrum truncated at 1e-5)
 __global__ void __launch_bounds__(256) matfn_kernel(const double* __restrict__ w, const double* __restrict__ lam, int n,
-                                                    int np, double power, double cut, double* __restrict__ out) {
+                                                    int np, double power, double cut, double* __restrict__ out,
+                                                    const int* __restrict__ only) {
     __shared__ double wi[16][17], wj[16][17], g[16];
     const int b = blockIdx.z;
+    if (only && only[b] == 0) return;
     const double* W = w + (size_t)b * np * np;
     const double* L = lam + (size_t)b * np;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -307,25 +311,6 @@ __global__ void __launch_bounds__(256) matfn_kernel(const double* __restrict__ w
     if (i < n && j < n) out[(size_t)b * n * n + (size_t)i * n + j] = acc;
 }
 
-// C[b] = A[b] * B[b]   (n x n fp64, row-major)
-__global__ void __launch_bounds__(256) dgemm_small_kernel(const double* __restrict__ a, const double* __restrict__ bm,
-                                                          double* __restrict__ c, int n) {
-    __shared__ double sa[16][17], sb[16][17];
-    const size_t off = (size_t)blockIdx.z * n * n;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
-    double acc = 0.0;
-    for (int k0 = 0; k0 < n; k0 += 16) {
-        sa[ty][tx] = (i < n && k0 + tx < n) ? a[off + (size_t)i * n + k0 + tx] : 0.0;
-        sb[ty][tx] = (k0 + ty < n && j < n) ? bm[off + (size_t)(k0 + ty) * n + j] : 0.0;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc = fma(sa[ty][k], sb[k][tx], acc);
-        __syncthreads();
-    }
-    if (i < n && j < n) c[off + (size_t)i * n + j] = acc;
-}
-
 }  // namespace
 
 // ---- internal host API -------------------------------------------------------------------------
@@ -344,7 +329,7 @@ size_t eig_workspace_bytes(int64_t batch, int n) {
 
 // a [batch,n,n] -> W/lam in workspace
 int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* ws, size_t ws_bytes, double** w_out,
-                  double** lam_out, int* sweeps, cudaStream_t stream, double tol) {
+                  double** lam_out, int* sweeps, cudaStream_t stream, double tol, const int* only) {
     RPST_CHECK_ARG(n >= 1 && n <= 512, "sym_eig: order must be in [1, 512] (got %d)", n);
     const int np = eig_padded_order(n);
     if (ws_bytes < eig_workspace_bytes(batch, n)) {
@@ -363,7 +348,7 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
     const int bc = wide ? 32 : 16, cta_cols = 2 * bc;
     p.a = a; p.diag_add = diag_add; p.n = n; p.np = np; p.ctas = np / cta_cols; p.max_sweeps = 20;
     p.tol = tol > 0.0 ? tol : kEigConverged;
-    p.w = w; p.lam = lam; p.sweeps = sweeps;
+    p.w = w; p.lam = lam; p.sweeps = sweeps; p.only = only;
     size_t smem = (size_t)cta_cols * np * sizeof(double) + 2 * sizeof(double);
     if (spread && smem < (120u << 10)) smem = 120u << 10;
     cudaLaunchConfig_t cfg{};
@@ -418,17 +403,10 @@ int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* 
 }
 
 int eig_matfn(const double* w, const double* lam, int64_t batch, int n, double power, double cut, double* out,
-              cudaStream_t stream) {
+              cudaStream_t stream, const int* only) {
     const int np = eig_padded_order(n);
     dim3 grid((unsigned)((n + 15) / 16), (unsigned)((n + 15) / 16), (unsigned)batch);
-    matfn_kernel<<<grid, 256, 0, stream>>>(w, lam, n, np, power, cut, out);
-    RPST_CUDA(cudaGetLastError());
-    return RPST_OK;
-}
-
-int dgemm_small(const double* a, const double* b, double* c, int64_t batch, int n, cudaStream_t stream) {
-    dim3 grid((unsigned)((n + 15) / 16), (unsigned)((n + 15) / 16), (unsigned)batch);
-    dgemm_small_kernel<<<grid, 256, 0, stream>>>(a, b, c, n);
+    matfn_kernel<<<grid, 256, 0, stream>>>(w, lam, n, np, power, cut, out, only);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
@@ -451,11 +429,11 @@ extern "C" int rpst_sym_eig_fn(const double* a, int64_t batch, int64_t n, double
     RPST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "sym_eig: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *w, *lam;
-    int rc = eig_decompose(a, batch, (int)n, diag_add, workspace, workspace_bytes, &w, &lam, sweeps, st, 0.0);
+    int rc = eig_decompose(a, batch, (int)n, diag_add, workspace, workspace_bytes, &w, &lam, sweeps, st, 0.0, nullptr);
     if (rc) return rc;
     // network/wct_rp.py:14-17 / 32-35: the spectrum is cut at the first value below 1e-5
-    if (out_sqrt && (rc = eig_matfn(w, lam, batch, (int)n, 0.5, 1e-5, out_sqrt, st))) return rc;
-    if (out_inv_sqrt && (rc = eig_matfn(w, lam, batch, (int)n, -0.5, 1e-5, out_inv_sqrt, st))) return rc;
+    if (out_sqrt && (rc = eig_matfn(w, lam, batch, (int)n, 0.5, 1e-5, out_sqrt, st, nullptr))) return rc;
+    if (out_inv_sqrt && (rc = eig_matfn(w, lam, batch, (int)n, -0.5, 1e-5, out_inv_sqrt, st, nullptr))) return rc;
     if (eigenvalues) {
         const int np = eig_padded_order((int)n);
         RPST_CUDA(cudaMemcpy2DAsync(eigenvalues, (size_t)n * sizeof(double), lam, (size_t)np * sizeof(double),

@@ -24,10 +24,15 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
 int eig_padded_order(int n);
 size_t eig_workspace_bytes(int64_t batch, int n);
 int eig_decompose(const double* a, int64_t batch, int n, double diag_add, void* ws, size_t ws_bytes, double** w_out,
-                  double** lam_out, int* sweeps, cudaStream_t stream, double tol);
+                  double** lam_out, int* sweeps, cudaStream_t stream, double tol, const int* only);
 int eig_matfn(const double* w, const double* lam, int64_t batch, int n, double power, double cut, double* out,
-              cudaStream_t stream);
-int dgemm_small(const double* a, const double* b, double* c, int64_t batch, int n, cudaStream_t stream);
+              cudaStream_t stream, const int* only);
+// nsroot.cu: Newton-Schulz roots of positive definite matrices; flag[b] = 1 where the Jacobi path must take over
+size_t ns_roots_workspace_bytes(int64_t batch, int n);
+int ns_roots(const double* a, int64_t batch, int n, double diag_add, double lmin, double* root, double* iroot, int* flag,
+             void* workspace, size_t workspace_bytes, cudaStream_t st);
+int dgemm_batched(const double* a, const double* b, double* c, int64_t batch, int n, cudaStream_t st);
+extern int64_t g_wct_roots_ns;
 // Jacobi stop for the WCT's own decompositions: a sweep that saw |cos| < 1e-5 leaves ~1e-10 (quadratic convergence),
 // far below the fp32-grade covariances that go in; the public rpst_sym_eig_fn keeps 1e-8 (-> 1e-16).  One sweep less.
 constexpr double kWctEigTol = 1e-5;
@@ -80,7 +85,7 @@ __global__ void transform_finalize_kernel(const double* __restrict__ t, const fl
 }
 
 struct WctLayout {
-    size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, eig, mats[6], t32, bias,
+    size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, flag, ns, eig, mats[6], t32, bias,
         t_hi, t_lo, x_hi, x_lo, fused, total;
     int splits;
 };
@@ -110,6 +115,8 @@ WctLayout wct_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     l.partial = take((size_t)l.splits * c * c * sizeof(float));
     l.cov_c = take((size_t)n * c * c * sizeof(double));
     l.cov_s = take((size_t)n * c * c * sizeof(double));
+    l.flag = take((size_t)n * sizeof(int));
+    l.ns = take(ns_roots_workspace_bytes(n, (int)c));
     l.eig = take(eig_workspace_bytes(n, (int)c));
     for (int i = 0; i < 6; ++i) l.mats[i] = take((size_t)n * c * c * sizeof(double));
     l.t32 = take((size_t)c * c * sizeof(float));
@@ -198,23 +205,34 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
     double *ew, *el;
     const size_t eig_bytes = l.mats[0] - l.eig;
     double* T = m[5];
-    rc = eig_decompose(cov_c, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol);
-    if (rc) return rc;
+    // (A + 1e-4 I)^(+-1/2): Newton-Schulz where the matrix is positive definite as constructed (lmin), the Jacobi
+    // eigensolver with the reference's |s| / 1e-5-cut semantics for the matrices that iteration flags (or for all of
+    // them with the knob off)
+    int* flag = reinterpret_cast<int*>(w + l.flag);
+    auto roots = [&](const double* a, double lmin, double* root, double* iroot) -> int {
+        const int* only = nullptr;
+        if (g_wct_roots_ns && c > 64) {          // up to 64 channels the Jacobi solve is as fast as the iteration's launches
+            if (int r = ns_roots(a, n, (int)c, 1e-4, lmin, root, iroot, flag, w + l.ns, l.eig - l.ns, st)) return r;
+            only = flag;
+        }
+        if (int r = eig_decompose(a, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol, only)) return r;
+        if (root) if (int r = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, root, st, only)) return r;
+        if (iroot) if (int r = eig_matfn(ew, el, n, (int)c, -0.5, 1e-5, iroot, st, only)) return r;
+        return RPST_OK;
+    };
     double* iroot = m[1];
-    if ((rc = eig_matfn(ew, el, n, (int)c, -0.5, 1e-5, iroot, st))) return rc;
     if (method == 0) {
         double* root = m[0];
-        if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, root, st))) return rc;
-        if ((rc = dgemm_small(root, cov_s, m[2], n, (int)c, st))) return rc;       // C^1/2 S
-        if ((rc = dgemm_small(m[2], root, m[3], n, (int)c, st))) return rc;        // C^1/2 S C^1/2
-        if ((rc = eig_decompose(m[3], n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol))) return rc;
-        if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, m[4], st))) return rc;   // middle^(1/2)
-        if ((rc = dgemm_small(iroot, m[4], m[2], n, (int)c, st))) return rc;
-        if ((rc = dgemm_small(m[2], iroot, T, n, (int)c, st))) return rc;
+        if ((rc = roots(cov_c, 1.0, root, iroot))) return rc;                       // cov_c carries + I (network/wct_rp.py:87)
+        if ((rc = dgemm_batched(root, cov_s, m[2], n, (int)c, st))) return rc;      // C^1/2 S
+        if ((rc = dgemm_batched(m[2], root, m[3], n, (int)c, st))) return rc;       // C^1/2 S C^1/2
+        if ((rc = roots(m[3], 1e-4, m[4], nullptr))) return rc;                     // middle^(1/2)
+        if ((rc = dgemm_batched(iroot, m[4], m[2], n, (int)c, st))) return rc;
+        if ((rc = dgemm_batched(m[2], iroot, T, n, (int)c, st))) return rc;
     } else {
-        if ((rc = eig_decompose(cov_s, n, (int)c, 1e-4, w + l.eig, eig_bytes, &ew, &el, nullptr, st, kWctEigTol))) return rc;
-        if ((rc = eig_matfn(ew, el, n, (int)c, 0.5, 1e-5, m[4], st))) return rc;   // S^(1/2)
-        if ((rc = dgemm_small(m[4], iroot, T, n, (int)c, st))) return rc;
+        if ((rc = roots(cov_c, 1.0, nullptr, iroot))) return rc;
+        if ((rc = roots(cov_s, 1e-4, m[4], nullptr))) return rc;                    // S^(1/2)
+        if ((rc = dgemm_batched(m[4], iroot, T, n, (int)c, st))) return rc;
     }
     if (transform_out)
         RPST_CUDA(cudaMemcpyAsync(transform_out, T, (size_t)n * c * c * sizeof(double), cudaMemcpyDeviceToDevice, st));

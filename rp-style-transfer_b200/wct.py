@@ -64,6 +64,25 @@ def wct_fuse(content_feats: torch.Tensor, style_feats: torch.Tensor, method: str
 
 
 @device_guard
+def spd_roots(A: torch.Tensor, lmin: float, diag_add: float = 1e-4):
+    """(A + diag_add I)^(1/2), (A + diag_add I)^(-1/2) and the per-matrix "not accepted" flags of the Newton-Schulz
+    iteration (`rpst_spd_roots`); A [b,n,n] or [n,n] symmetric with every shifted eigenvalue >= lmin."""
+    if not A.is_cuda:
+        raise RuntimeError("rpst: matrix functions need a CUDA tensor (there is no CPU path)")
+    squeeze = A.dim() == 2
+    a = (A[None] if squeeze else A).to(torch.float64).contiguous()
+    assert a.dim() == 3 and a.shape[1] == a.shape[2]
+    b, n = a.shape[:2]
+    L = _lib.lib()
+    ws = _ws(L.rpst_spd_roots_workspace_bytes(b, n), a.device)
+    rs, ri = torch.empty_like(a), torch.empty_like(a)
+    flags = torch.zeros(b, dtype=torch.int32, device=a.device)
+    _lib.check(L.rpst_spd_roots(a.data_ptr(), b, n, diag_add, lmin, rs.data_ptr(), ri.data_ptr(), flags.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream()))
+    return (rs[0], ri[0], flags) if squeeze else (rs, ri, flags)
+
+
+@device_guard
 def whiten_and_color(cF: torch.Tensor, sF: torch.Tensor, method: str = "closed-form") -> torch.Tensor:
     """Function form of network/wct_rp.py:82 — cF [C,HWc], sF [C,HWs] (any float dtype; the reference
     passes fp64) -> [C,HWc] in cF's dtype."""
