@@ -31,13 +31,20 @@ constexpr uint32_t kCovPartBytes = 2 * kTileBytes;          // [256 rows x 64 po
 
 struct CovParams {
     const float* x;          // [c, hw] one sample, row stride hw
-    const float* shift;      // [cp] per-channel shift (rows >= c: 0)
+    float* shift;            // [cp] per-channel shift (rows >= c: 0); written by the TMA kernel itself
     float* partial;          // [grid, cp, cp] per-CTA partial Gram (blocks on/above the diagonal only)
     float* rowsum;           // [grid * 2, cp] per-CTA and converter-group sums of (x - shift)
     int64_t hw;
     int c, cp;               // channels, padded to 128 / 256
     int k_tiles;             // ceil(hw / 64)
     int passes;              // 1: bf16, 3: bf16x3
+    // TMA kernel only: the whole covariance in ONE launch (shift in the prologue, grid barrier, distributed fp64 finalize)
+    int* barrier;            // zeroed before the launch
+    double* s_sum;           // [cp] column sums of the shifted values (exchange buffer)
+    double* cov;             // [c, c] result
+    float* mean;             // [c] exact means or null
+    double diag_add;
+    unsigned long long* prof;   // optional [8 x 2] %globaltimer stamps of CTA 0 and the last CTA (tuning knob "wct_cov_prof")
 };
 
 // {lo, hi} -> packed bf16x2 with round-to-nearest-even: lo in bits 0..15 (the element at the lower address)
@@ -237,6 +244,22 @@ __device__ __forceinline__ void tma_load_box_2d(void* smem_dst, const CUtensorMa
         :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+// k-th grid-wide barrier of a cooperative launch (every CTA resident): the counter was zeroed before the launch
+__device__ __forceinline__ void grid_barrier(int* counter, int k) {
+    __threadfence();                                   // this thread's global writes before the arrival
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1);
+        const int target = k * (int)gridDim.x;
+        const uint64_t t0 = global_timer_ns();
+        while (ld_acquire(counter) < target) {
+            __nanosleep(32);
+            if (watchdog_expired(t0)) __trap();
+        }
+    }
+    __syncthreads();
+}
+
 template <int PARTS>
 __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid_constant__ CUtensorMap tmap, CovParams p) {
     using Cfg = CovTmaCfg<PARTS>;
@@ -265,24 +288,60 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
-    for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_shift[r] = r < p.cp ? __ldg(p.shift + r) : 0.f;
+    // the producer thread (the one that initialised the barriers) starts the first boxes at once: they fly while the
+    // converter warps compute the shift
+    const bool prof = p.prof != nullptr && threadIdx.x == 64 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+    unsigned long long* pr = p.prof + (blockIdx.x == 0 ? 0 : 8);
+    if (prof) pr[0] = global_timer_ns();
+    const int total_boxes = nkt * m_tiles;
+    const int pre_boxes = total_boxes < NF ? total_boxes : NF;
+    auto issue_box = [&](int u) {
+        const int it = u / m_tiles, h = u - it * m_tiles;
+        const int pos0 = (int)(((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileK);
+        const uint32_t sl = (uint32_t)u % NF;
+        mbar_arrive_expect_tx(&ffull[sl], kCovBoxBytes);
+        tma_load_box_2d(fring + (size_t)sl * kCovBoxBytes, &tmap, pos0, h * kCovBoxRows, &ffull[sl]);
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
+        for (int u = 0; u < pre_boxes; ++u) issue_box(u);
+    }
+    if (warp >= 2) {
+        // Centring shift = mean of up to 32 segments of 64 positions spread over the plane.  The channels are dealt over
+        // the CTAs (one warp per channel, every load independent) and exchanged through global memory: when every CTA
+        // sampled every channel itself, 148 CTAs asked the same L2 lines at the same moment (10.8 us).  Any shift is exact
+        // after the rank-1 correction; it only has to be within a few sigma of the mean.
+        const int segs = (int)(p.hw / 64 > 32 ? 32 : p.hw / 64);      // hw >= 64
+        const int64_t stride = (p.hw / segs) & ~(int64_t)3;            // >= 64, keeps the 8-byte loads aligned
+        for (int ch = (int)blockIdx.x + (warp - 2) * (int)gridDim.x; ch < p.cp; ch += kCovTmaConvWarps * (int)gridDim.x) {
+            float a = 0.f;
+            if (ch < p.c) {
+                const float* xr = p.x + (int64_t)ch * p.hw + 2 * lane;
+#pragma unroll 8
+                for (int sg = 0; sg < segs; ++sg) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(xr + sg * stride));
+                    a += v.x + v.y;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                a /= (float)(segs * 64);
+            }
+            if (lane == 0) p.shift[ch] = a;
+        }
+    }
+    grid_barrier(p.barrier, 1);
+    for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_shift[r] = r < p.cp ? __ldcg(p.shift + r) : 0.f;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    if (prof) pr[1] = global_timer_ns();
 
     if (warp == 0) {
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
-            uint32_t use = 0;
-            for (int it = 0; it < nkt; ++it) {
-                const int pos0 = (int)(((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTileK);
-                for (int h = 0; h < m_tiles; ++h, ++use) {
-                    const uint32_t s = use % NF;
-                    mbar_wait(&fempty[s], ((use / NF) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&ffull[s], kCovBoxBytes);
-                    tma_load_box_2d(fring + (size_t)s * kCovBoxBytes, &tmap, pos0, h * kCovBoxRows, &ffull[s]);
-                }
+            for (int u = pre_boxes; u < total_boxes; ++u) {
+                mbar_wait(&fempty[(uint32_t)u % NF], (((uint32_t)u / NF) & 1u) ^ 1u);
+                issue_box(u);
             }
         }
     } else if (warp == 1) {
@@ -368,6 +427,7 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(&ofull[os]);
         }
+        if (prof) pr[2] = global_timer_ns();
         // row sums of the shifted values: the 16 lanes sharing a row add up, fixed order
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -380,43 +440,123 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
                 if ((lane & 15) == 0 && row < p.cp) p.rowsum[(size_t)blockIdx.x * p.cp + row] = a;
             }
         }
-        if (warp <= 5) {                                         // epilogue: warps 2..5 = TMEM quarters 2,3,0,1
-            const int q = warp & 3;
+        {
+            // epilogue on all 16 converter warps: warp w reads TMEM lane quarter w & 3 (the only one it may access) and
+            // every fourth 32-column chunk of it; each lane stores whole 32-byte sectors (256-bit stores)
+            const int q = warp & 3, sub = (warp - 2) >> 2;
             const int r = q * 32 + lane;
             float* out = p.partial + (size_t)blockIdx.x * p.cp * p.cp;
             if (nkt > 0) {
                 mbar_wait(&acc_full, 0);
                 tcgen05_fence_after();
             }
+            const int chunks0 = p.cp / 32, chunks = chunks0 + (m_tiles == 2 ? 4 : 0);
             float vals[32];
-            for (int c0 = 0; c0 < p.cp; c0 += 32) {              // M-tile 0: rows 0..127, all columns
-                if (nkt > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, vals);
+            for (int ck = sub; ck < chunks; ck += 4) {
+                // M-tile 0: rows 0..127, all columns; M-tile 1: rows 128..255, columns 128..255 (TMEM columns 256..383)
+                const bool second = ck >= chunks0;
+                const int c0 = second ? (ck - chunks0) * 32 : ck * 32;
+                if (nkt > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (second ? 256u : 0u) + (uint32_t)c0, vals);
                 else
 #pragma unroll
                     for (int j = 0; j < 32; ++j) vals[j] = 0.f;
-                float4* dst = reinterpret_cast<float4*>(out + (size_t)r * p.cp + c0);
+                float* dst = second ? out + (size_t)(128 + r) * p.cp + 128 + c0 : out + (size_t)r * p.cp + c0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
-            }
-            if (m_tiles == 2) {
-                for (int c0 = 0; c0 < 128; c0 += 32) {           // M-tile 1: rows 128..255, columns 128..255
-                    if (nkt > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, vals);
-                    else
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) vals[j] = 0.f;
-                    float4* dst = reinterpret_cast<float4*>(out + (size_t)(128 + r) * p.cp + 128 + c0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
-                }
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                 :: "l"(dst + 8 * j), "f"(vals[8 * j]), "f"(vals[8 * j + 1]), "f"(vals[8 * j + 2]), "f"(vals[8 * j + 3]),
+                                    "f"(vals[8 * j + 4]), "f"(vals[8 * j + 5]), "f"(vals[8 * j + 6]), "f"(vals[8 * j + 7]) : "memory");
             }
         }
     }
     tcgen05_fence_before();
+    __threadfence();                                   // partial Gram and row sums visible before the grid barrier
     __syncthreads();
     if (warp == 0) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (prof) pr[3] = global_timer_ns();
+    // ---- grid barriers (cooperative launch: every CTA is resident) and the fp64 finalize spread over the CTAs ----
+    grid_barrier(p.barrier, 2);
+    if (prof) pr[4] = global_timer_ns();
+    const int parts = (int)gridDim.x;
+    double* s_S = reinterpret_cast<double*>(smem);                         // [256] column sums of the shifted values
+    double* red = s_S + kCovMaxC;                                          // [2 rows][18 slices][8 columns][32 groups]: 72 KiB
+    // S[r] = sum over CTAs of the partial row sums: rows dealt over the CTAs, one warp per row, lanes over the CTAs,
+    // lane-ordered tree (fixed order); exchanged through global memory (every CTA summing every row itself: 11 us of
+    // same-line L2 contention)
+    for (int r = (int)blockIdx.x + warp * (int)gridDim.x; r < p.cp; r += (kCovTmaThreads / 32) * (int)gridDim.x) {
+        double a = 0.0;
+        for (int z = lane; z < parts; z += 32) a += (double)__ldcg(p.rowsum + (size_t)z * p.cp + r);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            p.s_sum[r] = a;
+            if (p.mean && r < p.c) p.mean[r] = (float)((double)s_shift[r] + a / (double)p.hw);
+        }
+    }
+    grid_barrier(p.barrier, 3);
+    for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_S[r] = r < p.cp ? __ldcg(p.s_sum + r) : 0.0;
+    __syncthreads();
+    if (prof) pr[5] = global_timer_ns();
+    const double hw = (double)p.hw;
+    // Covariance rows (computed SYRK blocks only) are dealt over the CTAs, two rows in flight at a time (a CTA owns one or
+    // two rows at C = 256 and the phase is latency-bound): thread (jg, zs) sums 8 columns of every 18th partial.
+    for (int ibase = blockIdx.x; ibase < p.cp; ibase += 2 * gridDim.x) {
+        const int jg = threadIdx.x & 31, zs = threadIdx.x >> 5;          // 32 groups of eight columns x 18 slices of the partials
+        double a[2][8];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = ibase + rr * (int)gridDim.x;
+            const int j0 = (i >= 128 ? 128 : 0) + 8 * jg;                // rows >= 128 start at column 128
+            const bool live = i < p.cp && j0 < p.cp && (i < 128 || jg < 16);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[rr][e] = 0.0;
+            if (live) {
+                const float* src = p.partial + (size_t)i * p.cp + j0;
+                const size_t zstride = (size_t)p.cp * p.cp;
+#pragma unroll 1
+                for (int k0 = 0; k0 < 9; k0 += 5) {                      // 5 + 4 sector loads in flight (148 partials)
+                    float t[5][8];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const int z = zs + 18 * (k0 + k);
+                        if (k0 + k < 9 && z < parts) {
+                            asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=f"(t[k][0]), "=f"(t[k][1]), "=f"(t[k][2]), "=f"(t[k][3]), "=f"(t[k][4]), "=f"(t[k][5]),
+                                           "=f"(t[k][6]), "=f"(t[k][7]) : "l"(src + (size_t)z * zstride) : "memory");
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) t[k][e] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) a[rr][e] += (double)t[k][e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) red[(((size_t)rr * 18 + zs) * 8 + e) * 32 + jg] = a[rr][e];   // [row][slice][column][group]
+        }
+        __syncthreads();
+        if (zs < 16) {                                                   // thread (jg, rr = zs / 8, e = zs % 8) finishes one column
+            const int rr = zs >> 3, e = zs & 7;
+            const int i = ibase + rr * (int)gridDim.x;
+            const int j = (i >= 128 ? 128 : 0) + 8 * jg + e;
+            if (i < p.c && j < p.c && (i < 128 || jg < 16)) {
+                double g = 0.0;
+#pragma unroll
+                for (int q = 0; q < 18; ++q) g += red[(((size_t)rr * 18 + q) * 8 + e) * 32 + jg];   // fixed order
+                const double v = (g - s_S[i] * s_S[j] / hw) / (hw - 1.0);
+                p.cov[(size_t)i * p.c + j] = v + (i == j ? p.diag_add : 0.0);
+                if (i < 128 && j >= 128) p.cov[(size_t)j * p.c + i] = v;        // block (1,0) is the mirror of block (0,1)
+            }
+        }
+        __syncthreads();
+    }
+    if (prof) pr[6] = global_timer_ns();
 }
 
 // sub-sampled per-channel mean (up to 32 segments of 64 positions spread over the plane): the centring shift.
@@ -522,9 +662,10 @@ size_t cov_fused_workspace_bytes(int64_t c) {
     const size_t cp = c <= 128 ? 128 : 256;
     const size_t g = (size_t)sm_count();
     return align_up(g * cp * cp * sizeof(float), 256) + align_up(g * kCovGroups * cp * sizeof(float), 256) +
-           align_up(cp * sizeof(float), 256) + align_up(cp * sizeof(double), 256);
+           align_up(cp * sizeof(float), 256) + align_up(cp * sizeof(double), 256) + 256;   // + the grid-barrier counter
 }
 
+int64_t g_wct_cov_prof = 0;  // device pointer to 16 x uint64 time stamps (0 = off); bring-up / tuning only
 int64_t g_wct_cov_tma = 1;   // tuning knob "wct_cov_tma": 1 = TMA-staged kernel, 0 = register-staged kernel
 
 namespace {
@@ -555,8 +696,6 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
     float* rowsum = reinterpret_cast<float*>(w + align_up((size_t)g * cp * cp * sizeof(float), 256));
     float* shift = reinterpret_cast<float*>(reinterpret_cast<char*>(rowsum) + align_up((size_t)g * kCovGroups * cp * sizeof(float), 256));
     double* s_sum = reinterpret_cast<double*>(reinterpret_cast<char*>(shift) + align_up((size_t)cp * sizeof(float), 256));
-    cov_shift_kernel<<<(cp + 7) / 8, 256, 0, st>>>(x, (int)c, cp, hw, shift);
-    RPST_CUDA(cudaGetLastError());
     CovParams p{};
     p.x = x; p.shift = shift; p.partial = partial; p.rowsum = rowsum; p.hw = hw; p.c = (int)c; p.cp = cp;
     p.k_tiles = (int)((hw + kTileK - 1) / kTileK);
@@ -572,7 +711,6 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
         RPST_CUDA(cudaFuncSetAttribute(cov_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CovTmaCfg<2>::smem));
         configured = true;
     }
-    int entries = grid * kCovGroups;
     EncodeTiledFn encode = g_wct_cov_tma && hw < (1ll << 31) - 64 ? encode_tiled_fn() : nullptr;
     if (encode) {
         // x as a 2-D tensor [c rows, hw positions]; boxes of 128 rows x 64 positions (256-byte row pieces)
@@ -588,13 +726,31 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
             set_error("wct covariance: cuTensorMapEncodeTiled failed (%d)", (int)r);
             return RPST_ERR_CUDA;
         }
-        entries = grid;
-        if (passes == 3) cov_tma_kernel<2><<<grid, kCovTmaThreads, CovTmaCfg<2>::smem, st>>>(tmap, p);
-        else cov_tma_kernel<1><<<grid, kCovTmaThreads, CovTmaCfg<1>::smem, st>>>(tmap, p);
-    } else {
-        if (passes == 3) cov_fused_kernel<2><<<grid, kCovThreads, smem, st>>>(p);
-        else cov_fused_kernel<1><<<grid, kCovThreads, smem, st>>>(p);
+        // one cooperative launch: shift, SYRK, grid barrier, fp64 finalize (every CTA must be resident for the barrier)
+        int* barrier = reinterpret_cast<int*>(reinterpret_cast<char*>(s_sum) + align_up((size_t)cp * sizeof(double), 256));
+        RPST_CUDA(cudaMemsetAsync(barrier, 0, sizeof(int), st));
+        p.barrier = barrier; p.cov = cov; p.mean = mean; p.diag_add = diag_add; p.s_sum = s_sum; p.shift = shift;
+        p.prof = reinterpret_cast<unsigned long long*>(g_wct_cov_prof);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kCovTmaThreads);
+        cfg.dynamicSmemBytes = passes == 3 ? CovTmaCfg<2>::smem : CovTmaCfg<1>::smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (passes == 3) RPST_CUDA(cudaLaunchKernelEx(&cfg, cov_tma_kernel<2>, tmap, p));
+        else RPST_CUDA(cudaLaunchKernelEx(&cfg, cov_tma_kernel<1>, tmap, p));
+        return RPST_OK;
     }
+    cov_shift_kernel<<<(cp + 7) / 8, 256, 0, st>>>(x, (int)c, cp, hw, shift);
+    RPST_CUDA(cudaGetLastError());
+    p.shift = shift;
+    const int entries = grid * kCovGroups;
+    if (passes == 3) cov_fused_kernel<2><<<grid, kCovThreads, smem, st>>>(p);
+    else cov_fused_kernel<1><<<grid, kCovThreads, smem, st>>>(p);
     RPST_CUDA(cudaGetLastError());
     cov_rowsum_kernel<<<(cp + 31) / 32, 256, 0, st>>>(rowsum, shift, entries, (int)c, cp, (double)hw, s_sum, mean);
     RPST_CUDA(cudaGetLastError());
