@@ -118,6 +118,11 @@ struct GemmParams {
     int batch;
     int64_t a_batch_bytes, b_batch_bytes;   // byte strides of the packed operands (0 = shared by the batch)
     int64_t out_batch;                      // element stride of the output
+    // TOPK epilogue (MRF): instead of storing the tile, every row keeps its `topk` largest values of the
+    // tile's columns (ties: lower column first) -> cand_val / cand_idx [m, n_tiles * 4, topk]; `out` is not written
+    int topk;
+    float* cand_val;
+    int* cand_idx;
 };
 
 __device__ __forceinline__ void gemm_tile(int rem, int m_tiles, int n_tiles, int& mb, int& nb) {
@@ -130,7 +135,11 @@ __device__ __forceinline__ void gemm_tile(int rem, int m_tiles, int n_tiles, int
 // Persistent: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (A-tile-major order so that
 // concurrently running CTAs share operand tiles in L2).  Two 256-column TMEM accumulators: the epilogue
 // of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams p) {
+constexpr int kTopkSubs = 4;   // TOPK epilogue: 4 warps per TMEM lane quarter, 64 columns of the tile each (one warp per
+                               // quarter took 2.5x the tile's MMA time for its two passes)
+template <int TOPK>   // 0: store the tile; 4 / 8: top-k epilogue tracking that many values (k <= TOPK)
+__global__ void __launch_bounds__(TOPK ? 64 + 128 * kTopkSubs : kGemmThreads, 1) gemm_packed_kernel(GemmParams p) {
+    constexpr int kEpiWarps = TOPK ? 4 * kTopkSubs : 4;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles must start on a 1024-byte boundary of the shared address space
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -152,7 +161,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);   // one arrival per epilogue warp
+            mbar_init(&acc_empty[b], kEpiWarps);   // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -253,6 +262,76 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
             const int64_t row = (int64_t)mb * 128 + q * 32 + lane;
             const float radd = (p.row_add && row < p.m) ? __ldg(p.row_add + row) : 0.f;
             const int ncols = (int)min((int64_t)kGemmBN, p.n - (int64_t)nb * kGemmBN);   // valid columns of this tile
+            if (TOPK) {
+                // Top-k of this row over the tile's columns without a divergent insertion (a lane inserts at ~k ln(256/k)
+                // of the 256 columns, but SOME lane of the warp inserts at nearly every column, so a conditional
+                // insertion chain ran for the whole warp almost every time: 0.67 ms against 0.44 for the materialised
+                // path).  Pass 1: branch-free min/max chain on the VALUES only -> the tile's k-th largest value tau and
+                // the number of strictly larger ones.  Pass 2 (TMEM read again): emit every x > tau and the first
+                // (k - greater) columns with x == tau (ascending column order = the reference's tie order,
+                // network/base.py:338-344), unsorted; the merge kernel orders them.
+                constexpr int KM = TOPK ? TOPK : 1;   // levels of the chain: always all of them (a runtime bound put the list
+                                                      // into local memory: 137 cycles per element); k only picks tau
+                const int kk = p.topk;
+                float bv[KM];
+#pragma unroll
+                for (int r = 0; r < KM; ++r) bv[r] = -INFINITY;
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * kGemmBN) + ((uint32_t)(q * 32) << 16);
+                const int sub = (warp - 2) >> 2;                                  // this warp's 64-column slice of the tile
+                const int cbeg = sub * (kGemmBN / kTopkSubs), cend = min(ncols, cbeg + kGemmBN / kTopkSubs);
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(tacc + (uint32_t)c0, v);
+                    const int col0 = nb * kGemmBN + c0;
+                    const bool ragged = col0 + 32 > p.n;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = p.alpha * v[j];
+                        if (ragged && col0 + j >= p.n) x = -INFINITY;
+#pragma unroll
+                        for (int r = 0; r < KM; ++r) {
+                            const float hi = fmaxf(bv[r], x);
+                            x = fminf(bv[r], x);
+                            bv[r] = hi;
+                        }
+                    }
+                }
+                float tau = -INFINITY;
+                int greater = 0;
+#pragma unroll
+                for (int r = 0; r < KM; ++r) tau = r == kk - 1 ? bv[r] : tau;
+#pragma unroll
+                for (int r = 0; r < KM; ++r) greater += (r < kk && bv[r] > tau) ? 1 : 0;
+                int need_eq = kk - greater, pos = 0;
+                const int64_t base = ((((int64_t)bi * p.m + row) * p.n_tiles + nb) * kTopkSubs + sub) * kk;
+                const bool live = row < p.m;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(tacc + (uint32_t)c0, v);
+                    const int col0 = nb * kGemmBN + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = p.alpha * v[j];
+                        const bool valid = col0 + j < p.n;
+                        const bool gt = valid && x > tau;
+                        const bool eq = valid && x == tau && need_eq > 0;
+                        if ((gt || eq) && live && pos < kk) {
+                            p.cand_val[base + pos] = x;
+                            p.cand_idx[base + pos] = col0 + j;
+                            ++pos;
+                            if (eq) --need_eq;
+                        }
+                    }
+                }
+                // fewer than k valid columns in this tile: pad with "nothing" entries
+                if (live)
+                    for (; pos < kk; ++pos) {
+                        p.cand_val[base + pos] = -INFINITY;
+                        p.cand_idx[base + pos] = 0x7fffffff;
+                    }
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 float v[32];
@@ -277,6 +356,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_packed_kernel(GemmParams
                                 dst[j] = fmaf(p.alpha, v[j], radd + (p.col_add ? __ldg(p.col_add + col0 + j) : 0.f));
                     }
                 }
+            }
             }
             // hand the accumulator back to the MMA thread
             tcgen05_fence_before();
@@ -361,6 +441,9 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                        const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
 
+// set by gemm_packed_topk around its call of gemm_packed_batched (same thread): selects the TOPK epilogue
+static thread_local struct { int k; float* val; int* idx; } g_topk_request = {0, nullptr, nullptr};
+
 int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                         int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                         const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
@@ -413,7 +496,9 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
     static PerDeviceFlag configured_on;
     bool& configured = configured_on.get();
     if (!configured) {
-        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     p.batch = batch; p.a_batch_bytes = a_batch_bytes; p.b_batch_bytes = b_batch_bytes; p.out_batch = out_batch;
@@ -421,9 +506,31 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
     RPST_CHECK_ARG(total_tiles < (1ll << 30), "gemm_packed: too many output tiles");
     int64_t grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;
-    gemm_packed_kernel<<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
+    if (g_topk_request.k > 0) {
+        p.topk = g_topk_request.k; p.cand_val = g_topk_request.val; p.cand_idx = g_topk_request.idx;
+        constexpr int threads = 64 + 128 * kTopkSubs;
+        if (p.topk <= 4) gemm_packed_kernel<4><<<(unsigned)grid, threads, smem, stream>>>(p);
+        else gemm_packed_kernel<8><<<(unsigned)grid, threads, smem, stream>>>(p);
+    } else {
+        gemm_packed_kernel<0><<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
+    }
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
+}
+
+// lists of candidates per row that gemm_packed_topk emits for n columns
+int gemm_topk_lists(int64_t n) { return (int)((n + kGemmBN - 1) / kGemmBN) * kTopkSubs; }
+
+// A.B^T with the per-row top-k epilogue: candidates [m, gemm_topk_lists(n), topk] (value, column), unsorted inside a
+// list; the tile itself is never stored.  alpha = -1 ranks the negated product (MRF `reverse`).
+int gemm_packed_topk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t m, int64_t n, int64_t k,
+                     int passes, float alpha, int topk, float* cand_val, int* cand_idx, cudaStream_t stream) {
+    RPST_CHECK_ARG(topk >= 1 && topk <= 8 && cand_val && cand_idx, "gemm_packed_topk: bad top-k request");
+    g_topk_request.k = topk; g_topk_request.val = cand_val; g_topk_request.idx = cand_idx;
+    const int rc = gemm_packed_batched(a_hi, a_lo, b_hi, b_lo, nullptr, m, n, k, n, passes, alpha, nullptr, nullptr, 1, 0, 1, 0, 0,
+                                       0, stream);
+    g_topk_request.k = 0;
+    return rc;
 }
 
 }  // namespace rpst

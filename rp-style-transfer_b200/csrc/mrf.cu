@@ -3,9 +3,11 @@
 //
 //   1. mrf_norm_kernel     per-position channel L2 norms of content / style (F.normalize, eps 1e-12)
 //   2. pack_operand        normalised features -> bf16 hi/lo K-major tiles (positions x channels)
-//   3. gemm_packed x2      NCC = c^T s  and  NCC^T = s^T c on the tensor cores, bf16x3 (fp32-grade) so
-//                          that top-k INDICES agree with the reference on tie-free inputs
-//   4. topk_rows_kernel    warp-per-row running top-k (k <= 8) of NCC (dim 1) and of NCC^T (dim 0)
+//   3. gemm_packed_topk x2 NCC = c^T s  and  NCC^T = s^T c on the tensor cores, bf16x3 (fp32-grade) so that top-k
+//                          INDICES agree with the reference on tie-free inputs; the L x L products are NEVER stored
+//                          (SURVEY 2b K10): the GEMM epilogue keeps every row's running top-k (k <= 8) of each
+//                          64-column slice of a tile straight out of TMEM (two branch-free passes) -> [L, L/64, k] candidates
+//   4. topk_merge_kernel   warp per row: merges the per-tile candidate lists (values descending, ties -> lower index)
 //   5. mrf_loss_kernel     sum over the union of both top-k sets of ||a_i - b_j||^2, evaluated sparsely
 //                          from the NCC values (no L x L affinity / distance temporaries), fp64 tree
 //   (optional) mrf_scatter_kernel  the dense binary [L,L] affinity map the reference returns
@@ -19,45 +21,59 @@ int pack_operand(const float* x, int64_t rows, int64_t k, int64_t stride_r, int6
 int gemm_packed(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                 int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                 const float* col_add, cudaStream_t stream);
+int gemm_topk_lists(int64_t n);
+int gemm_packed_topk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t m, int64_t n, int64_t k,
+                     int passes, float alpha, int topk, float* cand_val, int* cand_idx, cudaStream_t stream);
 
 namespace {
 
 constexpr int kMaxTopK = 8;
 
-// x [c, l] -> sq[l] = sum_c x^2, nrm[l] = max(sqrt(sq), 1e-12), inv[l] = 1/nrm
-__global__ void __launch_bounds__(128) mrf_norm_kernel(const float* __restrict__ x, int64_t c, int64_t l,
+// x [c, l] -> sq[l] = sum_c x^2, nrm[l] = max(sqrt(sq), 1e-12), inv[l] = 1/nrm.
+// Block = 32 positions (lanes) x 8 channel slices (warps): every load is one 128-byte line, 8 independent lines in flight
+// per warp; the slices meet in shared memory and are added in slice order.
+__global__ void __launch_bounds__(256) mrf_norm_kernel(const float* __restrict__ x, int64_t c, int64_t l,
                                                        float* __restrict__ sq, float* __restrict__ nrm,
                                                        float* __restrict__ inv) {
-    const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (pos >= l) return;
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t pos = blockIdx.x * 32ll + lane;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int64_t ch = 0;
-    for (; ch + 4 <= c; ch += 4) {
+    if (pos < l) {
+        int64_t ch = w;
+        for (; ch + 24 < c; ch += 32) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float v = __ldg(x + (ch + u) * l + pos);
-            acc[u] = fmaf(v, v, acc[u]);
+            for (int u = 0; u < 4; ++u) {
+                const float v = __ldg(x + (ch + 8 * u) * l + pos);
+                acc[u] = fmaf(v, v, acc[u]);
+            }
+        }
+        for (; ch < c; ch += 8) {
+            const float v = __ldg(x + ch * l + pos);
+            acc[0] = fmaf(v, v, acc[0]);
         }
     }
-    for (; ch < c; ++ch) {
-        const float v = __ldg(x + ch * l + pos);
-        acc[0] = fmaf(v, v, acc[0]);
+    red[w][lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    if (w == 0 && pos < l) {
+        float s = red[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) s += red[q][lane];
+        const float n = fmaxf(sqrtf(s), 1e-12f);
+        sq[pos] = s;
+        nrm[pos] = n;
+        inv[pos] = 1.f / n;
     }
-    const float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    const float n = fmaxf(sqrtf(s), 1e-12f);
-    sq[pos] = s;
-    nrm[pos] = n;
-    inv[pos] = 1.f / n;
 }
 
-// Running top-k of each row of a row-major [rows, cols] matrix.  One warp per row.  Values sorted
-// descending, ties resolved towards the lower column index.
-// idx_out[row*idx_stride_row + r*idx_stride_k], val_out likewise.
+// Merge of the per-tile candidate lists of the GEMM's top-k epilogue: cand_* [rows, nt, K], every list sorted (value
+// descending, ties -> lower column).  One warp per row; lane t folds tiles t, t + 32, ... into its own sorted list,
+// then K rounds of warp arg-max over the list heads.  Values sorted descending, ties towards the lower column index;
+// idx_out[row*stride_row + r*stride_k], val_out likewise.
 template <int K>
-__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ mat, int64_t rows, int64_t cols,
-                                                        int64_t ld, int64_t* __restrict__ idx_out,
-                                                        float* __restrict__ val_out, int64_t stride_row,
-                                                        int64_t stride_k) {
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                                                         int64_t rows, int nt, int64_t* __restrict__ idx_out,
+                                                         float* __restrict__ val_out, int64_t stride_row, int64_t stride_k) {
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x / 32) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -65,22 +81,25 @@ __global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict_
     int id[K];
 #pragma unroll
     for (int r = 0; r < K; ++r) { v[r] = -INFINITY; id[r] = 0x7fffffff; }
-    const float* src = mat + row * ld;
-    for (int64_t cidx = lane; cidx < cols; cidx += 32) {
-        float x = __ldg(src + cidx);
-        int xi = (int)cidx;
-        if (x > v[K - 1]) {   // strictly greater: an equal later element never displaces an earlier one
+    for (int t = lane; t < nt; t += 32) {
+        const float* cv = cand_val + (row * nt + t) * K;
+        const int* ci = cand_idx + (row * nt + t) * K;
 #pragma unroll
-            for (int r = 0; r < K; ++r) {
-                const bool before = x > v[r] || (x == v[r] && xi < id[r]);
-                if (before) {
-                    const float tv = v[r]; const int ti = id[r];
-                    v[r] = x; id[r] = xi; x = tv; xi = ti;
+        for (int e = 0; e < K; ++e) {
+            float x = __ldg(cv + e);
+            int xi = __ldg(ci + e);
+            if (x > v[K - 1] || (x == v[K - 1] && xi < id[K - 1])) {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const bool before = x > v[r] || (x == v[r] && xi < id[r]);
+                    if (before) {
+                        const float tv = v[r]; const int ti = id[r];
+                        v[r] = x; id[r] = xi; x = tv; xi = ti;
+                    }
                 }
             }
         }
     }
-    // merge the 32 sorted lists: K rounds of warp arg-max over the list heads
     for (int r = 0; r < K; ++r) {
         float bv = v[0];
         int bi = id[0];
@@ -114,14 +133,19 @@ struct LossParams {
     float sign;            // -1 if the map was negated (reverse=True)
     double scale;          // 1/(l*k) or 1/(l*l)
     float* loss;
+    double* partial;       // [kLossBlocks]
+    int* ticket;           // zero on entry, reset by the kernel
 };
 
-// dist_ij = |a_i|^2 + |b_j|^2 - 2 a_i.b_j with a_i.b_j = ncc_ij * |a_i| * |b_j|
-__global__ void __launch_bounds__(1024) mrf_loss_kernel(LossParams p) {
-    __shared__ double red[32];
+// dist_ij = |a_i|^2 + |b_j|^2 - 2 a_i.b_j with a_i.b_j = ncc_ij * |a_i| * |b_j|.  kLossBlocks blocks write fp64 partial
+// sums, the last one to finish (ticket) adds them in block order: deterministic, one launch.
+constexpr int kLossBlocks = 64;
+__global__ void __launch_bounds__(256) mrf_loss_kernel(LossParams p) {
+    __shared__ double red[8];
+    __shared__ bool last;
     double acc = 0.0;
     const int64_t n = p.l * p.k;
-    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+    for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < n; t += kLossBlocks * 256ll) {
         {   // row set: (i, idx1[i][r])
             const int64_t i = t / p.k;
             const int64_t j = p.idx1[t];
@@ -143,11 +167,20 @@ __global__ void __launch_bounds__(1024) mrf_loss_kernel(LossParams p) {
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) *p.loss = (float)(v * p.scale);
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int q = 0; q < 8; ++q) v += red[q];
+        p.partial[blockIdx.x] = v;
+        __threadfence();
+        last = atomicAdd(p.ticket, 1) == kLossBlocks - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double v = 0.0;
+        for (int q = 0; q < kLossBlocks; ++q) v += __ldcg(p.partial + q);
+        *p.loss = (float)(v * p.scale);
+        *p.ticket = 0;                       // ready for the next call on this workspace
     }
 }
 
@@ -163,7 +196,8 @@ struct MrfLayout {
     size_t tiles, vec;             // bytes of one packed operand / one [l] float vector
     size_t off_tiles[4];           // c_hi, c_lo, s_hi, s_lo
     size_t off_vec[6];             // c_sq, c_nrm, c_inv, s_sq, s_nrm, s_inv
-    size_t off_ncc, off_ncct, off_val1, off_val0, total;
+    size_t off_cval, off_cidx, off_val1, off_val0, off_loss, total;    // top-k candidates [l, gemm_topk_lists(l), k] (shared by both products)
+    int nt;
 };
 
 MrfLayout mrf_layout(int64_t c, int64_t l, int k) {
@@ -173,33 +207,35 @@ MrfLayout mrf_layout(int64_t c, int64_t l, int k) {
     size_t o = 0;
     for (int i = 0; i < 4; ++i) { m.off_tiles[i] = o; o += align_up(m.tiles, 256); }
     for (int i = 0; i < 6; ++i) { m.off_vec[i] = o; o += m.vec; }
-    m.off_ncc = o; o += align_up((size_t)l * l * sizeof(float), 256);
-    m.off_ncct = o; o += align_up((size_t)l * l * sizeof(float), 256);
+    m.nt = gemm_topk_lists(l);
+    m.off_cval = o; o += align_up((size_t)l * m.nt * k * sizeof(float), 256);
+    m.off_cidx = o; o += align_up((size_t)l * m.nt * k * sizeof(int), 256);
     m.off_val1 = o; o += align_up((size_t)l * k * sizeof(float), 256);
     m.off_val0 = o; o += align_up((size_t)l * k * sizeof(float), 256);
+    m.off_loss = o; o += 1024;                 // 64 fp64 partial sums + the ticket
     m.total = o;
     return m;
 }
 
 template <int K>
-int launch_topk(const float* mat, int64_t rows, int64_t cols, int64_t ld, int64_t* idx, float* val, int64_t sr,
-                int64_t sk, cudaStream_t st) {
-    topk_rows_kernel<K><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(mat, rows, cols, ld, idx, val, sr, sk);
+int launch_merge(const float* cv, const int* ci, int64_t rows, int nt, int64_t* idx, float* val, int64_t sr, int64_t sk,
+                 cudaStream_t st) {
+    topk_merge_kernel<K><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cv, ci, rows, nt, idx, val, sr, sk);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
 
-int topk_dispatch(int k, const float* mat, int64_t rows, int64_t cols, int64_t ld, int64_t* idx, float* val,
-                  int64_t sr, int64_t sk, cudaStream_t st) {
+int merge_dispatch(int k, const float* cv, const int* ci, int64_t rows, int nt, int64_t* idx, float* val, int64_t sr,
+                   int64_t sk, cudaStream_t st) {
     switch (k) {
-        case 1: return launch_topk<1>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        case 2: return launch_topk<2>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        case 3: return launch_topk<3>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        case 4: return launch_topk<4>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        case 5: return launch_topk<5>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        case 6: return launch_topk<6>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        case 7: return launch_topk<7>(mat, rows, cols, ld, idx, val, sr, sk, st);
-        default: return launch_topk<8>(mat, rows, cols, ld, idx, val, sr, sk, st);
+        case 1: return launch_merge<1>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        case 2: return launch_merge<2>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        case 3: return launch_merge<3>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        case 4: return launch_merge<4>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        case 5: return launch_merge<5>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        case 6: return launch_merge<6>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        case 7: return launch_merge<7>(cv, ci, rows, nt, idx, val, sr, sk, st);
+        default: return launch_merge<8>(cv, ci, rows, nt, idx, val, sr, sk, st);
     }
 }
 
@@ -207,7 +243,7 @@ int topk_dispatch(int k, const float* mat, int64_t rows, int64_t cols, int64_t l
 
 // per-position channel norms (shared with the adaptive SANet cosine affinity)
 int channel_norms(const float* x, int64_t c, int64_t l, float* sq, float* nrm, float* inv, cudaStream_t st) {
-    mrf_norm_kernel<<<(unsigned)((l + 127) / 128), 128, 0, st>>>(x, c, l, sq, nrm, inv);
+    mrf_norm_kernel<<<(unsigned)((l + 31) / 32), 256, 0, st>>>(x, c, l, sq, nrm, inv);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
 }
@@ -239,9 +275,9 @@ extern "C" int rpst_mrf_match(const float* content, const float* style, int64_t 
     char* w = static_cast<char*>(workspace);
     float* vec[6];
     for (int i = 0; i < 6; ++i) vec[i] = reinterpret_cast<float*>(w + m.off_vec[i]);
-    const unsigned nb = (unsigned)((l + 127) / 128);
-    mrf_norm_kernel<<<nb, 128, 0, st>>>(content, c, l, vec[0], vec[1], vec[2]);
-    mrf_norm_kernel<<<nb, 128, 0, st>>>(style, c, l, vec[3], vec[4], vec[5]);
+    const unsigned nb = (unsigned)((l + 31) / 32);
+    mrf_norm_kernel<<<nb, 256, 0, st>>>(content, c, l, vec[0], vec[1], vec[2]);
+    mrf_norm_kernel<<<nb, 256, 0, st>>>(style, c, l, vec[3], vec[4], vec[5]);
     RPST_CUDA(cudaGetLastError());
     void* c_hi = w + m.off_tiles[0]; void* c_lo = w + m.off_tiles[1];
     void* s_hi = w + m.off_tiles[2]; void* s_lo = w + m.off_tiles[3];
@@ -249,18 +285,20 @@ extern "C" int rpst_mrf_match(const float* content, const float* style, int64_t 
     if (rc) return rc;
     rc = pack_operand(style, l, c, 1, l, vec[5], s_hi, passes == 3 ? s_lo : nullptr, st);
     if (rc) return rc;
-    float* ncc = reinterpret_cast<float*>(w + m.off_ncc);
-    float* ncct = reinterpret_cast<float*>(w + m.off_ncct);
+    float* cval = reinterpret_cast<float*>(w + m.off_cval);
+    int* cidx = reinterpret_cast<int*>(w + m.off_cidx);
     const float alpha = reverse ? -1.f : 1.f;
-    rc = gemm_packed(c_hi, c_lo, s_hi, s_lo, ncc, l, l, c, l, passes, alpha, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = gemm_packed(s_hi, s_lo, c_hi, c_lo, ncct, l, l, c, l, passes, alpha, nullptr, nullptr, st);
-    if (rc) return rc;
     float* val1 = reinterpret_cast<float*>(w + m.off_val1);
     float* val0 = reinterpret_cast<float*>(w + m.off_val0);
-    rc = topk_dispatch(k, ncc, l, l, l, idx_dim1, val1, k, 1, st);     // [l, k]
+    // NCC rows (content i -> style j: torch.topk(dim=1)) and NCC^T rows (style j -> content i: dim=0); the candidate
+    // buffers are reused by the second product (stream order)
+    rc = gemm_packed_topk(c_hi, c_lo, s_hi, s_lo, l, l, c, passes, alpha, k, cval, cidx, st);
     if (rc) return rc;
-    rc = topk_dispatch(k, ncct, l, l, l, idx_dim0, val0, 1, l, st);    // [k, l]
+    rc = merge_dispatch(k, cval, cidx, l, m.nt, idx_dim1, val1, k, 1, st);      // [l, k]
+    if (rc) return rc;
+    rc = gemm_packed_topk(s_hi, s_lo, c_hi, c_lo, l, l, c, passes, alpha, k, cval, cidx, st);
+    if (rc) return rc;
+    rc = merge_dispatch(k, cval, cidx, l, m.nt, idx_dim0, val0, 1, l, st);      // [k, l]
     if (rc) return rc;
     if (affinity) {
         RPST_CUDA(cudaMemsetAsync(affinity, 0, (size_t)l * l * sizeof(float), st));
@@ -274,7 +312,10 @@ extern "C" int rpst_mrf_match(const float* content, const float* style, int64_t 
         lp.l = l; lp.k = k; lp.sign = alpha;
         lp.scale = loss_mean_over_all ? 1.0 / ((double)l * (double)l) : 1.0 / ((double)l * (double)k);
         lp.loss = loss;
-        mrf_loss_kernel<<<1, 1024, 0, st>>>(lp);
+        lp.partial = reinterpret_cast<double*>(w + m.off_loss);
+        lp.ticket = reinterpret_cast<int*>(w + m.off_loss + 768);
+        RPST_CUDA(cudaMemsetAsync(lp.ticket, 0, sizeof(int), st));
+        mrf_loss_kernel<<<kLossBlocks, 256, 0, st>>>(lp);
         RPST_CUDA(cudaGetLastError());
     }
     return RPST_OK;
@@ -304,8 +345,8 @@ extern "C" int rpst_pairwise_sqdist(const float* a, const float* b, int64_t d, i
     float* v = reinterpret_cast<float*>(w + 2 * ta + 2 * tb);
     float* a_sq = v; float* a_t1 = v + vb / 4; float* a_t2 = v + 2 * vb / 4;
     float* b_sq = v + 3 * vb / 4; float* b_t1 = v + 4 * vb / 4; float* b_t2 = v + 5 * vb / 4;
-    mrf_norm_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(a, d, m, a_sq, a_t1, a_t2);
-    mrf_norm_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b, d, n, b_sq, b_t1, b_t2);
+    mrf_norm_kernel<<<(unsigned)((m + 31) / 32), 256, 0, st>>>(a, d, m, a_sq, a_t1, a_t2);
+    mrf_norm_kernel<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(b, d, n, b_sq, b_t1, b_t2);
     RPST_CUDA(cudaGetLastError());
     int rc = pack_operand(a, m, d, 1, m, nullptr, a_hi, a_lo, st);
     if (rc) return rc;
