@@ -8,12 +8,13 @@
 //                         (hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM, ~2^-16 relative error,
 //                         i.e. fp32-grade results at one third of the bf16 tensor rate).
 //
-// Kernel anatomy (persistent, one CTA per SM walking 128 x 256 output tiles, 6 warps):
+// Kernel anatomy (persistent, one CTA per SM walking 128 x 256 output tiles, 6 warps; 18 with the top-k epilogue):
 //   warp 0 / 1 thread : TMA producer — one 1-D bulk copy per 16 KiB operand tile into a 4-stage ring
 //   warp 1            : allocates TMEM (2 x 256 columns); 1 thread issues tcgen05.mma (M=128, N=256, K=16,
 //                       4 per stage), commits the stage back to the producer and the finished
 //                       accumulator to the epilogue
-//   warps 2..5        : epilogue — tcgen05.ld (each warp its 32-lane TMEM quarter), scale/add, store;
+//   warps 2..5 [..17] : epilogue — tcgen05.ld (warp w: TMEM lane quarter w % 4, column slice (w - 2) / 4), scale/add,
+//                       store (256-bit), or top-k selection, or packed bf16 operand tiles for a following product;
 //                       runs concurrently with the MMAs of the next tile (double-buffered accumulator)
 #include <cuda_fp16.h>
 
@@ -86,7 +87,12 @@ __global__ void __launch_bounds__(256) pack_operand_kernel(PackParams p) {
 }
 
 // ------------------------------------------------------------------------------------------ gemm
+constexpr int kTopkSubs = 4;   // TOPK epilogue: 4 warps per TMEM lane quarter, 64 columns of the tile each (one warp per quarter
+                               // took 2.5x the tile's MMA time for its two passes).  The storing epilogues use them only for short
+                               // K: with 16 warps the 16384^2 K = 512 fp32 product went 755 -> 715 us, but the K = 16384
+                               // products (P.V, f_psi) lost 2-8 %.
 constexpr int kGemmThreads = 192;
+constexpr int kGemmTopkThreads = 64 + 128 * kTopkSubs;
 constexpr int kGemmBN = 256;                         // output tile: 128 x 256
 constexpr int kGemmBTiles = kGemmBN / kTileRows;     // 16 KiB B tiles per stage and precision part
 constexpr uint32_t kGemmPartBytes = kTileBytes * (1 + kGemmBTiles);   // A tile + B tiles of one part (48 KiB)
@@ -123,6 +129,11 @@ struct GemmParams {
     int topk;
     float* cand_val;
     int* cand_idx;
+    // PACKED epilogue (TOPK = -1): the product leaves as bf16 hi (+ lo) K-major operand tiles [m x n(K)] for the next GEMM
+    // (rows = this product's rows, K = its columns) instead of fp32: no fp32 round trip and no pack pass in between
+    char* pk_hi;
+    char* pk_lo;
+    int pk_ktiles;           // ceil(n / 64)
 };
 
 __device__ __forceinline__ void gemm_tile(int rem, int m_tiles, int n_tiles, int& mb, int& nb) {
@@ -135,11 +146,13 @@ __device__ __forceinline__ void gemm_tile(int rem, int m_tiles, int n_tiles, int
 // Persistent: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (A-tile-major order so that
 // concurrently running CTAs share operand tiles in L2).  Two 256-column TMEM accumulators: the epilogue
 // of tile i overlaps the MMAs of tile i+1.
-constexpr int kTopkSubs = 4;   // TOPK epilogue: 4 warps per TMEM lane quarter, 64 columns of the tile each (one warp per
-                               // quarter took 2.5x the tile's MMA time for its two passes)
-template <int TOPK>   // 0: store the tile; 4 / 8: top-k epilogue tracking that many values (k <= TOPK)
-__global__ void __launch_bounds__(TOPK ? 64 + 128 * kTopkSubs : kGemmThreads, 1) gemm_packed_kernel(GemmParams p) {
-    constexpr int kEpiWarps = TOPK ? 4 * kTopkSubs : 4;
+// TOPK 0: store the tile; 4 / 8: top-k epilogue tracking that many values (k <= TOPK); -1: packed operand tiles.
+// WIDE: 16 epilogue warps instead of 4 (always with the top-k epilogue; for the storing epilogues when K <= 1024, where the
+// epilogue of a tile takes longer than its MMAs).
+template <int TOPK, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? kGemmTopkThreads : kGemmThreads, 1) gemm_packed_kernel(GemmParams p) {
+    constexpr int kSubs = WIDE ? kTopkSubs : 1;
+    constexpr int kEpiWarps = 4 * kSubs;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operand tiles must start on a 1024-byte boundary of the shared address space
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(TOPK ? 64 + 128 * kTopkSubs : kGemmThreads, 1)
             }
         }
     } else {
-        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        // epilogue warps: TMEM lane quarter = warp % 4, column slice = (warp - 2) / 4
         const int q = warp & 3;
         int ti = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
@@ -262,7 +275,9 @@ __global__ void __launch_bounds__(TOPK ? 64 + 128 * kTopkSubs : kGemmThreads, 1)
             const int64_t row = (int64_t)mb * 128 + q * 32 + lane;
             const float radd = (p.row_add && row < p.m) ? __ldg(p.row_add + row) : 0.f;
             const int ncols = (int)min((int64_t)kGemmBN, p.n - (int64_t)nb * kGemmBN);   // valid columns of this tile
-            if (TOPK) {
+            const int sub = (warp - 2) >> 2;                                  // this warp's column slice of the tile
+            const int cbeg = sub * (kGemmBN / kSubs), cend = min(ncols, cbeg + kGemmBN / kSubs);
+            if (TOPK > 0) {
                 // Top-k of this row over the tile's columns without a divergent insertion (a lane inserts at ~k ln(256/k)
                 // of the 256 columns, but SOME lane of the warp inserts at nearly every column, so a conditional
                 // insertion chain ran for the whole warp almost every time: 0.67 ms against 0.44 for the materialised
@@ -270,15 +285,13 @@ __global__ void __launch_bounds__(TOPK ? 64 + 128 * kTopkSubs : kGemmThreads, 1)
                 // the number of strictly larger ones.  Pass 2 (TMEM read again): emit every x > tau and the first
                 // (k - greater) columns with x == tau (ascending column order = the reference's tie order,
                 // network/base.py:338-344), unsorted; the merge kernel orders them.
-                constexpr int KM = TOPK ? TOPK : 1;   // levels of the chain: always all of them (a runtime bound put the list
+                constexpr int KM = TOPK > 0 ? TOPK : 1;   // levels of the chain: always all of them (a runtime bound put the list
                                                       // into local memory: 137 cycles per element); k only picks tau
                 const int kk = p.topk;
                 float bv[KM];
 #pragma unroll
                 for (int r = 0; r < KM; ++r) bv[r] = -INFINITY;
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * kGemmBN) + ((uint32_t)(q * 32) << 16);
-                const int sub = (warp - 2) >> 2;                                  // this warp's 64-column slice of the tile
-                const int cbeg = sub * (kGemmBN / kTopkSubs), cend = min(ncols, cbeg + kGemmBN / kTopkSubs);
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cend; c0 += 32) {
                     float v[32];
@@ -331,15 +344,55 @@ __global__ void __launch_bounds__(TOPK ? 64 + 128 * kTopkSubs : kGemmThreads, 1)
                         p.cand_val[base + pos] = -INFINITY;
                         p.cand_idx[base + pos] = 0x7fffffff;
                     }
+            } else if (TOPK < 0) {
+                // one 16-byte chunk (8 columns) per store at its swizzled place; columns past n are zero (K padding)
+                const int r = q * 32 + lane;
+                char* hi_rb = p.pk_hi + (int64_t)bi * p.out_batch + (int64_t)mb * p.pk_ktiles * kTileBytes;
+                char* lo_rb = p.pk_lo ? p.pk_lo + (int64_t)bi * p.out_batch + (int64_t)mb * p.pk_ktiles * kTileBytes : nullptr;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + kGemmBN / kSubs; c0 += 32) {
+                    const int64_t col0 = (int64_t)nb * kGemmBN + c0;
+                    if (col0 >= (int64_t)p.pk_ktiles * kTileK) break;
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + (uint32_t)(buf * kGemmBN) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        __align__(16) __nv_bfloat16 h[8];
+                        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int64_t col = col0 + ch * 8 + e;
+                            const float x = col < p.n ? fmaf(p.alpha, v[ch * 8 + e], radd + (p.col_add ? __ldg(p.col_add + col) : 0.f)) : 0.f;
+                            split_bf16(x, h[e], l[e]);
+                        }
+                        const int64_t kt = col0 / kTileK;
+                        const int cidx = (int)((col0 % kTileK) / 8) + ch;
+                        const size_t off = (size_t)kt * kTileBytes + tile_chunk_offset(r, cidx);
+                        *reinterpret_cast<uint4*>(hi_rb + off) = *reinterpret_cast<const uint4*>(h);
+                        if (lo_rb) *reinterpret_cast<uint4*>(lo_rb + off) = *reinterpret_cast<const uint4*>(l);
+                    }
+                }
             } else {
 #pragma unroll 1
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 float v[32];
                 tmem_ld_32x32(tmem_base + (uint32_t)(buf * kGemmBN) + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                 const int64_t col0 = (int64_t)nb * kGemmBN + c0;
                 if (row < p.m) {
                     float* dst = out + row * p.ldo + col0;
-                    if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                    if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0)) {
+                        // whole 32-byte sectors per lane (256-bit stores)
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                o[e] = fmaf(p.alpha, v[j + e], radd + (p.col_add ? __ldg(p.col_add + col0 + j + e) : 0.f));
+                            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                                         :: "l"(dst + j), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]),
+                                            "f"(o[7]) : "memory");
+                        }
+                    } else if (col0 + 32 <= p.n && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             float4 o;
@@ -443,6 +496,7 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
 
 // set by gemm_packed_topk around its call of gemm_packed_batched (same thread): selects the TOPK epilogue
 static thread_local struct { int k; float* val; int* idx; } g_topk_request = {0, nullptr, nullptr};
+static thread_local struct { char* hi; char* lo; } g_packed_request = {nullptr, nullptr};
 
 int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                         int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
@@ -496,9 +550,12 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
     static PerDeviceFlag configured_on;
     bool& configured = configured_on.get();
     if (!configured) {
-        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RPST_CUDA(cudaFuncSetAttribute(gemm_packed_kernel<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     p.batch = batch; p.a_batch_bytes = a_batch_bytes; p.b_batch_bytes = b_batch_bytes; p.out_batch = out_batch;
@@ -506,16 +563,34 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
     RPST_CHECK_ARG(total_tiles < (1ll << 30), "gemm_packed: too many output tiles");
     int64_t grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;
+    const bool wide = p.k_per_split <= 16;
     if (g_topk_request.k > 0) {
         p.topk = g_topk_request.k; p.cand_val = g_topk_request.val; p.cand_idx = g_topk_request.idx;
-        constexpr int threads = 64 + 128 * kTopkSubs;
-        if (p.topk <= 4) gemm_packed_kernel<4><<<(unsigned)grid, threads, smem, stream>>>(p);
-        else gemm_packed_kernel<8><<<(unsigned)grid, threads, smem, stream>>>(p);
+        if (p.topk <= 4) gemm_packed_kernel<4, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
+        else gemm_packed_kernel<8, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
+    } else if (g_packed_request.hi) {
+        p.pk_hi = g_packed_request.hi; p.pk_lo = g_packed_request.lo; p.pk_ktiles = (int)((n + kTileK - 1) / kTileK);
+        if (wide) gemm_packed_kernel<-1, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
+        else gemm_packed_kernel<-1, false><<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
     } else {
-        gemm_packed_kernel<0><<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
+        if (wide) gemm_packed_kernel<0, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
+        else gemm_packed_kernel<0, false><<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
     }
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
+}
+
+// alpha A.B^T (+ row_add + col_add) written as packed bf16 hi (+ lo) operand tiles [m x n] (K = n) for a following
+// gemm_packed call: the tile buffers must hold packed_operand_bytes(m, n); rows past m / columns past n are zero-filled
+// by the epilogue for every tile it visits (m rounded up to 128 rows is covered, n up to a multiple of 64).
+int gemm_packed_to_tiles(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t m, int64_t n, int64_t k,
+                         int passes, float alpha, void* out_hi, void* out_lo, cudaStream_t stream) {
+    RPST_CHECK_ARG(out_hi != nullptr, "gemm_packed_to_tiles: null output");
+    g_packed_request.hi = static_cast<char*>(out_hi); g_packed_request.lo = static_cast<char*>(out_lo);
+    const int rc = gemm_packed_batched(a_hi, a_lo, b_hi, b_lo, nullptr, m, n, k, n, passes, alpha, nullptr, nullptr, 1, 0, 1, 0, 0,
+                                       0, stream);
+    g_packed_request.hi = nullptr; g_packed_request.lo = nullptr;
+    return rc;
 }
 
 // lists of candidates per row that gemm_packed_topk emits for n columns

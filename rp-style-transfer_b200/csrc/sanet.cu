@@ -17,6 +17,8 @@ namespace rpst {
 size_t packed_operand_bytes(int64_t rows, int64_t k);
 int pack_operand_shift(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
                        const float* row_scale, const float* row_shift, void* hi, void* lo, cudaStream_t stream);
+int gemm_packed_to_tiles(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t m, int64_t n, int64_t k,
+                         int passes, float alpha, void* out_hi, void* out_lo, cudaStream_t stream);
 int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                        const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
@@ -71,6 +73,8 @@ struct RowParams {
     int k_tiles;          // ceil(cols / 64)
     int mode;             // 0 softmax(x); 1 sigmoid(scale*(x-clamp)); 2 softmax(relu(x-clamp))
     float scale;
+    int pre;              // 1: the input row goes through softmax first (modes 1, 2 then act on the probabilities):
+                          //    softmax + clamp of the adaptive attention in ONE pass over the L x L logits
     // blockIdx.y = sample of a group: element strides of in/out32 and clamp, byte stride of the tile buffers
     int64_t in_batch, out_batch, clamp_batch, tile_batch_bytes;
 };
@@ -85,18 +89,28 @@ __global__ void __launch_bounds__(kRowThreads) attn_rows_kernel(RowParams p) {
     if (p.hi) p.hi = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(p.hi) + bi * p.tile_batch_bytes);
     if (p.lo) p.lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(p.lo) + bi * p.tile_batch_bytes);
     const float cl = p.clamp ? __ldg(p.clamp + bi * p.clamp_batch + row) : 0.f;
+    float mx0 = 0.f, inv0 = 1.f;           // first softmax (pre)
+    if (p.pre) {
+        float m = -INFINITY;
+        for (int64_t j = threadIdx.x; j < p.cols; j += kRowThreads) m = fmaxf(m, x[j]);
+        mx0 = block_max(m, red);
+        float s = 0.f;
+        for (int64_t j = threadIdx.x; j < p.cols; j += kRowThreads) s += expf(x[j] - mx0);
+        inv0 = 1.f / block_sum(s, red);
+    }
+    auto load = [&](int64_t j) { const float v = x[j]; return p.pre ? expf(v - mx0) * inv0 : v; };
     float mx = 0.f, inv_sum = 1.f;
     if (p.mode != 1) {
         float m = -INFINITY;
         for (int64_t j = threadIdx.x; j < p.cols; j += kRowThreads) {
-            float v = x[j];
+            float v = load(j);
             if (p.mode == 2) v = fmaxf(v - cl, 0.f);
             m = fmaxf(m, v);
         }
         mx = block_max(m, red);
         float s = 0.f;
         for (int64_t j = threadIdx.x; j < p.cols; j += kRowThreads) {
-            float v = x[j];
+            float v = load(j);
             if (p.mode == 2) v = fmaxf(v - cl, 0.f);
             s += expf(v - mx);
         }
@@ -112,7 +126,7 @@ __global__ void __launch_bounds__(kRowThreads) attn_rows_kernel(RowParams p) {
             const int64_t j = q * 8 + e;
             float v = 0.f;
             if (j < p.cols) {
-                v = x[j];
+                v = load(j);
                 if (p.mode == 0) v = expf(v - mx) * inv_sum;
                 else if (p.mode == 1) v = 1.f / (1.f + expf(-p.scale * (v - cl)));
                 else v = expf(fmaxf(v - cl, 0.f) - mx) * inv_sum;
@@ -154,6 +168,25 @@ __global__ void __launch_bounds__(kRowThreads) attn_rows_reg_kernel(RowParams p)
     for (int j = 0; j < kRowRegVecs; ++j) {
         const int idx = j * kRowThreads + threadIdx.x;
         if (idx < nvec) v[j] = __ldcs(x4 + idx);
+    }
+    if (p.pre) {                           // probabilities first, still in registers
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kRowRegVecs; ++j)
+            if (j * kRowThreads + (int)threadIdx.x < nvec) m = fmaxf(m, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+        const float mx0 = block_max(m, red);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kRowRegVecs; ++j) {
+            if (j * kRowThreads + (int)threadIdx.x < nvec) {
+                v[j].x = expf(v[j].x - mx0); v[j].y = expf(v[j].y - mx0);
+                v[j].z = expf(v[j].z - mx0); v[j].w = expf(v[j].w - mx0);
+                sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            }
+        }
+        const float inv0 = 1.f / block_sum(sum, red);
+#pragma unroll
+        for (int j = 0; j < kRowRegVecs; ++j) { v[j].x *= inv0; v[j].y *= inv0; v[j].z *= inv0; v[j].w *= inv0; }
     }
     float mx = 0.f, inv_sum = 1.f;
     if (p.mode != 1) {
@@ -443,8 +476,9 @@ AdaLayout ada_layout(int64_t c, int64_t lc, int64_t ls, int64_t lh) {
 
 int launch_rows(const float* in, float* out32, void* hi, void* lo, const float* clamp, int64_t rows, int64_t cols,
                 int mode, float scale, cudaStream_t st, int kb = 1, int64_t in_batch = 0, int64_t out_batch = 0,
-                int64_t tile_batch_bytes = 0, int64_t clamp_batch = 0) {
+                int64_t tile_batch_bytes = 0, int64_t clamp_batch = 0, int pre = 0) {
     RowParams p{};
+    p.pre = pre;
     p.in = in; p.out32 = out32; p.hi = static_cast<__nv_bfloat16*>(hi); p.lo = static_cast<__nv_bfloat16*>(lo);
     p.clamp = clamp; p.rows = rows; p.cols = cols; p.k_tiles = (int)((cols + kTileK - 1) / kTileK);
     p.mode = mode; p.scale = scale;
@@ -650,9 +684,8 @@ extern "C" int rpst_sanet_attn_clamped_fwd(const float* f, const float* g, const
     int rc;
     for (int64_t i = 0; i < b; ++i) {
         if ((rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l, s, st))) return rc;
-        if ((rc = launch_rows(s, s, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;                       // P
         if ((rc = launch_rows(s, nullptr, w + l.p_hi, passes == 3 ? w + l.p_lo : nullptr, clamp + i * lc, lc, ls, mode,
-                              scale, st))) return rc;                                                                // S' tiles
+                              scale, st, 1, 0, 0, 0, 0, 1))) return rc;                  // softmax + clamp -> S' tiles, one pass
         if ((rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l, out + i * c * lc, st))) return rc;
     }
     return RPST_OK;
@@ -765,19 +798,28 @@ extern "C" int rpst_sanet_attn_adaptive_fwd(const float* f, const float* g, cons
         if ((rc = channel_norms(style_raw + i * c_raw * ls, c_raw, ls, vec[3], vec[4], vec[5], st))) return rc;
         if ((rc = pack_operand_shift(content_raw + i * c_raw * lc, lc, c_raw, 1, lc, vec[2], nullptr, w + l.a.q_hi, w + l.a.q_lo, st))) return rc;
         if ((rc = pack_operand_shift(style_raw + i * c_raw * ls, ls, c_raw, 1, ls, vec[5], nullptr, w + l.a.k_hi, w + l.a.k_lo, st))) return rc;
-        if ((rc = gemm_packed_splitk(w + l.a.q_hi, w + l.a.q_lo, w + l.a.k_hi, w + l.a.k_lo, aff, lc, ls, c_raw, ls, 3, 1.f,
-                                     nullptr, nullptr, 1, 0, st))) return rc;
-        // f_psi: hidden = aff @ W0^T + b0 (tensor cores, affinity rows packed into the P tile buffers)
-        if ((rc = pack_operand_shift(aff, lc, ls, ls, 1, nullptr, nullptr, w + l.a.p_hi, w + l.a.p_lo, st))) return rc;
+        // the affinity leaves its GEMM as the packed A operand of the f_psi product (rows = content positions, K = style
+        // positions): no fp32 L x L map, no pack pass (a true back-to-back GEMM would need the
+        // [128 x L/16] hidden accumulator next to the affinity tile in TMEM: 1024 + 256 columns of 512 at L = 16384)
+        (void)aff;
+        if ((rc = gemm_packed_to_tiles(w + l.a.q_hi, w + l.a.q_lo, w + l.a.k_hi, w + l.a.k_lo, lc, ls, c_raw, 3, 1.f,
+                                       w + l.a.p_hi, w + l.a.p_lo, st))) return rc;
+        // f_psi: hidden = aff @ W0^T + b0 (tensor cores)
         if ((rc = gemm_packed_splitk(w + l.a.p_hi, w + l.a.p_lo, w + l.w_hi, w + l.w_lo, hidden, lc, lh, ls, lh, 3, 1.f,
                                      nullptr, b0, 1, 0, st))) return rc;
         psi_head_kernel<<<(unsigned)((lc + 7) / 8), 256, 0, st>>>(hidden, w2, b2, lc, lh, mode, from_value, value_interval, clampv);
         RPST_CUDA(cudaGetLastError());
         // plain attention first (claim_before), then the clamped one (claim_after) straight into operand tiles
         if ((rc = scores(f + i * c * lc, g + i * c * ls, c, lc, ls, passes, w, l.a, before, st))) return rc;
+        if (!claim_before) {
+            // softmax and clamp in one pass over the logits (the probabilities are not an output)
+            if ((rc = launch_rows(before, claim_after ? claim_after + i * lc * ls : nullptr, w + l.a.p_hi,
+                                  passes == 3 ? w + l.a.p_lo : nullptr, clampv, lc, ls, mode, scale_value, st, 1, 0, 0, 0, 0, 1))) return rc;
+        } else {
         if ((rc = launch_rows(before, before, nullptr, nullptr, nullptr, lc, ls, 0, 0.f, st))) return rc;
         if ((rc = launch_rows(before, claim_after ? claim_after + i * lc * ls : nullptr, w + l.a.p_hi,
                               passes == 3 ? w + l.a.p_lo : nullptr, clampv, lc, ls, mode, scale_value, st))) return rc;
+        }
         if ((rc = weighted_values(h + i * c * ls, c, lc, ls, passes, w, l.a, out + i * c * lc, st))) return rc;
     }
     return RPST_OK;
