@@ -114,10 +114,10 @@ def config3(dev, peaks, cpu=True, batch=16):
     flops = 3 * 2 * ch * ch * h * w * n            # two covariances + apply counted as full GEMMs (103.1 GFLOP / sample)
     byts = 4 * ch * h * w * 4 * n                  # read c twice, s once, write once
     tp = tensor_pipe_summary().get("wct", {})
-    out = {"workload": "configs[2]: WCT whitening/colouring 16x256x512x512 (closed form, fp64 matrix functions on device)",
+    out = {"workload": "configs[2]: WCT whitening/colouring 16x256x512x512 (closed form, fp64 Newton-Schulz matrix roots on device)",
            "ms_per_sample_fp32grade": ms32 / n, "ms_per_sample_bf16": ms16 / n, "flops_per_sample": flops // n,
            "bytes_per_sample": byts // n,
-           "roofline": {"bound": "mixed: tensor (covariance / apply) + hbm + latency (Jacobi)",
+           "roofline": {"bound": "mixed: tensor + hbm (covariance / apply) + fp64 pipe (matrix roots)",
                         "achieved": flops / (ms32 / 1e3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": flops / (ms32 / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
                         "achieved_bf16": flops / (ms16 / 1e3) / 1e12,

@@ -9,4 +9,8 @@ python tools/one_flash.py 128 1 > gpurun_out/p_flash_plain.log 2>&1 && ncu --met
 python tools/one_wct.py 2 > gpurun_out/p_wct_plain.log 2>&1 && ncu --metrics $M --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches_wct.csv python tools/one_wct.py 2 > gpurun_out/p_wct_ncu.log 2>&1
 python tools/one_flash.py 128 1 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:flash_attn -s 2 -c 2 -o gpurun_out/r02_flash_full python tools/one_flash.py 128 1 > gpurun_out/p_flash_full.log 2>&1
 $B > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:adain_tma -s 15 -c 5 -o gpurun_out/r02_adain_full $B > gpurun_out/p_adain_full.log 2>&1
-tail -2 gpurun_out/p_flash_full.log gpurun_out/p_adain_full.log
+python tools/one_wct.py 2 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:cov_tma -s 2 -c 1 -o gpurun_out/r02_cov_tma_full python tools/one_wct.py 2 > gpurun_out/p_cov_full.log 2>&1
+python tools/one_wct.py 16 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:ns_gemm -s 60 -c 2 -o gpurun_out/r02_ns_gemm_full python tools/one_wct.py 16 > gpurun_out/p_ns_full.log 2>&1
+python tools/one_mrf.py > /dev/null 2>&1 && ncu --metrics $M --clock-control none -c 100 --csv --log-file gpurun_out/r02_launches_mrf.csv python tools/one_mrf.py > gpurun_out/p_mrf_ncu.log 2>&1
+python tools/one_adaptive.py > /dev/null 2>&1 && ncu --metrics $M --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches_adaptive.csv python tools/one_adaptive.py > gpurun_out/p_ada_ncu.log 2>&1
+tail -2 gpurun_out/p_flash_full.log gpurun_out/p_adain_full.log gpurun_out/p_cov_full.log gpurun_out/p_ns_full.log
