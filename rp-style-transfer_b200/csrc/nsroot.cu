@@ -286,17 +286,21 @@ __global__ void ns_plan_kernel(const double* __restrict__ part, int batch, doubl
     nit[b] = k;
 }
 
-// Y_0 = s (A + d I), Z_0 = I
+// Y_0 = s (A + d I); Z_0 = I makes the first step's T and Z products trivial, so they are written here:
+// T_0 = 1.5 I - 0.5 a_0^2 Y_0 and Z_1 = a_0 T_0 (exactly what the products with the identity would give)
 __global__ void __launch_bounds__(256) ns_init_kernel(const double* __restrict__ a, int n, double diag_add,
-                                                      const double* __restrict__ scale, int* __restrict__ nit,
-                                                      double* __restrict__ y0, double* __restrict__ z0) {
+                                                      const double* __restrict__ scale, const double* __restrict__ alpha,
+                                                      double* __restrict__ y0, double* __restrict__ t0, double* __restrict__ z1) {
     const int b = blockIdx.y;
     const size_t off = (size_t)b * n * n;
-    const double s = scale[b];
+    const double s = scale[b], al = alpha[b * kNsMaxIt];
     for (int e = blockIdx.x * 256 + threadIdx.x; e < n * n; e += gridDim.x * 256) {
         const int r = e / n, c = e % n;
-        y0[off + e] = s * (a[off + e] + (r == c ? diag_add : 0.0));
-        z0[off + e] = r == c ? 1.0 : 0.0;
+        const double y = s * (a[off + e] + (r == c ? diag_add : 0.0));
+        const double t = (r == c ? 1.5 : 0.0) - 0.5 * al * al * y;
+        y0[off + e] = y;
+        t0[off + e] = t;
+        z1[off + e] = al * t;
     }
 }
 
@@ -423,7 +427,7 @@ int ns_roots(const double* a, int64_t batch, int n, double diag_add, double lmin
     ns_plan_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>(norm, (int)batch, lmin, maxit, scale, alpha, nit, capped);
     RPST_CUDA(cudaGetLastError());
     const unsigned eb = (unsigned)(((size_t)n * n + 255) / 256 < 64 ? ((size_t)n * n + 255) / 256 : 64);
-    ns_init_kernel<<<dim3(eb, (unsigned)batch), 256, 0, st>>>(a, n, diag_add, scale, nit, y[0], z[0]);
+    ns_init_kernel<<<dim3(eb, (unsigned)batch), 256, 0, st>>>(a, n, diag_add, scale, alpha, y[0], t, z[1]);
     RPST_CUDA(cudaGetLastError());
     int rc;
     GemmArgs g{};
@@ -431,9 +435,11 @@ int ns_roots(const double* a, int64_t batch, int n, double diag_add, double lmin
     g.n = n; g.batch = (int)batch; g.alpha = alpha; g.nit = nit; g.partial = partial;
     for (int it = 0; it < maxit; ++it) {
         g.it = it;
-        g.jobs = 1; g.mode = kStepT;
-        if ((rc = launch_gemm(g, st))) return rc;
-        g.jobs = 2; g.mode = kStepYZ;
+        if (it > 0) {                       // step 0: T_0 and Z_1 came from the init kernel, only Y_1 = a_0 Y_0 T_0 is a product
+            g.jobs = 1; g.mode = kStepT;
+            if ((rc = launch_gemm(g, st))) return rc;
+        }
+        g.jobs = it > 0 ? 2 : 1; g.mode = kStepYZ;
         if ((rc = launch_gemm(g, st))) return rc;
     }
     g.jobs = 1; g.mode = kCheck;
