@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_policy) : "memory");
 }
 
+// 2-D tiled load through a tensor map (CUtensorMap in kernel parameter space): box at element coordinates {c0 (inner), c1}.
+__device__ __forceinline__ void tma_load_box_2d(void* smem_dst, const void* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
 // 1-D bulk copy shared -> global (bulk async-group completion).
 __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t l2_policy) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"

@@ -238,12 +238,6 @@ template <int PARTS> struct CovTmaCfg {
     static constexpr size_t smem = 1024 + (size_t)fstages * kCovBoxBytes + (size_t)ostages * ostage;   // 225 KiB
 };
 
-__device__ __forceinline__ void tma_load_box_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-
 // k-th grid-wide barrier of a cooperative launch (every CTA resident): the counter was zeroed before the launch
 __device__ __forceinline__ void grid_barrier(int* counter, int k) {
     __threadfence();                                   // this thread's global writes before the arrival
@@ -685,6 +679,20 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 }  // namespace
+
+// 2-D fp32 tensor map [outer rows, inner elements] (row pitch = inner * 4 bytes) with boxes of box_outer x box_inner;
+// false when the driver entry point is not available.  `map` points at a CUtensorMap.
+bool tmap_encode_2d_f32(void* map, const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    const cuuint64_t gstride[1] = {(cuuint64_t)inner * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // cov [c,c] fp64 = centred covariance of x [c,hw] (+ diag_add on the diagonal); mean [c] fp32 exact channel means
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,

@@ -20,6 +20,7 @@
 //   warp 1        tcgen05.mma issuer + TMEM owner                        statistics -> fp32 or packed tiles)
 //                                                            warps 6..13  converters
 // Two 256-column TMEM accumulators: the epilogue of item i overlaps the MMAs of item i+1.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -28,6 +29,7 @@
 namespace rpst {
 
 size_t packed_operand_bytes(int64_t rows, int64_t k);
+bool tmap_encode_2d_f32(void* map, const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer);   // cov.cu
 
 namespace {
 
@@ -102,15 +104,31 @@ __device__ __forceinline__ PwItem pw_item(const PwParams& p, int item) {
 // EPI: 0 fp32 output only, 1 packed operand tiles (+ optional fp32), 2 fp32 output + epilogue statistics.
 // Separate instantiations keep each kernel's code small: the warp roles run different code at the same time and
 // a 64 KiB kernel thrashed the instruction cache (12 % of the stalls were "no instruction").
-template <int PARTS, bool VEC, int EPI>
-__global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
+//
+// XTMA (VEC, cin % 64 == 0, EPI 0 / 1): the fp32 x tile of a k-block ([64 channels x 128 positions], 32 KiB) comes in by
+// 2-D tensor-map TMA into a two-deep ring and the converter warps read it from shared memory.  The register-staged
+// converters (three buffers of 8 float4 per thread) were bound by global-load latency: ncu long_scoreboard 45 %,
+// 3.1 TB/s over read + write.  Shared memory then holds ONE A stage (converting a k-block takes a quarter of its MMA
+// time, and convert + MMA in series still fit under the k-block's HBM time), the B ring and the x ring: 224 KiB.
+template <int PARTS, bool VEC, int EPI, bool XTMA>
+__global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_constant__ CUtensorMap xmap, PwParams p) {
     // stage: A hi [128 pos x 64 ch] 16 KiB (+ lo 16 KiB), B hi [256 out x 64 ch] 32 KiB (+ lo 32 KiB)
     constexpr uint32_t kA = kTileBytes, kB = 2 * kTileBytes;
     constexpr uint32_t kStage = PARTS * (kA + kB);
     constexpr int NST = PARTS == 2 ? 2 : 4;
+    constexpr int NX = 2;
+    constexpr uint32_t kXBox = 64 * 128 * sizeof(float);        // 32 KiB
+    static_assert(!XTMA || (VEC && EPI != 2), "XTMA: vector path, no epilogue statistics (their static arrays need the room)");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // XTMA layout: [A (PARTS * kA)][B stage 0 .. NST-1 (PARTS * kB each)][x box 0 .. NX-1]
+    unsigned char* const xring = smem + PARTS * kA + (size_t)NST * PARTS * kB;
+    auto a_stage = [&](int s) -> unsigned char* { return XTMA ? smem : smem + (size_t)s * kStage; };
+    auto b_stage = [&](int s) -> unsigned char* {
+        return XTMA ? smem + PARTS * kA + (size_t)s * PARTS * kB : smem + (size_t)s * kStage + PARTS * kA;
+    };
     __shared__ uint64_t full_a[NST], full_b[NST], empty[NST], acc_full[2], acc_empty[2];
+    __shared__ uint64_t xfull[NX], xempty[NX], a_empty;
     __shared__ uint32_t tmem_slot;
     __shared__ float stat_tile[EPI == 2 ? 4 * 32 * 33 : 1];
     __shared__ float stat_acc[EPI == 2 ? 4 * kPwMaxC * 2 : 1];   // running per-warp column sums of the current sample
@@ -127,6 +145,11 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], 4);
         }
+        for (int b = 0; b < NX; ++b) {
+            mbar_init(&xfull[b], 1);
+            mbar_init(&xempty[b], kPwConvWarps);
+        }
+        mbar_init(&a_empty, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -143,9 +166,15 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
                 const PwItem w = pw_item(p, item);
                 const int n_sub = w.ncol / 128;
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
+                    if (XTMA) {                              // x box of this k-block: positions 128 t .., channel rows sample * cin + 64 kb ..
+                        const uint32_t xs = it % NX;
+                        mbar_wait(&xempty[xs], ((it / NX) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&xfull[xs], kXBox);
+                        tma_load_box_2d(xring + (size_t)xs * kXBox, &xmap, w.t * 128, w.sample * p.cin + kb * 64, &xfull[xs]);
+                    }
                     const int s = it % NST;
                     mbar_wait(&empty[s], ((it / NST) & 1u) ^ 1u);
-                    unsigned char* st = smem + (size_t)s * kStage;
+                    unsigned char* st = b_stage(s) - PARTS * kA;
                     mbar_arrive_expect_tx(&full_b[s], (uint32_t)(PARTS * n_sub) * kTileBytes);
                     for (int part = 0; part < PARTS; ++part)
                         for (int sub = 0; sub < n_sub; ++sub)
@@ -169,11 +198,12 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
                 const uint32_t d = tmem_base + (uint32_t)(buf * 256);
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const int s = it % NST;
-                    mbar_wait(&full_a[s], (it / NST) & 1u);
+                    if (XTMA) mbar_wait(&full_a[0], it & 1u);
+                    else mbar_wait(&full_a[s], (it / NST) & 1u);
                     mbar_wait(&full_b[s], (it / NST) & 1u);
                     tcgen05_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)s * kStage), a_lo = a_hi + kA;
-                    const uint32_t b_hi = a_hi + PARTS * kA, b_lo = b_hi + kB;
+                    const uint32_t a_hi = smem_u32(a_stage(s)), a_lo = a_hi + kA;
+                    const uint32_t b_hi = smem_u32(b_stage(s)), b_lo = b_hi + kB;
 #pragma unroll
                     for (int k = 0; k < kTileK / kUmmaK; ++k) {
                         const uint32_t ko = k * kUmmaK * 2;            // B: 16 channels = 32 bytes along its K-major rows
@@ -185,6 +215,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
                         }
                     }
                     umma_commit(&empty[s]);
+                    if (XTMA) umma_commit(&a_empty);                 // the single A stage may be rewritten
                     if (kb == p.kb - 1) umma_commit(&acc_full[buf]);
                 }
             }
@@ -315,6 +346,48 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
         // lane -> positions 4 lane .. 4 lane + 3 of the tile: MN-atom lane / 16, 16-byte chunk (lane % 16) / 2, half lane & 1
         const uint32_t lane_off = (uint32_t)(lane >> 4) * kPwLBO + ((uint32_t)lane & 1u) * 8u;
         const uint32_t chunk = ((uint32_t)lane & 15u) >> 1;
+        if (XTMA) {
+            uint32_t u = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const PwItem w = pw_item(p, item);
+                for (int kb = 0; kb < p.kb; ++kb, ++u) {
+                    const uint32_t xs = u % NX;
+                    mbar_wait(&xfull[xs], (u / NX) & 1u);
+                    const unsigned char* box = xring + (size_t)xs * kXBox + (size_t)(cw * 8) * 512 + lane * 16;
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(box + j * 512);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&xempty[xs]);            // the box may be overwritten
+                    const int sidx = w.sample * p.cin + kb * 64 + cw * 8;
+                    float sb[8], ml[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        sb[j] = p.sub ? __ldg(p.sub + sidx + j) : 0.f;
+                        ml[j] = p.mul ? __ldg(p.mul + sidx + j) : 1.f;
+                    }
+                    mbar_wait(&a_empty, (u & 1u) ^ 1u);                  // the MMAs of the previous k-block have read A
+                    unsigned char* a_hi = smem + (size_t)cw * kPwSBO + lane_off;
+                    unsigned char* a_lo = a_hi + kA;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = (v[j].x - sb[j]) * ml[j], b = (v[j].y - sb[j]) * ml[j];
+                        const float c2 = (v[j].z - sb[j]) * ml[j], d = (v[j].w - sb[j]) * ml[j];
+                        const uint32_t off = (uint32_t)j * 128u + ((chunk ^ (uint32_t)j) << 4);
+                        const uint32_t h01 = pw_pack_bf16x2(a, b), h23 = pw_pack_bf16x2(c2, d);
+                        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
+                        if (PARTS == 2) {
+                            const uint32_t l01 = pw_pack_bf16x2(a - __uint_as_float(h01 << 16), b - __uint_as_float(h01 & 0xffff0000u));
+                            const uint32_t l23 = pw_pack_bf16x2(c2 - __uint_as_float(h23 << 16), d - __uint_as_float(h23 & 0xffff0000u));
+                            *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l01, l23);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_a[0]);
+                }
+            }
+        } else {
         // Work units (item, k-block) in issue order; three register buffers rotate so that the loads of two units are in
         // flight while a third is converted (load-latency bound: 8 loads per thread in flight gave 1.7 TB/s).  Two cursors
         // (load / convert) walk the unit sequence incrementally: no divisions in the loop.
@@ -420,6 +493,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(PwParams p) {
             load_unit(v1, ld);
             conv_unit(v2, cv);
         }
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -449,6 +523,8 @@ __global__ void __launch_bounds__(128) pw_stats_finalize_kernel(const float* __r
 }
 
 }  // namespace
+
+int64_t g_pw_x_tma = 1;   // tuning knob "pw_x_tma": 1 = x tiles by tensor-map TMA when the shape allows, 0 = register-staged converters
 
 bool pw_conv_supported(int64_t cin, int64_t cout) { return cin >= 1 && cin <= kPwMaxC && cout >= 1 && cout <= kPwMaxC; }
 
@@ -482,30 +558,38 @@ int pw_conv(const PwArgs& a, cudaStream_t st) {
     const int64_t items = (int64_t)p.batch * p.tiles * p.col_tiles;
     if (items == 0) return RPST_OK;
     RPST_CHECK_ARG(items < (1ll << 30), "conv1x1: too many work items");
-    constexpr size_t smem = 1024 + 2 * 2 * (kTileBytes + 2 * kTileBytes);   // 193 KiB for every instantiation
+    constexpr size_t smem = 1024 + 2 * 2 * (kTileBytes + 2 * kTileBytes);   // 193 KiB for every register-staged instantiation
+    constexpr size_t smem_x = 1024 + 2 * kTileBytes + 2 * 2 * 2 * kTileBytes + 2 * 64 * 128 * sizeof(float);   // 225 KiB (XTMA)
     const bool vec = p.vec_ok && a.cin % 8 == 0;
     const int epi = p.out_hi ? 1 : (p.stats ? 2 : 0);
     RPST_CHECK_ARG(!(p.out_hi && p.stats), "conv1x1: packed output and epilogue statistics are separate modes");
     int grid = sm_count();
     if (grid > items) grid = (int)items;
-    static PerDeviceFlag configured_on[12];
-#define RPST_PW_CASE(PARTS, VEC, EPI)                                                                                     \
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    const bool xtma = g_pw_x_tma && vec && epi != 2 && a.cin % 64 == 0 && a.hw < (1ll << 31) - 128 &&
+                      a.b * a.cin < (1ll << 31) && tmap_encode_2d_f32(&xmap, a.x, (uint64_t)a.hw, (uint64_t)(a.b * a.cin), 128, 64);
+    static PerDeviceFlag configured_on[24];
+#define RPST_PW_CASE(PARTS, VEC, EPI, XT)                                                                                 \
     {                                                                                                                     \
-        bool& configured = configured_on[((PARTS) - 1) * 6 + (VEC) * 3 + (EPI)].get();                                    \
+        bool& configured = configured_on[(((PARTS) - 1) * 6 + (VEC) * 3 + (EPI)) * 2 + (XT)].get();                       \
         if (!configured) {                                                                                                \
-            RPST_CUDA(cudaFuncSetAttribute(pw_conv_kernel<PARTS, VEC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                           (int)smem));                                                                   \
+            RPST_CUDA(cudaFuncSetAttribute(pw_conv_kernel<PARTS, VEC, EPI, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)((XT) ? smem_x : smem)));                                                 \
             configured = true;                                                                                            \
         }                                                                                                                 \
-        pw_conv_kernel<PARTS, VEC, EPI><<<grid, kPwThreads, smem, st>>>(p);                                               \
+        pw_conv_kernel<PARTS, VEC, EPI, XT><<<grid, kPwThreads, (XT) ? smem_x : smem, st>>>(xmap, p);                     \
     }
 #define RPST_PW_EPI(PARTS, VEC)                                                    \
-    if (epi == 0) RPST_PW_CASE(PARTS, VEC, 0) else if (epi == 1) RPST_PW_CASE(PARTS, VEC, 1) else RPST_PW_CASE(PARTS, VEC, 2)
+    if (epi == 0) RPST_PW_CASE(PARTS, VEC, 0, false) else if (epi == 1) RPST_PW_CASE(PARTS, VEC, 1, false) else RPST_PW_CASE(PARTS, VEC, 2, false)
+#define RPST_PW_EPI_X(PARTS)                                                       \
+    if (epi == 0) RPST_PW_CASE(PARTS, true, 0, true) else RPST_PW_CASE(PARTS, true, 1, true)
     if (a.passes == 3) {
-        if (vec) { RPST_PW_EPI(2, true) } else { RPST_PW_EPI(2, false) }
+        if (xtma) { RPST_PW_EPI_X(2) } else if (vec) { RPST_PW_EPI(2, true) } else { RPST_PW_EPI(2, false) }
     } else {
-        if (vec) { RPST_PW_EPI(1, true) } else { RPST_PW_EPI(1, false) }
+        if (xtma) { RPST_PW_EPI_X(1) } else if (vec) { RPST_PW_EPI(1, true) } else { RPST_PW_EPI(1, false) }
     }
+#undef RPST_PW_EPI_X
 #undef RPST_PW_EPI
 #undef RPST_PW_CASE
     RPST_CUDA(cudaGetLastError());
