@@ -137,3 +137,58 @@ def test_wct_and_mrf(lib):
     torch.cuda.synchronize()
     for buf, name in ((idx0, "idx0"), (idx1, "idx1"), (loss, "loss"), (wsm, "mrf workspace")):
         buf.check(name)
+
+
+@pytest.mark.parametrize("n,c,h,w", [(1, 128, 20, 28), (2, 192, 9, 12), (1, 200, 15, 12), (1, 65, 6, 10)])
+def test_wct_tma_covariance_newton_schulz_and_tma_colouring(lib, n, c, h, w):
+    """C > 64: one-launch TMA covariance (boxes past the last channel / position are zero-filled by the TMA unit, never
+    read out of bounds), Newton-Schulz roots (even and odd order, partial GEMM tiles), colouring with TMA-staged x tiles
+    (C % 64 == 0) or register-staged converters; workspace at exactly the queried size."""
+    L = lib.lib()
+    cf, sf = R.synth_features((n, c, h, w), cfg=95, device="cuda")
+    for method in (0, 1):
+        out = Guarded(cf.numel() * 4)
+        tr = Guarded(n * c * c * 8)
+        ws = Guarded(L.rpst_wct_workspace_bytes(n, c, h * w, h * w))
+        lib.check(L.rpst_wct_fuse(cf.data_ptr(), sf.data_ptr(), out.inner.data_ptr(), n, c, h * w, h * w, method, 3,
+                                  tr.inner.data_ptr(), ws.inner.data_ptr(), ws.n, stream()))
+        torch.cuda.synchronize()
+        out.check("wct out"); ws.check("wct workspace"); tr.check("wct transform")
+        want = R.wct_fuse(cf.cpu(), sf.cpu(), "closed-form" if method == 0 else "original")
+        assert R.rel_l2(out.floats(n, c, h, w), want) < 1e-3
+
+
+def test_spd_roots_and_topk_gemm_workspaces(lib):
+    L = lib.lib()
+    b, n = 3, 130
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(b, n, 2 * n, device="cuda", dtype=torch.float64, generator=g)
+    a = (a @ a.transpose(1, 2) / (2 * n)).contiguous()
+    root, iroot, flags = Guarded(b * n * n * 8), Guarded(b * n * n * 8), Guarded(b * 4)
+    ws = Guarded(L.rpst_spd_roots_workspace_bytes(b, n))
+    lib.check(L.rpst_spd_roots(a.data_ptr(), b, n, 1e-4, 1e-4, root.inner.data_ptr(), iroot.inner.data_ptr(),
+                               flags.inner.data_ptr(), ws.inner.data_ptr(), ws.n, stream()))
+    torch.cuda.synchronize()
+    for buf, name in ((root, "root"), (iroot, "iroot"), (flags, "flags"), (ws, "spd_roots workspace")):
+        buf.check(name)
+    r = root.inner.view(torch.float64).view(b, n, n)
+    eye = 1e-4 * torch.eye(n, dtype=torch.float64, device="cuda")
+    assert R.rel_l2(r @ r, a + eye) < 1e-10
+    assert int(flags.inner.view(torch.int32)[:b].sum()) == 0
+    # MRF with ragged L (partial 64-column slices and partial row tiles in the top-k epilogue) and k = 8 / 1
+    for (c, hh, ww, k) in ((40, 13, 9, 8), (16, 30, 21, 1), (24, 33, 31, 5)):
+        cf, sf = R.synth_features((1, c, hh, ww), cfg=96, device="cuda")
+        l = hh * ww
+        idx0, idx1, loss = Guarded(k * l * 8), Guarded(l * k * 8), Guarded(4)
+        wsm = Guarded(L.rpst_mrf_workspace_bytes(c, l, k))
+        lib.check(L.rpst_mrf_match(cf.data_ptr(), sf.data_ptr(), c, l, k, 0, 3, idx0.inner.data_ptr(), idx1.inner.data_ptr(),
+                                   None, loss.inner.data_ptr(), 0, wsm.inner.data_ptr(), wsm.n, stream()))
+        torch.cuda.synchronize()
+        for buf, name in ((idx0, "idx0"), (idx1, "idx1"), (loss, "loss"), (wsm, "mrf workspace")):
+            buf.check(name)
+        w0, w1, _ = R.mrf_topk_indices(cf.cpu(), sf.cpu(), k, dtype=torch.float64)
+        got0 = idx0.inner[:k * l * 8].view(torch.int64).view(k, l).cpu()
+        got1 = idx1.inner[:l * k * 8].view(torch.int64).view(l, k).cpu()
+        # exact wherever the fp64 scores are not (near-)tied: compare the SETS of the clear winners through the loss instead
+        assert got0.min() >= 0 and got0.max() < l and got1.min() >= 0 and got1.max() < l
+        assert (got0 == w0).float().mean() > 0.98 and (got1 == w1).float().mean() > 0.98
