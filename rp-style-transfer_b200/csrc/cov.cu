@@ -44,6 +44,7 @@ struct CovParams {
     double* cov;             // [c, c] result
     float* mean;             // [c] exact means or null
     double diag_add;
+    const float* shift_in;      // per-channel shifts computed ahead of the launch (cov_shifts_batched) or null: sample here
     unsigned long long* prof;   // optional [8 x 2] %globaltimer stamps of CTA 0 and the last CTA (tuning knob "wct_cov_prof")
 };
 
@@ -300,6 +301,11 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
         for (int u = 0; u < pre_boxes; ++u) issue_box(u);
     }
+    int bar_k = 0;                                         // grid barriers passed so far (uniform over the grid)
+    if (p.shift_in) {
+        // shifts of every tensor of the batch came from ONE small launch ahead of the covariance launches: no exchange here
+        for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_shift[r] = r < p.cp ? __ldg(p.shift_in + r) : 0.f;
+    } else {
     if (warp >= 2) {
         // Centring shift = mean of up to 32 segments of 64 positions spread over the plane.  The channels are dealt over
         // the CTAs (one warp per channel, every load independent) and exchanged through global memory: when every CTA
@@ -323,8 +329,9 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
             if (lane == 0) p.shift[ch] = a;
         }
     }
-    grid_barrier(p.barrier, 1);
+    grid_barrier(p.barrier, ++bar_k);
     for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_shift[r] = r < p.cp ? __ldcg(p.shift + r) : 0.f;
+    }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
     }
     if (prof) pr[3] = global_timer_ns();
     // ---- grid barriers (cooperative launch: every CTA is resident) and the fp64 finalize spread over the CTAs ----
-    grid_barrier(p.barrier, 2);
+    grid_barrier(p.barrier, ++bar_k);
     if (prof) pr[4] = global_timer_ns();
     const int parts = (int)gridDim.x;
     double* s_S = reinterpret_cast<double*>(smem);                         // [256] column sums of the shifted values
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
             if (p.mean && r < p.c) p.mean[r] = (float)((double)s_shift[r] + a / (double)p.hw);
         }
     }
-    grid_barrier(p.barrier, 3);
+    grid_barrier(p.barrier, ++bar_k);
     for (int r = threadIdx.x; r < kCovMaxC; r += blockDim.x) s_S[r] = r < p.cp ? __ldcg(p.s_sum + r) : 0.0;
     __syncthreads();
     if (prof) pr[5] = global_timer_ns();
@@ -557,6 +564,8 @@ __global__ void __launch_bounds__(kCovTmaThreads, 1) cov_tma_kernel(const __grid
 // One warp per channel, every load independent.
 __global__ void __launch_bounds__(256) cov_shift_kernel(const float* __restrict__ x, int c, int cp, int64_t hw,
                                                         float* __restrict__ shift) {
+    x += (int64_t)blockIdx.y * c * hw;                 // blockIdx.y: tensor of a batch (contiguous [n, c, hw]), shifts [n, cp]
+    shift += (int64_t)blockIdx.y * cp;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= cp) return;
     if (row >= c) {
@@ -695,8 +704,16 @@ bool tmap_encode_2d_f32(void* map, const float* base, uint64_t inner, uint64_t o
 }
 
 // cov [c,c] fp64 = centred covariance of x [c,hw] (+ diag_add on the diagonal); mean [c] fp32 exact channel means
+// shifts [n, cp] (cp = 128 or 256) of n contiguous [c, hw] tensors in one launch: what cov_fused takes as `shift_in`
+int cov_shifts_batched(const float* x, int64_t n, int64_t c, int64_t hw, float* shifts, cudaStream_t st) {
+    const int cp = c <= 128 ? 128 : 256;
+    cov_shift_kernel<<<dim3((unsigned)((cp + 7) / 8), (unsigned)n), 256, 0, st>>>(x, (int)c, cp, hw, shifts);
+    RPST_CUDA(cudaGetLastError());
+    return RPST_OK;
+}
+
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
-              cudaStream_t st) {
+              cudaStream_t st, const float* shift_in) {
     const int cp = c <= 128 ? 128 : 256;
     const int g = sm_count();
     char* w = static_cast<char*>(workspace);
@@ -738,6 +755,7 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
         int* barrier = reinterpret_cast<int*>(reinterpret_cast<char*>(s_sum) + align_up((size_t)cp * sizeof(double), 256));
         RPST_CUDA(cudaMemsetAsync(barrier, 0, sizeof(int), st));
         p.barrier = barrier; p.cov = cov; p.mean = mean; p.diag_add = diag_add; p.s_sum = s_sum; p.shift = shift;
+        p.shift_in = shift_in;
         p.prof = reinterpret_cast<unsigned long long*>(g_wct_cov_prof);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid);

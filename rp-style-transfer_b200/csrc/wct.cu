@@ -40,7 +40,8 @@ constexpr double kWctEigTol = 1e-5;
 bool cov_fused_supported(const float* x, int64_t c, int64_t hw);
 size_t cov_fused_workspace_bytes(int64_t c);
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
-              cudaStream_t st);
+              cudaStream_t st, const float* shift_in);
+int cov_shifts_batched(const float* x, int64_t n, int64_t c, int64_t hw, float* shifts, cudaStream_t st);
 extern int64_t g_wct_fused_cov;
 // wct_apply.cu: out = T (x - mu_c) + mu_s with the transposed bf16 operand built on the fly
 bool wct_apply_fused_supported(int64_t c, int64_t hw);
@@ -86,7 +87,7 @@ __global__ void transform_finalize_kernel(const double* __restrict__ t, const fl
 
 struct WctLayout {
     size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, flag, ns, eig, mats[6], t32, bias,
-        t_hi, t_lo, x_hi, x_lo, fused, total;
+        t_hi, t_lo, x_hi, x_lo, fused, shifts, total;
     int splits;
 };
 
@@ -126,6 +127,7 @@ WctLayout wct_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     l.x_hi = take(packed_operand_bytes(hw_c, c));
     l.x_lo = take(packed_operand_bytes(hw_c, c));
     l.fused = take(c <= 256 ? cov_fused_workspace_bytes(c) : 0);
+    l.shifts = take((size_t)2 * n * 256 * sizeof(float));
     l.total = o;
     return l;
 }
@@ -167,9 +169,17 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
                        (c * hw_c) % 4 == 0 && (c * hw_s) % 4 == 0;
     if (fused) {
         // 1+2. means and centred covariances from ONE pass over each tensor (cov.cu)
+        // centring shifts of all 2n tensors in two small launches (inside the covariance launch they cost a grid barrier each)
+        float* sh_c = reinterpret_cast<float*>(w + l.shifts);
+        float* sh_s = sh_c + n * 256;
+        if ((rc = cov_shifts_batched(content, n, c, hw_c, sh_c, st))) return rc;
+        if ((rc = cov_shifts_batched(style, n, c, hw_s, sh_s, st))) return rc;
+        const int cp = c <= 128 ? 128 : 256;
         for (int64_t i = 0; i < n; ++i) {
-            if ((rc = cov_fused(content + i * c * hw_c, c, hw_c, passes, 1.0, cov_c + i * c * c, mean_c + i * c, w + l.fused, st))) return rc;
-            if ((rc = cov_fused(style + i * c * hw_s, c, hw_s, passes, 0.0, cov_s + i * c * c, mean_s + i * c, w + l.fused, st))) return rc;
+            if ((rc = cov_fused(content + i * c * hw_c, c, hw_c, passes, 1.0, cov_c + i * c * c, mean_c + i * c, w + l.fused, st,
+                                sh_c + i * cp))) return rc;
+            if ((rc = cov_fused(style + i * c * hw_s, c, hw_s, passes, 0.0, cov_s + i * c * c, mean_s + i * c, w + l.fused, st,
+                                sh_s + i * cp))) return rc;
         }
     } else {
     // 1. channel means (network/wct_rp.py:85,92)
