@@ -53,7 +53,16 @@ RPST_API const char* rpst_last_error(void);
  *                      0 disables the watchdog (debuggers, MPS time-slicing, compute-sanitizer); applies to all devices
  *   "attn_flash"       1 (default): C = 512 attention runs as one flash-style kernel when the shape allows; 0: GEMM -> rows -> GEMM
  *   "wct_fused_cov" / "wct_fused_apply"   1 (default): fused convert+centre+SYRK covariance / fused colouring apply (C <= 256)
- *   "attn_flash_prof"  device pointer to 32 x uint64 cycle counters filled by the flash kernel's pair 0 (0 = off) */
+ *   "attn_flash_prof"  device pointer to 32 x uint64 cycle counters filled by the flash kernel's pair 0 (0 = off)
+ *   "wct_cov_tma"      1 (default): covariance as ONE cooperative launch with TMA-staged fp32 boxes; 0: register-staged kernel
+ *                      + separate shift / row-sum / finalize launches
+ *   "wct_roots_ns"     1 (default): matrix roots by Newton-Schulz for C > 64, Jacobi for the matrices it flags; 0: Jacobi only;
+ *                      2: Newton-Schulz with every matrix flagged (exercises the predicated Jacobi path)
+ *   "wct_ns_flagged"   (read only) matrices handed to the Jacobi path by the Newton-Schulz acceptance test since load
+ *   "pw_x_tma"         1 (default): pointwise convolution stages its fp32 input tiles by tensor-map TMA when the shape
+ *                      allows (C_in % 64 == 0, 16-byte aligned rows); 0: register-staged converters
+ *   "eig_wide"         Jacobi block width: -1 auto, 0 / 1 force 16- / 32-column blocks
+ *   "wct_cov_prof"     device pointer to 16 x uint64 %globaltimer stamps of the covariance launch (0 = off) */
 RPST_API int rpst_set_tuning(const char* name, int64_t value);
 RPST_API int64_t rpst_get_tuning(const char* name);
 

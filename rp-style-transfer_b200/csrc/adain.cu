@@ -1492,6 +1492,7 @@ extern int64_t g_eig_wide;          // eig.cu
 extern int64_t g_wct_cov_tma;       // cov.cu
 extern int64_t g_wct_cov_prof;      // cov.cu
 extern int64_t g_pw_x_tma;          // pwconv.cu
+extern int64_t g_ns_dmma;           // nsroot.cu
 extern int64_t g_wct_roots_ns;      // nsroot.cu
 int64_t g_wct_fused_apply = 1;  // 1: WCT colouring through the fused transpose+convert+GEMM kernel (wct_apply.cu), C <= 256
 int64_t g_wct_fused_cov = 1;    // 1: WCT covariances through the fused convert+centre+SYRK kernel (cov.cu) when the shape allows
@@ -1518,6 +1519,7 @@ int set_adain_tuning(const char* name, int64_t v, bool set, int64_t* out) {
     else if (!strcmp(name, "wct_cov_tma")) slot = &g_wct_cov_tma;
     else if (!strcmp(name, "wct_cov_prof")) slot = &g_wct_cov_prof;
     else if (!strcmp(name, "pw_x_tma")) slot = &g_pw_x_tma;
+    else if (!strcmp(name, "ns_dmma")) slot = &g_ns_dmma;
     else if (!strcmp(name, "wct_roots_ns")) slot = &g_wct_roots_ns;
     else if (!strcmp(name, "wct_fused_cov")) slot = &g_wct_fused_cov;
     else if (!strcmp(name, "wct_fused_apply")) slot = &g_wct_fused_apply;

@@ -21,6 +21,9 @@
 #include "common.cuh"
 
 namespace rpst {
+
+int64_t g_ns_dmma = 1;   // tuning knob "ns_dmma": 1 = fp64 tensor-core products (mma.sync f64) for even orders, 0 = DFMA kernel
+
 namespace {
 
 constexpr int kNsMaxIt = 24;
@@ -353,9 +356,149 @@ NsLayout ns_layout(int64_t batch, int n) {
     return l;
 }
 
+// ---- the same products on the fp64 tensor-core path (mma.sync.m8n8k4.f64) --------------------------------------------
+// The DFMA kernel above stops at 55-58 % of the fp64 pipe with one CTA per SM or two (three 64-bit register operands per
+// FMA); a DMMA carries 8 FMAs per thread on one A and one B register.  Even n only (cp.async tiles).  CTA tile 128 x 64,
+// warp tile 32 x 32 = 4 x 4 m8n8 tiles, k-tiles of 16 = four k4 steps.  Shared-memory strides (A rows 20 doubles, B rows
+// 68) put the 16 lanes of a half warp on 16 different bank pairs for both fragment loads.
+constexpr int kDA = 20, kDB = 68;
+constexpr int kDStage = kGM * kDA + kGK * kDB;             // 3648 doubles = 29184 bytes
+constexpr size_t kDmmaSmem = 2 * (size_t)kDStage * sizeof(double);
+
+__device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGThreads, 2) ns_gemm_dmma_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) unsigned char dmma_smem[];
+    double* tile_smem = reinterpret_cast<double*>(dmma_smem);
+    const int job = (int)blockIdx.z / g.batch, smp = (int)blockIdx.z % g.batch;
+    const int n = g.n;
+    double alpha = 1.0;
+    int par = 0;
+    if (MODE == kStepT || MODE == kStepYZ) {
+        if (g.it >= g.nit[smp]) return;
+        alpha = g.alpha[smp * kNsMaxIt + g.it];
+        par = g.it & 1;
+    } else if (MODE == kCheck) {
+        par = g.nit[smp] & 1;
+    }
+    const size_t off = (size_t)smp * n * n;
+    const double *A, *B;
+    double* C = nullptr;
+    if (MODE == kPlain) {
+        A = g.a + off; B = g.b + off; C = g.c + off;
+    } else if (MODE == kStepT) {
+        A = g.z[par] + off; B = g.y[par] + off; C = g.t + off;
+    } else if (MODE == kStepYZ) {
+        if (job == 0) { A = g.y[par] + off; B = g.t + off; C = g.y[par ^ 1] + off; }
+        else          { A = g.t + off; B = g.z[par] + off; C = g.z[par ^ 1] + off; }
+    } else {
+        A = g.z[par] + off; B = g.y[par] + off;
+    }
+    const int i0 = blockIdx.y * kGM, j0 = blockIdx.x * kGN;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int gid = lane >> 2, tig = lane & 3;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    auto issue = [&](int k0, int stage) {
+        double* as = tile_smem + stage * kDStage;
+        double* bs = as + kGM * kDA;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ch = threadIdx.x + q * kGThreads, m = ch >> 3, k = (ch & 7) * 2;
+            const bool ok = i0 + m < n && k0 + k < n;
+            cp_async_16(as + m * kDA + k, ok ? A + (size_t)(i0 + m) * n + k0 + k : A, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int ch = threadIdx.x + q * kGThreads, k = ch >> 5, c = (ch & 31) * 2;
+            const bool ok = k0 + k < n && j0 + c < n;
+            cp_async_16(bs + k * kDB + c, ok ? B + (size_t)(k0 + k) * n + j0 + c : B, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+    const int nk = (n + kGK - 1) / kGK;
+    issue(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        if (kt + 1 < nk) { issue((kt + 1) * kGK, (kt + 1) & 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* as = tile_smem + (kt & 1) * kDStage + (32 * wm + gid) * kDA + tig;
+        const double* bs = tile_smem + (kt & 1) * kDStage + kGM * kDA + tig * kDB + 32 * wn + gid;
+#pragma unroll
+        for (int kk = 0; kk < kGK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = as[(8 * i) * kDA + kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = bs[kk * kDB + 8 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+
+    double mul = 1.0, diag = 0.0;
+    if (MODE == kStepT) { mul = -0.5 * alpha * alpha; diag = 1.5; }
+    else if (MODE == kStepYZ) mul = alpha;
+    double sq = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i0 + 32 * wm + 8 * i + gid;
+        if (r >= n) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = j0 + 32 * wn + 8 * j + 2 * tig;
+            const double v0 = acc[i][j][0] * mul + (r == c ? diag : 0.0);
+            const double v1 = acc[i][j][1] * mul + (r == c + 1 ? diag : 0.0);
+            if (MODE == kCheck) {
+                if (c < n) { const double d = v0 - (r == c ? 1.0 : 0.0); sq = fma(d, d, sq); }
+                if (c + 1 < n) { const double d = v1 - (r == c + 1 ? 1.0 : 0.0); sq = fma(d, d, sq); }
+                continue;
+            }
+            if (c + 1 < n) *reinterpret_cast<double2*>(C + (size_t)r * n + c) = make_double2(v0, v1);   // n even, c even
+            else if (c < n) C[(size_t)r * n + c] = v0;
+        }
+    }
+    if (MODE == kCheck) {
+        const double t = block_sum_256(sq, tile_smem);
+        if (threadIdx.x == 0) g.partial[(size_t)smp * gridDim.x * gridDim.y + blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
 int launch_gemm(GemmArgs g, cudaStream_t st) {
     dim3 grid((unsigned)((g.n + kGN - 1) / kGN), (unsigned)((g.n + kGM - 1) / kGM), (unsigned)(g.jobs * g.batch));
     const bool even = (g.n & 1) == 0;
+    if (even && g_ns_dmma) {
+        static PerDeviceFlag configured_on;
+        bool& configured = configured_on.get();
+        if (!configured) {
+            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
+            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kStepT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
+            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kStepYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
+            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kCheck>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
+            configured = true;
+        }
+        switch (g.mode) {
+            case kPlain: ns_gemm_dmma_kernel<kPlain><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+            case kStepT: ns_gemm_dmma_kernel<kStepT><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+            case kStepYZ: ns_gemm_dmma_kernel<kStepYZ><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+            default: ns_gemm_dmma_kernel<kCheck><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+        }
+        RPST_CUDA(cudaGetLastError());
+        return RPST_OK;
+    }
     switch (g.mode) {
         case kPlain:
             if (even) ns_gemm_kernel<kPlain, true><<<grid, kGThreads, 0, st>>>(g);
