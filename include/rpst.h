@@ -61,6 +61,7 @@ RPST_API const char* rpst_last_error(void);
  *   "wct_ns_flagged"   (read only) matrices handed to the Jacobi path by the Newton-Schulz acceptance test since load
  *   "pw_x_tma"         1 (default): pointwise convolution stages its fp32 input tiles by tensor-map TMA when the shape
  *                      allows (C_in % 64 == 0, 16-byte aligned rows); 0: register-staged converters
+ *   "ns_dmma"          1 (default): Newton-Schulz products on fp64 tensor-core MMAs (even orders); 0: DFMA kernel
  *   "eig_wide"         Jacobi block width: -1 auto, 0 / 1 force 16- / 32-column blocks
  *   "wct_cov_prof"     device pointer to 16 x uint64 %globaltimer stamps of the covariance launch (0 = off) */
 RPST_API int rpst_set_tuning(const char* name, int64_t value);
