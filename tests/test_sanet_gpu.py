@@ -248,3 +248,27 @@ def test_cal_affinity_matrix_is_differentiable(rpst):
     cg, sg = c.cuda().requires_grad_(), s.cuda().requires_grad_()
     (rpst.cal_affinity_matrix(cg, sg) * w.cuda()).sum().backward()
     assert R.rel_l2(cg.grad, cd.grad) < 1e-4 and R.rel_l2(sg.grad, sd.grad) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["aea", "relu"])
+@pytest.mark.parametrize("c,h,w", [(48, 15, 13), (64, 16, 24)])
+def test_adaptive_ragged_shapes_fused_and_unfused_row_pass(rpst, mode, c, h, w):
+    """AdaptiveSANet at L = 195 / 384 (partial row tiles, partial 64-wide K tiles): the affinity leaves its GEMM as packed
+    operand tiles (zero padding written by the epilogue) and softmax + clamp run as ONE row pass when the intermediate
+    maps are not kept; with `keep_claims` the two-pass form runs.  Both against the fp64 oracle (network/sanet.py:114-138)."""
+    torch.manual_seed(3)
+    L = h * w
+    m = rpst.AdaptiveSANet(c, L, ada_module=mode).cuda()
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ct, st = R.synth_features((2, c, h, w), cfg=4)
+    want, before, after, clamp = R.adaptive_sanet_forward(ct, st, params, mode, dtype=torch.float64)
+    with torch.no_grad():
+        m.keep_claims = False
+        fused = m(ct.cuda(), st.cuda())
+        m.keep_claims = True
+        kept = m(ct.cuda(), st.cuda())
+    assert R.rel_l2(fused, want) < 2e-3, R.rel_l2(fused, want)
+    assert R.rel_l2(kept, want) < 2e-3, R.rel_l2(kept, want)
+    assert R.rel_l2(fused, kept) < 1e-5            # same arithmetic up to the order of the two softmax passes
+    assert R.rel_l2(m.claim_before, before) < 1e-3
+    assert R.rel_l2(m.claim_value.reshape(-1), clamp.reshape(-1)) < 1e-3
