@@ -42,7 +42,7 @@ out["wct"] = {"shape": "2 x 256 x 512 x 512 (second call), fp32-grade",
               "covariance": agg(cov), "apply": agg(app), "whole_call_2_samples": {k: v for k, v in agg(call).items() if k != "launches"},
               "newton_schulz": {"launches": len(ns), "us": round(sum(l["us"] for l in ns), 1), "working_launches": len(live),
                                 "working_us": round(sum(l["us"] for l in live), 1),
-                                "note": "fp64 products (mma.sync.m8n8k4.f64 for even orders; not counted by the tensor-pipe metric of the tcgen05 kernels); launches past a matrix's step count return at once"},
+                                "note": "fp64 tensor-core products (mma.sync.m8n8k4.f64; the tensor-pipe metric counts them: ~67 % in a working launch); launches past a matrix's step count return at once"},
               "kernel_only_tensor_pipe_pct": {"cov_tma_kernel": cov[0]["tensor_pipe_pct"], "pw_conv_kernel": wl[pw]["tensor_pipe_pct"]},
               "note": "round 1: covariance GEMM alone 70.8 %, with its pack pass 33 % (176 us).  Round 2: one cooperative launch per "
                       "covariance (shift, TMA-staged SYRK, grid barriers, fp64 finalize); its SYRK phase alone (the kernel before the "
