@@ -736,7 +736,19 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
         RPST_CUDA(cudaFuncSetAttribute(cov_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CovTmaCfg<2>::smem));
         configured = true;
     }
-    EncodeTiledFn encode = g_wct_cov_tma && hw < (1ll << 31) - 64 ? encode_tiled_fn() : nullptr;
+    // the one-launch kernel needs a cooperative launch with every CTA resident (grid barriers): one CTA per SM; a device
+    // (or MIG slice / MPS share) that cannot grant that takes the register-staged kernel + separate finalize launches
+    static int coop_ok[64] = {};     // 0 unknown, 1 yes, -1 no
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (coop_ok[dev] == 0) {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cov_tma_kernel<2>, kCovTmaThreads, CovTmaCfg<2>::smem) != cudaSuccess)
+            per_sm = 0;
+        coop_ok[dev] = (coop && per_sm >= 1) ? 1 : -1;
+    }
+    EncodeTiledFn encode = g_wct_cov_tma && coop_ok[dev] == 1 && hw < (1ll << 31) - 64 ? encode_tiled_fn() : nullptr;
     if (encode) {
         // x as a 2-D tensor [c rows, hw positions]; boxes of 128 rows x 64 positions (256-byte row pieces)
         CUtensorMap tmap;
