@@ -110,25 +110,27 @@ __device__ __forceinline__ PwItem pw_item(const PwParams& p, int item) {
 // converters (three buffers of 8 float4 per thread) were bound by global-load latency: ncu long_scoreboard 45 %,
 // 3.1 TB/s over read + write.  Shared memory then holds ONE A stage (converting a k-block takes a quarter of its MMA
 // time, and convert + MMA in series still fit under the k-block's HBM time), the B ring and the x ring: 224 KiB.
+constexpr int XTMA_NX = 2;   // x boxes in flight: 2 with one A stage (134 us for the WCT colouring); 1 with two A stages measured 150 us
 template <int PARTS, bool VEC, int EPI, bool XTMA>
 __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_constant__ CUtensorMap xmap, PwParams p) {
     // stage: A hi [128 pos x 64 ch] 16 KiB (+ lo 16 KiB), B hi [256 out x 64 ch] 32 KiB (+ lo 32 KiB)
     constexpr uint32_t kA = kTileBytes, kB = 2 * kTileBytes;
     constexpr uint32_t kStage = PARTS * (kA + kB);
     constexpr int NST = PARTS == 2 ? 2 : 4;
-    constexpr int NX = 2;
+    constexpr int NX = XTMA_NX;
+    constexpr int NA = XTMA ? 3 - NX : 1;                       // A stages on the XTMA layout: 224 KiB either way
     constexpr uint32_t kXBox = 64 * 128 * sizeof(float);        // 32 KiB
     static_assert(!XTMA || (VEC && EPI != 2), "XTMA: vector path, no epilogue statistics (their static arrays need the room)");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    // XTMA layout: [A (PARTS * kA)][B stage 0 .. NST-1 (PARTS * kB each)][x box 0 .. NX-1]
-    unsigned char* const xring = smem + PARTS * kA + (size_t)NST * PARTS * kB;
-    auto a_stage = [&](int s) -> unsigned char* { return XTMA ? smem : smem + (size_t)s * kStage; };
+    // XTMA layout: [A stage 0 .. NA-1 (PARTS * kA each)][B stage 0 .. NST-1 (PARTS * kB each)][x box 0 .. NX-1]
+    unsigned char* const xring = smem + (size_t)NA * PARTS * kA + (size_t)NST * PARTS * kB;
+    auto a_stage = [&](int s) -> unsigned char* { return XTMA ? smem + (size_t)s * PARTS * kA : smem + (size_t)s * kStage; };
     auto b_stage = [&](int s) -> unsigned char* {
-        return XTMA ? smem + PARTS * kA + (size_t)s * PARTS * kB : smem + (size_t)s * kStage + PARTS * kA;
+        return XTMA ? smem + (size_t)NA * PARTS * kA + (size_t)s * PARTS * kB : smem + (size_t)s * kStage + PARTS * kA;
     };
     __shared__ uint64_t full_a[NST], full_b[NST], empty[NST], acc_full[2], acc_empty[2];
-    __shared__ uint64_t xfull[NX], xempty[NX], a_empty;
+    __shared__ uint64_t xfull[2], xempty[2], a_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float stat_tile[EPI == 2 ? 4 * 32 * 33 : 1];
     __shared__ float stat_acc[EPI == 2 ? 4 * kPwMaxC * 2 : 1];   // running per-warp column sums of the current sample
@@ -145,11 +147,11 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_con
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], 4);
         }
-        for (int b = 0; b < NX; ++b) {
+        for (int b = 0; b < 2; ++b) {
             mbar_init(&xfull[b], 1);
             mbar_init(&xempty[b], kPwConvWarps);
+            mbar_init(&a_empty[b], 1);
         }
-        mbar_init(&a_empty, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_con
                     }
                     const int s = it % NST;
                     mbar_wait(&empty[s], ((it / NST) & 1u) ^ 1u);
-                    unsigned char* st = b_stage(s) - PARTS * kA;
+                    unsigned char* st = b_stage(s) - PARTS * kA;   // the loads below add PARTS * kA back
                     mbar_arrive_expect_tx(&full_b[s], (uint32_t)(PARTS * n_sub) * kTileBytes);
                     for (int part = 0; part < PARTS; ++part)
                         for (int sub = 0; sub < n_sub; ++sub)
@@ -198,11 +200,12 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_con
                 const uint32_t d = tmem_base + (uint32_t)(buf * 256);
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const int s = it % NST;
-                    if (XTMA) mbar_wait(&full_a[0], it & 1u);
+                    const int as = XTMA ? (int)(it % NA) : s;
+                    if (XTMA) mbar_wait(&full_a[as], (it / NA) & 1u);
                     else mbar_wait(&full_a[s], (it / NST) & 1u);
                     mbar_wait(&full_b[s], (it / NST) & 1u);
                     tcgen05_fence_after();
-                    const uint32_t a_hi = smem_u32(a_stage(s)), a_lo = a_hi + kA;
+                    const uint32_t a_hi = smem_u32(a_stage(as)), a_lo = a_hi + kA;
                     const uint32_t b_hi = smem_u32(b_stage(s)), b_lo = b_hi + kB;
 #pragma unroll
                     for (int k = 0; k < kTileK / kUmmaK; ++k) {
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_con
                         }
                     }
                     umma_commit(&empty[s]);
-                    if (XTMA) umma_commit(&a_empty);                 // the single A stage may be rewritten
+                    if (XTMA) umma_commit(&a_empty[as]);             // this A stage may be rewritten
                     if (kb == p.kb - 1) umma_commit(&acc_full[buf]);
                 }
             }
@@ -366,8 +369,9 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_con
                         sb[j] = p.sub ? __ldg(p.sub + sidx + j) : 0.f;
                         ml[j] = p.mul ? __ldg(p.mul + sidx + j) : 1.f;
                     }
-                    mbar_wait(&a_empty, (u & 1u) ^ 1u);                  // the MMAs of the previous k-block have read A
-                    unsigned char* a_hi = smem + (size_t)cw * kPwSBO + lane_off;
+                    const uint32_t as = u % NA;
+                    mbar_wait(&a_empty[as], ((u / NA) & 1u) ^ 1u);       // the MMAs that read this A stage last have completed
+                    unsigned char* a_hi = a_stage((int)as) + (size_t)cw * kPwSBO + lane_off;
                     unsigned char* a_lo = a_hi + kA;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_conv_kernel(const __grid_con
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_a[0]);
+                    if (lane == 0) mbar_arrive(&full_a[as]);
                 }
             }
         } else {
