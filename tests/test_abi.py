@@ -113,8 +113,9 @@ def test_product_path_has_no_cpu_fallback():
 
 def test_library_is_sm_100a_with_tcgen05_and_tma_sass():
     """The shipped library is built for sm_100a only and its SASS carries the Blackwell instructions the design
-    claims: tcgen05.mma (UTCHMMA), tcgen05.ld (LDTM), tcgen05.commit (UTCBAR), cp.async.bulk / TMA (UBLKCP)
-    and mbarriers (SYNCS) — B200_PROFILING.md's mnemonics."""
+    claims: tcgen05.mma (UTCHMMA), tcgen05.ld (LDTM), tcgen05.commit (UTCBAR), cp.async.bulk / TMA (UBLKCP),
+    tensor-map TMA (UTMALDG: covariance and pointwise-convolution input boxes), fp64 tensor-core MMAs (DMMA:
+    Newton-Schulz roots), 256-bit global stores and mbarriers (SYNCS) — B200_PROFILING.md's mnemonics."""
     import shutil
     import rpst
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
@@ -124,5 +125,5 @@ def test_library_is_sm_100a_with_tcgen05_and_tma_sass():
     archs = set(re.findall(r"\.(sm_\w+)\.cubin", elf))
     assert archs == {"sm_100a"}, archs
     sass = subprocess.run([cuobjdump, "-sass", rpst._lib.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS"):
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG.2D", "DMMA", "STG.E.ENL2.256", "SYNCS"):
         assert mnemonic in sass, mnemonic
