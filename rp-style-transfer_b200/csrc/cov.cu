@@ -748,7 +748,9 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
             per_sm = 0;
         coop_ok[dev] = (coop && per_sm >= 1) ? 1 : -1;
     }
-    EncodeTiledFn encode = g_wct_cov_tma && coop_ok[dev] == 1 && hw < (1ll << 31) - 64 ? encode_tiled_fn() : nullptr;
+    // small planes (fewer k-tiles than ~half the SMs): the in-kernel finalize would run on a handful of CTAs (a 64-position
+    // plane: ONE CTA walking 128 rows, 0.3 ms); they keep the separate, fully parallel finalize launches
+    EncodeTiledFn encode = g_wct_cov_tma && coop_ok[dev] == 1 && grid >= 64 && hw < (1ll << 31) - 64 ? encode_tiled_fn() : nullptr;
     if (encode) {
         // x as a 2-D tensor [c rows, hw positions]; boxes of 128 rows x 64 positions (256-byte row pieces)
         CUtensorMap tmap;

@@ -349,7 +349,7 @@ NsLayout ns_layout(int64_t batch, int n) {
     l.scale = take((size_t)batch * sizeof(double));
     l.nit = take((size_t)batch * sizeof(int));
     l.capped = take((size_t)batch * sizeof(int));
-    l.tiles = ((n + kGM - 1) / kGM) * ((n + kGN - 1) / kGN);
+    l.tiles = ((n + 63) / 64) * ((n + kGN - 1) / kGN);            // room for the 64-row tiling of small batches
     l.partial = take((size_t)batch * l.tiles * sizeof(double));
     l.norm = take((size_t)batch * kNormParts * sizeof(double));
     l.total = o;
@@ -370,8 +370,11 @@ __device__ __forceinline__ void dmma_884(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int MODE>
+// BM = 128: warps 4 x 2, 32 x 32 per warp; BM = 64 (small batches: twice the CTAs): warps 2 x 4, 32 x 16 per warp.
+template <int MODE, int BM>
 __global__ void __launch_bounds__(kGThreads, 2) ns_gemm_dmma_kernel(GemmArgs g) {
+    constexpr int WM = BM / 32, WN = 8 / WM, WNC = kGN / WN, NT = WNC / 8;     // warp grid, warp columns, n tiles per warp
+    constexpr int kStageD = BM * kDA + kGK * kDB;
     extern __shared__ __align__(16) unsigned char dmma_smem[];
     double* tile_smem = reinterpret_cast<double*>(dmma_smem);
     const int job = (int)blockIdx.z / g.batch, smp = (int)blockIdx.z % g.batch;
@@ -398,22 +401,22 @@ __global__ void __launch_bounds__(kGThreads, 2) ns_gemm_dmma_kernel(GemmArgs g) 
     } else {
         A = g.z[par] + off; B = g.y[par] + off;
     }
-    const int i0 = blockIdx.y * kGM, j0 = blockIdx.x * kGN;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * kGN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp % WM, wn = warp / WM;
     const int gid = lane >> 2, tig = lane & 3;
 
-    double acc[4][4][2];
+    double acc[4][NT][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     auto issue = [&](int k0, int stage) {
-        double* as = tile_smem + stage * kDStage;
-        double* bs = as + kGM * kDA;
+        double* as = tile_smem + stage * kStageD;
+        double* bs = as + BM * kDA;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < BM / 32; ++q) {
             const int ch = threadIdx.x + q * kGThreads, m = ch >> 3, k = (ch & 7) * 2;
             const bool ok = i0 + m < n && k0 + k < n;
             cp_async_16(as + m * kDA + k, ok ? A + (size_t)(i0 + m) * n + k0 + k : A, ok ? 16 : 0);
@@ -432,19 +435,19 @@ __global__ void __launch_bounds__(kGThreads, 2) ns_gemm_dmma_kernel(GemmArgs g) 
         if (kt + 1 < nk) { issue((kt + 1) * kGK, (kt + 1) & 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncthreads();
-        const double* as = tile_smem + (kt & 1) * kDStage + (32 * wm + gid) * kDA + tig;
-        const double* bs = tile_smem + (kt & 1) * kDStage + kGM * kDA + tig * kDB + 32 * wn + gid;
+        const double* as = tile_smem + (kt & 1) * kStageD + (32 * wm + gid) * kDA + tig;
+        const double* bs = tile_smem + (kt & 1) * kStageD + BM * kDA + tig * kDB + WNC * wn + gid;
 #pragma unroll
         for (int kk = 0; kk < kGK; kk += 4) {
-            double a[4], b[4];
+            double a[4], b[NT];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = as[(8 * i) * kDA + kk];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = bs[kk * kDB + 8 * j];
+            for (int j = 0; j < NT; ++j) b[j] = bs[kk * kDB + 8 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_884(acc[i][j], a[i], b[j]);
+                for (int j = 0; j < NT; ++j) dmma_884(acc[i][j], a[i], b[j]);
         }
         __syncthreads();
     }
@@ -458,8 +461,8 @@ __global__ void __launch_bounds__(kGThreads, 2) ns_gemm_dmma_kernel(GemmArgs g) 
         const int r = i0 + 32 * wm + 8 * i + gid;
         if (r >= n) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = j0 + 32 * wn + 8 * j + 2 * tig;
+        for (int j = 0; j < NT; ++j) {
+            const int c = j0 + WNC * wn + 8 * j + 2 * tig;
             const double v0 = acc[i][j][0] * mul + (r == c ? diag : 0.0);
             const double v1 = acc[i][j][1] * mul + (r == c + 1 ? diag : 0.0);
             if (MODE == kCheck) {
@@ -477,6 +480,13 @@ __global__ void __launch_bounds__(kGThreads, 2) ns_gemm_dmma_kernel(GemmArgs g) 
     }
 }
 
+// rows per CTA tile of the tensor-core GEMM: 64 when the 128-row tiling would leave a third of the SMs without a CTA
+int gemm_tile_rows(int n, int batch) {
+    if ((n & 1) || !g_ns_dmma) return kGM;
+    const int64_t ctas = (int64_t)((n + kGM - 1) / kGM) * ((n + kGN - 1) / kGN) * batch;
+    return ctas < 2 * sm_count() / 3 ? 64 : kGM;
+}
+
 int launch_gemm(GemmArgs g, cudaStream_t st) {
     dim3 grid((unsigned)((g.n + kGN - 1) / kGN), (unsigned)((g.n + kGM - 1) / kGM), (unsigned)(g.jobs * g.batch));
     const bool even = (g.n & 1) == 0;
@@ -484,17 +494,28 @@ int launch_gemm(GemmArgs g, cudaStream_t st) {
         static PerDeviceFlag configured_on;
         bool& configured = configured_on.get();
         if (!configured) {
-            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
-            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kStepT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
-            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kStepYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
-            RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<kCheck>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
+#define RPST_NS_ATTR(M, B) RPST_CUDA(cudaFuncSetAttribute(ns_gemm_dmma_kernel<M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem))
+            RPST_NS_ATTR(kPlain, 128); RPST_NS_ATTR(kStepT, 128); RPST_NS_ATTR(kStepYZ, 128); RPST_NS_ATTR(kCheck, 128);
+            RPST_NS_ATTR(kPlain, 64); RPST_NS_ATTR(kStepT, 64); RPST_NS_ATTR(kStepYZ, 64); RPST_NS_ATTR(kCheck, 64);
+#undef RPST_NS_ATTR
             configured = true;
         }
-        switch (g.mode) {
-            case kPlain: ns_gemm_dmma_kernel<kPlain><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
-            case kStepT: ns_gemm_dmma_kernel<kStepT><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
-            case kStepYZ: ns_gemm_dmma_kernel<kStepYZ><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
-            default: ns_gemm_dmma_kernel<kCheck><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+        // small batches: 64-row tiles double the CTA count (one 256^2 matrix: 16 / 32 CTAs per product instead of 8 / 16)
+        if (gemm_tile_rows(g.n, g.batch) == 64) {
+            dim3 grid64(grid.x, (unsigned)((g.n + 63) / 64), grid.z);
+            switch (g.mode) {
+                case kPlain: ns_gemm_dmma_kernel<kPlain, 64><<<grid64, kGThreads, kDmmaSmem, st>>>(g); break;
+                case kStepT: ns_gemm_dmma_kernel<kStepT, 64><<<grid64, kGThreads, kDmmaSmem, st>>>(g); break;
+                case kStepYZ: ns_gemm_dmma_kernel<kStepYZ, 64><<<grid64, kGThreads, kDmmaSmem, st>>>(g); break;
+                default: ns_gemm_dmma_kernel<kCheck, 64><<<grid64, kGThreads, kDmmaSmem, st>>>(g); break;
+            }
+        } else {
+            switch (g.mode) {
+                case kPlain: ns_gemm_dmma_kernel<kPlain, 128><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+                case kStepT: ns_gemm_dmma_kernel<kStepT, 128><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+                case kStepYZ: ns_gemm_dmma_kernel<kStepYZ, 128><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+                default: ns_gemm_dmma_kernel<kCheck, 128><<<grid, kGThreads, kDmmaSmem, st>>>(g); break;
+            }
         }
         RPST_CUDA(cudaGetLastError());
         return RPST_OK;
@@ -586,7 +607,8 @@ int ns_roots(const double* a, int64_t batch, int n, double diag_add, double lmin
     }
     g.jobs = 1; g.mode = kCheck;
     if ((rc = launch_gemm(g, st))) return rc;
-    ns_finish_kernel<<<dim3(eb, (unsigned)batch), 256, 0, st>>>(y[0], y[1], z[0], z[1], n, scale, nit, capped, partial, l.tiles,
+    const int tiles_used = ((n + gemm_tile_rows(n, (int)batch) - 1) / gemm_tile_rows(n, (int)batch)) * ((n + kGN - 1) / kGN);
+    ns_finish_kernel<<<dim3(eb, (unsigned)batch), 256, 0, st>>>(y[0], y[1], z[0], z[1], n, scale, nit, capped, partial, tiles_used,
                                                                 1e-14, g_wct_roots_ns == 2, root, iroot, flag);
     RPST_CUDA(cudaGetLastError());
     return RPST_OK;
