@@ -1,3 +1,4 @@
+// fp64 pipe microbenchmark: mma.sync.m8n8k4.f64 (DMMA) vs DFMA peak.  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/fp64_rate tools/micro/fp64_rate.cu
 #include <cstdio>
 __global__ void k(double* out, int iters) {
     double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
