@@ -183,6 +183,27 @@ def config4(dev, peaks, cpu=True, batch=16):
         del m, c, s
     except Exception as e:
         out["module_L16384"] = {"error": repr(e)[:200]}
+    # the adaptive variant of the same config (network/sanet.py:100-138, 'aea' clamp), one sample at relu4_1, and the MRF
+    # match + loss of network/mrf_rp.py at relu4_1 of a 512^2 image (top-k selected in the NCC GEMM epilogue)
+    try:
+        torch.manual_seed(0)
+        ma = rpst.AdaptiveSANet(512, 16384, ada_module="aea").to(dev)
+        ma.keep_claims = False
+        c, s = R.synth_features((1, 512, 128, 128), cfg=4, device=dev)
+        with torch.no_grad():
+            ms_ada = dev_time_ms(lambda: ma(c, s), 3, 1)
+        L = 16384
+        out["adaptive_module_L16384"] = {"ms_per_sample": ms_ada, "algorithmic_TFLOPs": (2.0 * L * L * 512 * 3 + 2.0 * L * L * (L // 16)) / ms_ada / 1e9,
+                                         "note": "affinity + f_psi Linear(L -> L/16) + logits + P.V, all fp32-grade (bf16x3)"}
+        del ma, c, s
+        torch.cuda.empty_cache()
+        c, s = R.synth_features((1, 512, 64, 64), cfg=6, device=dev)
+        with torch.no_grad():
+            ms_mrf = dev_time_ms(lambda: rpst.mrf_match(c, s, 5, want_loss=True), 5, 2)
+        out["mrf_match_loss_L4096_k5"] = {"ms": ms_mrf, "note": "C=512; NCC and NCC^T products never stored, indices bit-exact"}
+        del c, s
+    except Exception as e:
+        out["adaptive_module_L16384"] = {"error": repr(e)[:200]}
     out["l2"] = "operands of one call: 3 x 512 MiB (L=16384) / 3 x 128 MiB (L=4096), beyond L2"
     torch.cuda.empty_cache()
     if cpu:
