@@ -604,11 +604,12 @@ int pw_conv(const PwArgs& a, cudaStream_t st) {
 // (A dedicated copy of this kernel without the general epilogue measured 1.80 vs 1.83 ms per sample end to end: dropped.)
 bool wct_apply_fused_supported(int64_t c, int64_t hw) { return c >= 1 && c <= kPwMaxC && hw >= 1; }
 
+// n samples in one persistent launch: x / out [n,c,hw], mu_* [n,c], packed transforms t_batch_bytes apart
 int wct_apply_fused(const float* x, const float* mu_c, const float* mu_s, const void* t_hi, const void* t_lo, float* out,
-                    int64_t c, int64_t hw, int passes, cudaStream_t st) {
+                    int64_t n, int64_t t_batch_bytes, int64_t c, int64_t hw, int passes, cudaStream_t st) {
     PwArgs a{};
-    a.x = x; a.sub = mu_c; a.w_hi = t_hi; a.w_lo = t_lo; a.bias = mu_s; a.out = out;
-    a.b = 1; a.cin = c; a.cout = c; a.hw = hw; a.passes = passes;
+    a.x = x; a.sub = mu_c; a.w_hi = t_hi; a.w_lo = t_lo; a.w_batch = t_batch_bytes; a.bias = mu_s; a.bias_batch = c; a.out = out;
+    a.b = n; a.cin = c; a.cout = c; a.hw = hw; a.passes = passes;
     return pw_conv(a, st);
 }
 

@@ -44,9 +44,12 @@ int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add
 int cov_shifts_batched(const float* x, int64_t n, int64_t c, int64_t hw, float* shifts, cudaStream_t st);
 extern int64_t g_wct_fused_cov;
 // wct_apply.cu: out = T (x - mu_c) + mu_s with the transposed bf16 operand built on the fly
+int pack_operand_batched(const float* x, int64_t rows, int64_t k, int64_t stride_r, int64_t stride_k,
+                         const float* row_scale, const float* row_shift, void* hi, void* lo, int batch, int64_t x_batch,
+                         int64_t tile_batch_bytes, int64_t vec_batch, cudaStream_t stream);
 bool wct_apply_fused_supported(int64_t c, int64_t hw);
 int wct_apply_fused(const float* x, const float* mu_c, const float* mu_s, const void* t_hi, const void* t_lo, float* out,
-                    int64_t c, int64_t hw, int passes, cudaStream_t st);
+                    int64_t n, int64_t t_batch_bytes, int64_t c, int64_t hw, int passes, cudaStream_t st);
 extern int64_t g_wct_fused_apply;
 
 namespace {
@@ -66,6 +69,9 @@ __global__ void cov_reduce_kernel(const float* __restrict__ partial, int splits,
 __global__ void transform_finalize_kernel(const double* __restrict__ t, const float* __restrict__ mu_c,
                                           const float* __restrict__ mu_s, int c, float* __restrict__ t32,
                                           float* __restrict__ bias) {
+    // blockIdx.y: sample (T [n,c,c], mu_* [n,c], t32 [n,c,c], bias [n,c])
+    t += (size_t)blockIdx.y * c * c; mu_c += (size_t)blockIdx.y * c; mu_s += (size_t)blockIdx.y * c;
+    t32 += (size_t)blockIdx.y * c * c; bias += (size_t)blockIdx.y * c;
     const int i = blockIdx.x;
     double acc = 0.0;
     for (int j = threadIdx.x; j < c; j += blockDim.x) {
@@ -87,7 +93,7 @@ __global__ void transform_finalize_kernel(const double* __restrict__ t, const fl
 
 struct WctLayout {
     size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, flag, ns, eig, mats[6], t32, bias,
-        t_hi, t_lo, x_hi, x_lo, fused, shifts, total;
+        t_hi, t_lo, x_hi, x_lo, fused, shifts, t_tile, total;
     int splits;
 };
 
@@ -120,10 +126,11 @@ WctLayout wct_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     l.ns = take(ns_roots_workspace_bytes(n, (int)c));
     l.eig = take(eig_workspace_bytes(n, (int)c));
     for (int i = 0; i < 6; ++i) l.mats[i] = take((size_t)n * c * c * sizeof(double));
-    l.t32 = take((size_t)c * c * sizeof(float));
-    l.bias = take((size_t)c * sizeof(float));
-    l.t_hi = take(packed_operand_bytes(c, c));
-    l.t_lo = take(packed_operand_bytes(c, c));
+    l.t_tile = align_up(packed_operand_bytes(c, c), 256);          // per-sample stride of the packed transforms
+    l.t32 = take((size_t)n * c * c * sizeof(float));
+    l.bias = take((size_t)n * c * sizeof(float));
+    l.t_hi = take((size_t)n * l.t_tile);
+    l.t_lo = take((size_t)n * l.t_tile);
     l.x_hi = take(packed_operand_bytes(hw_c, c));
     l.x_lo = take(packed_operand_bytes(hw_c, c));
     l.fused = take(c <= 256 ? cov_fused_workspace_bytes(c) : 0);
@@ -249,22 +256,20 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
     // 4. apply: out_i = T_i X_i + (mu_s - T_i mu_c)
     float* t32 = reinterpret_cast<float*>(w + l.t32);
     float* bias = reinterpret_cast<float*>(w + l.bias);
+    // all samples at once: fp32 transforms + biases, packed transforms, and (fused path) ONE persistent colouring launch
+    // over the batch with per-sample weights (16 launches of each kind before: their tails added up to ~15 us per sample)
+    transform_finalize_kernel<<<dim3((unsigned)c, (unsigned)n), 128, 0, st>>>(T, mean_c, mean_s, (int)c, t32, bias);
+    RPST_CUDA(cudaGetLastError());
+    rc = pack_operand_batched(t32, c, c, c, 1, nullptr, nullptr, w + l.t_hi, w + l.t_lo, (int)n, c * c, (int64_t)l.t_tile, 0, st);
+    if (rc) return rc;
+    if (g_wct_fused_apply && wct_apply_fused_supported(c, hw_c))
+        return wct_apply_fused(content, mean_c, mean_s, w + l.t_hi, w + l.t_lo, out, n, (int64_t)l.t_tile, c, hw_c, passes, st);
     for (int64_t i = 0; i < n; ++i) {
-        transform_finalize_kernel<<<(unsigned)c, 128, 0, st>>>(T + i * c * c, mean_c + i * c, mean_s + i * c, (int)c, t32, bias);
-        RPST_CUDA(cudaGetLastError());
-        rc = pack_operand_shift(t32, c, c, c, 1, nullptr, nullptr, w + l.t_hi, w + l.t_lo, st);
-        if (rc) return rc;
-        if (g_wct_fused_apply && wct_apply_fused_supported(c, hw_c)) {
-            rc = wct_apply_fused(content + i * c * hw_c, mean_c + i * c, mean_s + i * c, w + l.t_hi, w + l.t_lo,
-                                 out + i * c * hw_c, c, hw_c, passes, st);
-            if (rc) return rc;
-            continue;
-        }
         rc = pack_operand_shift(content + i * c * hw_c, hw_c, c, 1, hw_c, nullptr, nullptr, w + l.x_hi,
                                 passes == 3 ? w + l.x_lo : nullptr, st);
         if (rc) return rc;
-        rc = gemm_packed_splitk(w + l.t_hi, w + l.t_lo, w + l.x_hi, w + l.x_lo, out + i * c * hw_c, c, hw_c, c, hw_c,
-                                passes, 1.f, bias, nullptr, 1, 0, st);
+        rc = gemm_packed_splitk(w + l.t_hi + i * l.t_tile, w + l.t_lo + i * l.t_tile, w + l.x_hi, w + l.x_lo, out + i * c * hw_c, c, hw_c,
+                                c, hw_c, passes, 1.f, bias + i * c, nullptr, 1, 0, st);
         if (rc) return rc;
     }
     return RPST_OK;
