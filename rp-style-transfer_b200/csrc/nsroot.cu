@@ -582,9 +582,10 @@ int ns_roots(const double* a, int64_t batch, int n, double diag_add, double lmin
     int* capped = reinterpret_cast<int*>(w + l.capped);
     double* partial = reinterpret_cast<double*>(w + l.partial);
     double* norm = reinterpret_cast<double*>(w + l.norm);
-    // step cap from the eigenvalue bound: l_0 = sqrt(lmin / 4 ||A||_F) reaches 1 - 1e-7 within 14 scaled steps for
-    // ||A||_F / lmin <= 1e6 and within 22 for <= 1e13; beyond the cap the matrix is flagged
-    const int maxit = lmin >= 0.5 ? 16 : kNsMaxIt;
+    // Step cap = number of launches (launches past a matrix's own count return at once, ~2 us each).  With l_0 =
+    // sqrt(lmin / 4 ||A||_F): lmin >= 0.5 (content side) needs 9 steps at ||A||_F = 2.5e3 and 12 at 1e6; lmin = 1e-4 needs
+    // 15 steps at ||A||_F = 1e4 and 19 at 2.5e7.  A matrix beyond the cap is flagged and goes to the Jacobi solver.
+    const int maxit = lmin >= 0.5 ? 12 : 20;
     ns_norm_kernel<<<dim3(kNormParts, (unsigned)batch), kGThreads, 0, st>>>(a, n, diag_add, norm);
     RPST_CUDA(cudaGetLastError());
     ns_plan_kernel<<<(unsigned)((batch + 63) / 64), 64, 0, st>>>(norm, (int)batch, lmin, maxit, scale, alpha, nit, capped);
