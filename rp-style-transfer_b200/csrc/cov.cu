@@ -713,7 +713,7 @@ int cov_shifts_batched(const float* x, int64_t n, int64_t c, int64_t hw, float* 
 }
 
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
-              cudaStream_t st, const float* shift_in) {
+              cudaStream_t st, const float* shift_in, int* barrier_zeroed) {
     const int cp = c <= 128 ? 128 : 256;
     const int g = sm_count();
     char* w = static_cast<char*>(workspace);

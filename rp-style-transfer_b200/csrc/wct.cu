@@ -40,7 +40,7 @@ constexpr double kWctEigTol = 1e-5;
 bool cov_fused_supported(const float* x, int64_t c, int64_t hw);
 size_t cov_fused_workspace_bytes(int64_t c);
 int cov_fused(const float* x, int64_t c, int64_t hw, int passes, double diag_add, double* cov, float* mean, void* workspace,
-              cudaStream_t st, const float* shift_in);
+              cudaStream_t st, const float* shift_in, int* barrier_zeroed);
 int cov_shifts_batched(const float* x, int64_t n, int64_t c, int64_t hw, float* shifts, cudaStream_t st);
 extern int64_t g_wct_fused_cov;
 // wct_apply.cu: out = T (x - mu_c) + mu_s with the transposed bf16 operand built on the fly
@@ -93,7 +93,7 @@ __global__ void transform_finalize_kernel(const double* __restrict__ t, const fl
 
 struct WctLayout {
     size_t stats, mean_c, mean_s, cov_tiles_hi, cov_tiles_lo, partial, cov_c, cov_s, flag, ns, eig, mats[6], t32, bias,
-        t_hi, t_lo, x_hi, x_lo, fused, shifts, t_tile, total;
+        t_hi, t_lo, x_hi, x_lo, fused, shifts, barriers, t_tile, total;
     int splits;
 };
 
@@ -135,6 +135,7 @@ WctLayout wct_layout(int64_t n, int64_t c, int64_t hw_c, int64_t hw_s) {
     l.x_lo = take(packed_operand_bytes(hw_c, c));
     l.fused = take(c <= 256 ? cov_fused_workspace_bytes(c) : 0);
     l.shifts = take((size_t)2 * n * 256 * sizeof(float));
+    l.barriers = take((size_t)2 * n * 4 * sizeof(int));
     l.total = o;
     return l;
 }
@@ -182,11 +183,13 @@ extern "C" int rpst_wct_fuse(const float* content, const float* style, float* ou
         if ((rc = cov_shifts_batched(content, n, c, hw_c, sh_c, st))) return rc;
         if ((rc = cov_shifts_batched(style, n, c, hw_s, sh_s, st))) return rc;
         const int cp = c <= 128 ? 128 : 256;
+        int* bars = reinterpret_cast<int*>(w + l.barriers);          // 4 ints per covariance launch, zeroed once for the batch
+        RPST_CUDA(cudaMemsetAsync(bars, 0, (size_t)2 * n * 4 * sizeof(int), st));
         for (int64_t i = 0; i < n; ++i) {
             if ((rc = cov_fused(content + i * c * hw_c, c, hw_c, passes, 1.0, cov_c + i * c * c, mean_c + i * c, w + l.fused, st,
-                                sh_c + i * cp))) return rc;
+                                sh_c + i * cp, bars + 8 * i))) return rc;
             if ((rc = cov_fused(style + i * c * hw_s, c, hw_s, passes, 0.0, cov_s + i * c * c, mean_s + i * c, w + l.fused, st,
-                                sh_s + i * cp))) return rc;
+                                sh_s + i * cp, bars + 8 * i + 4))) return rc;
         }
     } else {
     // 1. channel means (network/wct_rp.py:85,92)
