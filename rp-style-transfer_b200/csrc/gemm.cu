@@ -494,9 +494,18 @@ int gemm_packed_splitk(const void* a_hi, const void* a_lo, const void* b_hi, con
                        int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                        const float* col_add, int splits, int64_t split_stride, cudaStream_t stream);
 
-// set by gemm_packed_topk around its call of gemm_packed_batched (same thread): selects the TOPK epilogue
-static thread_local struct { int k; float* val; int* idx; } g_topk_request = {0, nullptr, nullptr};
-static thread_local struct { char* hi; char* lo; } g_packed_request = {nullptr, nullptr};
+// which epilogue a launch takes besides the plain fp32 store
+struct GemmEpilogue {
+    int topk = 0;            // > 0: top-k selection into cand_val / cand_idx
+    float* cand_val = nullptr;
+    int* cand_idx = nullptr;
+    char* pk_hi = nullptr;   // non-null: packed bf16 operand tiles
+    char* pk_lo = nullptr;
+};
+static int gemm_packed_launch(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                              int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                              const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
+                              int64_t b_batch_bytes, int64_t out_batch, const GemmEpilogue& epi, cudaStream_t stream);
 
 int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
                         int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
@@ -524,6 +533,14 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
                         int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
                         const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
                         int64_t b_batch_bytes, int64_t out_batch, cudaStream_t stream) {
+    return gemm_packed_launch(a_hi, a_lo, b_hi, b_lo, out, m, n, k, ldo, passes, alpha, row_add, col_add, splits, split_stride, batch,
+                              a_batch_bytes, b_batch_bytes, out_batch, GemmEpilogue{}, stream);
+}
+
+static int gemm_packed_launch(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, float* out, int64_t m,
+                              int64_t n, int64_t k, int64_t ldo, int passes, float alpha, const float* row_add,
+                              const float* col_add, int splits, int64_t split_stride, int batch, int64_t a_batch_bytes,
+                              int64_t b_batch_bytes, int64_t out_batch, const GemmEpilogue& epi, cudaStream_t stream) {
     RPST_CHECK_ARG(passes == 1 || passes == 3, "gemm_packed: passes must be 1 or 3");
     RPST_CHECK_ARG(batch >= 1, "gemm_packed: bad batch");
     RPST_CHECK_ARG(passes == 1 || (a_lo && b_lo), "gemm_packed: bf16x3 needs the lo operands");
@@ -564,12 +581,12 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
     int64_t grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;
     const bool wide = p.k_per_split <= 16;
-    if (g_topk_request.k > 0) {
-        p.topk = g_topk_request.k; p.cand_val = g_topk_request.val; p.cand_idx = g_topk_request.idx;
+    if (epi.topk > 0) {
+        p.topk = epi.topk; p.cand_val = epi.cand_val; p.cand_idx = epi.cand_idx;
         if (p.topk <= 4) gemm_packed_kernel<4, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
         else gemm_packed_kernel<8, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
-    } else if (g_packed_request.hi) {
-        p.pk_hi = g_packed_request.hi; p.pk_lo = g_packed_request.lo; p.pk_ktiles = (int)((n + kTileK - 1) / kTileK);
+    } else if (epi.pk_hi) {
+        p.pk_hi = epi.pk_hi; p.pk_lo = epi.pk_lo; p.pk_ktiles = (int)((n + kTileK - 1) / kTileK);
         if (wide) gemm_packed_kernel<-1, true><<<(unsigned)grid, kGemmTopkThreads, smem, stream>>>(p);
         else gemm_packed_kernel<-1, false><<<(unsigned)grid, kGemmThreads, smem, stream>>>(p);
     } else {
@@ -586,11 +603,9 @@ int gemm_packed_batched(const void* a_hi, const void* a_lo, const void* b_hi, co
 int gemm_packed_to_tiles(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t m, int64_t n, int64_t k,
                          int passes, float alpha, void* out_hi, void* out_lo, cudaStream_t stream) {
     RPST_CHECK_ARG(out_hi != nullptr, "gemm_packed_to_tiles: null output");
-    g_packed_request.hi = static_cast<char*>(out_hi); g_packed_request.lo = static_cast<char*>(out_lo);
-    const int rc = gemm_packed_batched(a_hi, a_lo, b_hi, b_lo, nullptr, m, n, k, n, passes, alpha, nullptr, nullptr, 1, 0, 1, 0, 0,
-                                       0, stream);
-    g_packed_request.hi = nullptr; g_packed_request.lo = nullptr;
-    return rc;
+    GemmEpilogue epi;
+    epi.pk_hi = static_cast<char*>(out_hi); epi.pk_lo = static_cast<char*>(out_lo);
+    return gemm_packed_launch(a_hi, a_lo, b_hi, b_lo, nullptr, m, n, k, n, passes, alpha, nullptr, nullptr, 1, 0, 1, 0, 0, 0, epi, stream);
 }
 
 // lists of candidates per row that gemm_packed_topk emits for n columns
@@ -601,11 +616,9 @@ int gemm_topk_lists(int64_t n) { return (int)((n + kGemmBN - 1) / kGemmBN) * kTo
 int gemm_packed_topk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t m, int64_t n, int64_t k,
                      int passes, float alpha, int topk, float* cand_val, int* cand_idx, cudaStream_t stream) {
     RPST_CHECK_ARG(topk >= 1 && topk <= 8 && cand_val && cand_idx, "gemm_packed_topk: bad top-k request");
-    g_topk_request.k = topk; g_topk_request.val = cand_val; g_topk_request.idx = cand_idx;
-    const int rc = gemm_packed_batched(a_hi, a_lo, b_hi, b_lo, nullptr, m, n, k, n, passes, alpha, nullptr, nullptr, 1, 0, 1, 0, 0,
-                                       0, stream);
-    g_topk_request.k = 0;
-    return rc;
+    GemmEpilogue epi;
+    epi.topk = topk; epi.cand_val = cand_val; epi.cand_idx = cand_idx;
+    return gemm_packed_launch(a_hi, a_lo, b_hi, b_lo, nullptr, m, n, k, n, passes, alpha, nullptr, nullptr, 1, 0, 1, 0, 0, 0, epi, stream);
 }
 
 }  // namespace rpst
