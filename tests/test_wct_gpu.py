@@ -235,3 +235,24 @@ def test_newton_schulz_flags_indefinite_input_and_jacobi_takes_over(rpst):
     # whether rounding really pushed an eigenvalue below the bound depends on the data; either way the result agrees with
     # the eigensolver (asserted above); the flag logic itself is pinned by test_spd_roots_against_known_spectra
     assert flagged in (0, 1)
+
+
+def test_wct_is_deterministic_and_safe_on_two_streams(rpst):
+    """Every reduction in the WCT path has a fixed order (per-CTA partial Grams, column sums, Newton-Schulz products), so
+    repeated calls are bit-identical; the covariance is a cooperative launch with grid barriers — two streams issuing it
+    concurrently must serialise, not deadlock, and give the same bits."""
+    c, s = R.synth_features((2, 256, 128, 128), cfg=3, device="cuda")
+    ref = rpst.wct_fuse(c, s)
+    for _ in range(10):
+        assert torch.equal(rpst.wct_fuse(c, s), ref)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            for _ in range(5):
+                o = rpst.wct_fuse(c, s)
+            outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
