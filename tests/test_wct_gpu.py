@@ -256,3 +256,23 @@ def test_wct_is_deterministic_and_safe_on_two_streams(rpst):
             outs.append(o)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
+
+
+def test_wct_cuda_graph_capture_and_replay(rpst):
+    """The whole fuse (memsets, cooperative covariance launches with tensor maps in their parameters, Newton-Schulz launches
+    whose step counts live on the device, colouring) only enqueues work on the given stream: it captures into a CUDA graph
+    and replays bit-identically (CUDA graphs)."""
+    c, s = R.synth_features((2, 256, 128, 128), cfg=3, device="cuda")
+    ref = rpst.wct_fuse(c, s)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        rpst.wct_fuse(c, s)                      # warm-up outside the capture (kernel attributes, driver entry point)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = rpst.wct_fuse(c, s)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
